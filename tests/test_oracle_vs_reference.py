@@ -1,0 +1,38 @@
+"""Pin the oracle against the LIVE reference at the BASELINE.json config shapes.
+
+Runs only where /root/reference exists (the build container).  The slowest case (SVHN,
+batch 256) takes the reference ~20 s on 8 vCPUs.
+"""
+import numpy as np
+import pytest
+
+from . import cases as K
+from . import refload, runners
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not refload.available(), reason="reference not present")]
+
+# big-batch cases cost the reference minutes in fp64; fp32 only here.
+FAST = [c for c in K.CONFIG_CASES if c.name not in ("C5_tiny_b512",)]
+
+
+@pytest.mark.parametrize("c", FAST, ids=lambda c: c.name)
+def test_oracle_f32_vs_live_reference_at_config_shape(c):
+    params, io = K.make_params(c), K.make_io(c)
+    ref = runners.run_reference(c, params=params, io=io)
+    got = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+    errs = runners.compare(got, ref)
+    assert set(errs) == set(ref)
+    bad = {k: e for k, e in errs.items() if not e <= 5e-6}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("c", [K.GOLDEN_CASES[1], K.GOLDEN_CASES[6], K.GOLDEN_CASES[8], K.GOLDEN_CASES[10],
+                               K.GOLDEN_CASES[13], K.GOLDEN_CASES[15]], ids=lambda c: c.name)
+def test_oracle_f64_vs_reference_fp64_twin(c):
+    params, io = K.make_params(c), K.make_io(c)
+    ref = runners.run_reference(c, params=params, io=io, double=True)
+    got = runners.run_oracle(c, params=params, io=io, dtype=np.float64)
+    errs = runners.compare(got, ref)
+    bad = {k: e for k, e in errs.items() if not e <= 1e-12}
+    assert not bad, bad

@@ -1,0 +1,1077 @@
+// Implicit operator-split (ADI) diffusion layers, forward and adjoint, for sm_100a.
+//
+// Reference behaviour (what is computed): mnist_test.py:33-198, fashion_mnist.py:40-196,
+// SVHN.py:38-230, cifar10.py:53-211, cifar_2version.py:52-187.  How it is computed here is
+// unrelated to the reference's op stream:
+//
+//   * pde_adi_prepare   one small kernel turns the four coefficient maps into factorised
+//                       Thomas tables (r, 1/pivot, r/pivot, clamp mask) per sweep, ONCE per
+//                       call, shared by the whole batch (the reference refactorises every
+//                       line of every sample).
+//   * adi_fwd_kernel    one warp owns channel c of PB samples; a lane owns one line of the
+//                       plane and keeps it in registers through the Thomas recurrences; the
+//                       plane lives in a padded shared-memory tile that is only used to turn
+//                       rows into columns between sweeps.  All num_steps run on-chip: one HBM
+//                       read and one HBM write per cell.
+//   * adi_bwd_kernel    recomputes the forward trajectory, checkpointing the state at the
+//                       end of every step in an L2-resident scratch, then walks the sweeps
+//                       backwards: transposed-tridiagonal solve for the adjoint, lambda*(Lx)
+//                       accumulated per pixel into lane-private shared-memory maps, and the
+//                       sweep input rebuilt as x_in = (A + eps I) x_out.  When the rebuild
+//                       would amplify rounding noise (device-computed bound), the kernel
+//                       switches to exact per-sweep checkpoints instead.
+//   * adi_finish_kernel sums the per-warp gradient partials in double (deterministic).
+#include "common.cuh"
+
+namespace pde {
+namespace adi {
+
+constexpr int kHeaderBytes = 4096;
+constexpr float kAmpLimit = 256.0f;  // see DESIGN.md "reverse reconstruction"
+
+struct Header {
+    int mode_exact;
+    float amp_bound;
+    int pad[2];
+    float scale[PDE_MAX_SWEEPS];
+    float t[PDE_MAX_SWEEPS];
+    unsigned rmax_bits[PDE_MAX_SWEEPS];
+};
+static_assert(sizeof(Header) <= kHeaderBytes, "header too large");
+
+template <int N>
+struct Geo {
+    static_assert(N % 4 == 0 && N >= 8 && N <= 32, "plane edge must be a multiple of 4 in [8, 32]");
+    // row stride (words) == 4 (mod 8): 128-bit row accesses by 8 consecutive lanes hit 32
+    // distinct banks, and column accesses (lane == column) are conflict-free for any stride.
+    static constexpr int ST = (N % 8 == 4) ? N : N + 4;
+    static constexpr int WORDS = N * ST;
+    static constexpr int Q = N / 4;
+};
+
+__host__ __device__ inline int sweeps_per_step(const pde_adi_desc &d) { return d.lie ? 2 : 3; }
+// axis 0: lines along W (alpha); axis 1: lines along H (beta)
+__host__ __device__ inline int sweep_axis(int k_in_step) { return k_in_step == 1 ? 1 : 0; }
+
+__host__ __device__ inline size_t table_elems(const pde_adi_desc &d) {
+    return (size_t)d.steps * sweeps_per_step(d) * d.C * d.N * d.N;
+}
+
+struct Tables {
+    const Header *hdr;
+    const float *r, *inv, *e, *msk;
+};
+
+__host__ __device__ inline Tables split_tables(const void *tables, const pde_adi_desc &d) {
+    Tables t;
+    const char *b = static_cast<const char *>(tables);
+    t.hdr = reinterpret_cast<const Header *>(b);
+    const float *f = reinterpret_cast<const float *>(b + kHeaderBytes);
+    const size_t T = table_elems(d);
+    t.r = f;
+    t.inv = f + T;
+    t.e = f + 2 * T;
+    t.msk = f + 3 * T;
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// prepare: coefficient map -> clamp -> smoothing -> r -> pivots.  One thread per (sweep,
+// channel, line); op-for-op the fp32 arithmetic of the reference (no FMA contraction).
+// Table layout: [s][c][i/4][line][i%4] so a warp reads one float4 per lane, fully coalesced.
+// ------------------------------------------------------------------------------------------
+__global__ void tables_kernel(pde_adi_desc d, pde_adi_schedule sch, const float *__restrict__ ab,
+                              const float *__restrict__ bb, const float *__restrict__ atc,
+                              const float *__restrict__ btc, char *tables) {
+    const int sps = sweeps_per_step(d), S = d.steps * sps, N = d.N, C = d.C;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * C * N) return;
+    const int line = idx % N, c = (idx / N) % C, s = idx / (N * C);
+    const int axis = sweep_axis(s % sps);
+    const float *base = axis ? bb : ab, *tc = axis ? btc : atc;
+    const float tt = sch.t[s], dts = sch.dts[s], h2 = sch.h2[s];
+    const float third = __fdiv_rn(1.0f, 3.0f);
+    Header *hdr = reinterpret_cast<Header *>(tables);
+    float *f = reinterpret_cast<float *>(tables + kHeaderBytes);
+    const size_t T = table_elems(d);
+    float *tr = f, *tinv = f + T, *te = f + 2 * T, *tm = f + 3 * T;
+
+    float kap[32], msk[32];
+    for (int i = 0; i < N; ++i) {
+        const size_t q = axis == 0 ? ((size_t)c * N + line) * N + i : ((size_t)c * N + i) * N + line;
+        const float raw = __fadd_rn(base[q], __fmul_rn(tc[q], tt));
+        bool m = raw >= d.cmin;
+        float k = raw < d.cmin ? d.cmin : raw;
+        if (d.has_max) {
+            m = m && raw <= d.cmax;
+            k = k > d.cmax ? d.cmax : k;
+        }
+        kap[i] = k;
+        msk[i] = m ? 1.0f : 0.0f;
+    }
+    float cst_prev = 0.0f, rmax = 0.0f;
+    for (int i = 0; i < N; ++i) {
+        float ks = kap[i];
+        if (d.smooth) {
+            const float a0 = __fmul_rn(kap[i > 0 ? i - 1 : 0], third);
+            const float a1 = __fmul_rn(kap[i], third);
+            const float a2 = __fmul_rn(kap[i < N - 1 ? i + 1 : N - 1], third);
+            ks = __fadd_rn(__fadd_rn(a0, a1), a2);
+        }
+        const float r = __fdiv_rn(__fmul_rn(ks, dts), h2);
+        const float b = (i == 0 || i == N - 1) ? __fadd_rn(1.0f, r) : __fadd_rn(1.0f, __fmul_rn(2.0f, r));
+        float den;
+        if (i == 0)
+            den = __fadd_rn(b, d.eps);
+        else
+            den = __fadd_rn(__fsub_rn(b, __fmul_rn(-r, cst_prev)), d.eps);
+        cst_prev = __fdiv_rn(-r, den);
+        const size_t o = (((size_t)s * C + c) * (N / 4) + i / 4) * N * 4 + (size_t)line * 4 + (i & 3);
+        tr[o] = r;
+        tinv[o] = __fdiv_rn(1.0f, den);
+        te[o] = -cst_prev;
+        tm[o] = msk[i];
+        rmax = fmaxf(rmax, fabsf(r));
+    }
+    atomicMax(&hdr->rmax_bits[s], __float_as_uint(rmax));
+}
+
+__global__ void header_kernel(pde_adi_desc d, pde_adi_schedule sch, char *tables) {
+    Header *hdr = reinterpret_cast<Header *>(tables);
+    const int sps = sweeps_per_step(d), S = d.steps * sps;
+    float amp = 1.0f;
+    for (int step = 0; step < d.steps; ++step) {
+        float a = 1.0f;
+        // the first sweep of a step is never rebuilt (its input is a checkpoint)
+        for (int k = 1; k < sps; ++k) a *= 1.0f + 4.0f * __uint_as_float(hdr->rmax_bits[step * sps + k]);
+        amp = fmaxf(amp, a);
+    }
+    for (int s = 0; s < S; ++s) {
+        hdr->scale[s] = __fdiv_rn(sch.dts[s], sch.h2[s]);
+        hdr->t[s] = sch.t[s];
+    }
+    hdr->amp_bound = amp;
+    hdr->mode_exact = (amp > kAmpLimit || !(amp == amp)) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// tile helpers.  A tile is one N x N plane with row stride ST in shared memory.
+// ------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void plane_to_tile(const float *__restrict__ g, float *tile, int lane, bool valid) {
+    constexpr int ST = Geo<N>::ST;
+    const float4 *g4 = reinterpret_cast<const float4 *>(g);
+#pragma unroll
+    for (int q0 = 0; q0 < N * N / 4; q0 += 32) {
+        const int q = q0 + lane;
+        if (q < N * N / 4) {
+            const float4 v = valid ? ld_stream(g4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int idx = 4 * q, r = idx / N, cc = idx % N;
+            *reinterpret_cast<float4 *>(&tile[r * ST + cc]) = v;
+        }
+    }
+}
+
+// out = tile                      (u0 == nullptr)
+// out = sig * u0 + om * tile      (skip epilogue, or gin = g + sig * gout with om == 1)
+template <int N>
+__device__ __forceinline__ void tile_to_plane(const float *tile, float *__restrict__ g, int lane,
+                                              const float *__restrict__ u0, float sig, float om) {
+    constexpr int ST = Geo<N>::ST;
+    float4 *g4 = reinterpret_cast<float4 *>(g);
+#pragma unroll
+    for (int q0 = 0; q0 < N * N / 4; q0 += 32) {
+        const int q = q0 + lane;
+        if (q < N * N / 4) {
+            const int idx = 4 * q, r = idx / N, cc = idx % N;
+            float4 v = *reinterpret_cast<const float4 *>(&tile[r * ST + cc]);
+            if (u0) {
+                const float4 w = ld_stream(reinterpret_cast<const float4 *>(u0) + q);
+                v.x = fmaf(om, v.x, sig * w.x);
+                v.y = fmaf(om, v.y, sig * w.y);
+                v.z = fmaf(om, v.z, sig * w.z);
+                v.w = fmaf(om, v.w, sig * w.w);
+            }
+            st_stream(g4 + q, v);
+        }
+    }
+}
+
+// 4 consecutive elements of the line owned by lane t: AX == 0 -> row t, AX == 1 -> column t.
+template <int N, int AX>
+__device__ __forceinline__ float4 ld4(const float *tile, int t, int q) {
+    constexpr int ST = Geo<N>::ST;
+    if (AX == 0) return *reinterpret_cast<const float4 *>(&tile[t * ST + 4 * q]);
+    return make_float4(tile[(4 * q) * ST + t], tile[(4 * q + 1) * ST + t], tile[(4 * q + 2) * ST + t],
+                       tile[(4 * q + 3) * ST + t]);
+}
+template <int N, int AX>
+__device__ __forceinline__ void st4(float *tile, int t, int q, float4 v) {
+    constexpr int ST = Geo<N>::ST;
+    if (AX == 0) {
+        *reinterpret_cast<float4 *>(&tile[t * ST + 4 * q]) = v;
+    } else {
+        tile[(4 * q) * ST + t] = v.x;
+        tile[(4 * q + 1) * ST + t] = v.y;
+        tile[(4 * q + 2) * ST + t] = v.z;
+        tile[(4 * q + 3) * ST + t] = v.w;
+    }
+}
+
+template <int N, int AX>
+__device__ __forceinline__ void ld_line(const float *tile, int t, float (&x)[N]) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+        const float4 v = ld4<N, AX>(tile, t, q);
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+}
+template <int N, int AX>
+__device__ __forceinline__ void st_line(float *tile, int t, const float (&x)[N]) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q)
+        st4<N, AX>(tile, t, q, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
+}
+
+// x[p][i] = sum_d mat[d * mstride] * tile_d[p][row t][i]   over the C channel tiles of a group.
+// mstride == 1 walks a row of the matrix (forward mix), mstride == C a column (adjoint).
+template <int N, int PB>
+__device__ __forceinline__ void mix_rows(const float *group_tiles, int tiles_per_chan, int C,
+                                         const float *__restrict__ mat, int mstride, int t,
+                                         float (&x)[PB][N]) {
+    constexpr int WORDS = Geo<N>::WORDS;
+#pragma unroll
+    for (int p = 0; p < PB; ++p)
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[p][i] = 0.0f;
+    for (int dd = 0; dd < C; ++dd) {
+        const float m = __ldg(mat + dd * mstride);
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            const float *tile = group_tiles + ((size_t)dd * tiles_per_chan + p) * WORDS;
+#pragma unroll
+            for (int q = 0; q < N / 4; ++q) {
+                const float4 v = ld4<N, 0>(tile, t, q);
+                x[p][4 * q] = fmaf(m, v.x, x[p][4 * q]);
+                x[p][4 * q + 1] = fmaf(m, v.y, x[p][4 * q + 1]);
+                x[p][4 * q + 2] = fmaf(m, v.z, x[p][4 * q + 2]);
+                x[p][4 * q + 3] = fmaf(m, v.w, x[p][4 * q + 3]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Thomas solve of (A + eps I) x = d for the PB lines a lane holds (same coefficients for all
+// PB: the factorisation is batch independent).  With inv = 1/pivot and e = r/pivot = -c*:
+//   d*_i = inv_i d_i + e_i d*_{i-1}         x_i = d*_i + e_i x_{i+1}
+// ------------------------------------------------------------------------------------------
+template <int N, int PB>
+__device__ __forceinline__ void thomas_solve(float (&x)[PB][N], const float4 *__restrict__ tinv,
+                                             const float4 *__restrict__ te) {
+    float e[N];
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+        const float4 iv = __ldg(tinv + q * N), ev = __ldg(te + q * N);
+        const float ivs[4] = {iv.x, iv.y, iv.z, iv.w}, evs[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * q + k;
+            e[i] = evs[k];
+#pragma unroll
+            for (int p = 0; p < PB; ++p)
+                x[p][i] = (i == 0) ? x[p][0] * ivs[k] : fmaf(evs[k], x[p][i - 1], x[p][i] * ivs[k]);
+        }
+    }
+#pragma unroll
+    for (int i = N - 2; i >= 0; --i)
+#pragma unroll
+        for (int p = 0; p < PB; ++p) x[p][i] = fmaf(e[i], x[p][i + 1], x[p][i]);
+}
+
+// Adjoint solve (A + eps I)^T lambda = g through the same factorisation A = L U:
+//   U^T w = g:        w_i = g_i + e_{i-1} w_{i-1}
+//   L^T lambda = w:   lambda_i = inv_i (w_i + r_{i+1} lambda_{i+1})
+template <int N, int PB>
+__device__ __forceinline__ void thomas_solve_adjoint(float (&g)[PB][N], const float4 *__restrict__ tr,
+                                                     const float4 *__restrict__ tinv,
+                                                     const float4 *__restrict__ te) {
+    float eprev = 0.0f;
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+        const float4 ev = __ldg(te + q * N);
+        const float evs[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * q + k;
+            if (i > 0) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) g[p][i] = fmaf(eprev, g[p][i - 1], g[p][i]);
+            }
+            eprev = evs[k];
+        }
+    }
+    float rnext = 0.0f;
+#pragma unroll
+    for (int q = N / 4 - 1; q >= 0; --q) {
+        const float4 iv = __ldg(tinv + q * N), rv = __ldg(tr + q * N);
+        const float ivs[4] = {iv.x, iv.y, iv.z, iv.w}, rvs[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+        for (int k = 3; k >= 0; --k) {
+            const int i = 4 * q + k;
+#pragma unroll
+            for (int p = 0; p < PB; ++p)
+                g[p][i] = (i == N - 1) ? g[p][i] * ivs[k] : fmaf(rnext * ivs[k], g[p][i + 1], g[p][i] * ivs[k]);
+            rnext = rvs[k];
+        }
+    }
+}
+
+struct Args {
+    pde_adi_desc d;
+    int S, sps, G, nitems, need_gin;
+    const char *tables;
+    const float *u, *gout, *chan, *skipw;
+    float *out, *gin;
+    float *scratch, *part_maps, *part_chan, *part_skip;
+};
+
+__device__ __forceinline__ void group_sync(int C, int group) {
+    if (C == 1)
+        __syncwarp();
+    else
+        named_barrier(1 + group, C * 32);
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <int N, int PB>
+__global__ void fwd_kernel(const Args a) {
+    constexpr int WORDS = Geo<N>::WORDS;
+    extern __shared__ __align__(16) float smem[];
+    const pde_adi_desc &d = a.d;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = d.C, group = warp / C, c = warp % C;
+    const bool active = lane < N;
+    const int t = active ? lane : N - 1;
+    float *gtiles = smem + (size_t)group * C * PB * WORDS;  // [C][PB][WORDS]
+    float *my = gtiles + (size_t)c * PB * WORDS;
+    const Tables T = split_tables(a.tables, d);
+    const size_t plane = (size_t)N * N;
+    float sig = 0.0f;
+    if (d.skip) sig = 1.0f / (1.0f + expf(-__ldg(a.skipw)));
+    const float om = 1.0f - sig;
+
+    for (int item = blockIdx.x * a.G + group; item < a.nitems; item += gridDim.x * a.G) {
+        const int b0 = item * PB;
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            const bool valid = b0 + p < d.B;
+            plane_to_tile<N>(a.u + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, my + p * WORDS, lane, valid);
+        }
+        __syncwarp();
+        float x[PB][N];
+        bool in_regs = false;  // x holds the state as rows
+        for (int step = 0; step < d.steps; ++step) {
+            const int s0 = step * a.sps;
+            if (d.chan_op == 1) {
+                if (in_regs && active) {
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
+                }
+                group_sync(C, group);
+                mix_rows<N, PB>(gtiles, PB, C, a.chan + c * C, 1, t, x);
+                group_sync(C, group);
+            } else if (!in_regs) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) ld_line<N, 0>(my + p * WORDS, t, x[p]);
+            }
+            {   // x sweep
+                const size_t o = ((size_t)s0 * C + c) * (N / 4) * N + t;
+                thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
+                                    reinterpret_cast<const float4 *>(T.e) + o);
+            }
+            if (active) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < PB; ++p) ld_line<N, 1>(my + p * WORDS, t, x[p]);
+            {   // y sweep
+                const size_t o = ((size_t)(s0 + 1) * C + c) * (N / 4) * N + t;
+                thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
+                                    reinterpret_cast<const float4 *>(T.e) + o);
+            }
+            if (active) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) st_line<N, 1>(my + p * WORDS, t, x[p]);
+            }
+            __syncwarp();
+            in_regs = false;
+            if (a.sps == 3) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) ld_line<N, 0>(my + p * WORDS, t, x[p]);
+                const size_t o = ((size_t)(s0 + 2) * C + c) * (N / 4) * N + t;
+                thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
+                                    reinterpret_cast<const float4 *>(T.e) + o);
+                in_regs = true;
+            }
+            if (d.chan_op == 2) {
+                if (in_regs && active) {
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
+                }
+                group_sync(C, group);
+                mix_rows<N, PB>(gtiles, PB, C, a.chan + c * C, 1, t, x);
+                group_sync(C, group);
+                in_regs = true;
+            }
+        }
+        if (in_regs && active) {
+#pragma unroll
+            for (int p = 0; p < PB; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            if (b0 + p < d.B) {
+                const size_t off = ((size_t)(b0 + p) * C + c) * plane;
+                tile_to_plane<N>(my + p * WORDS, a.out + off, lane, d.skip ? a.u + off : nullptr, sig, om);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+
+// checkpoint a lane's lines: scratch[(p*N + i)*32 + lane] (coalesced 128 B per element index)
+template <int N, int PB>
+__device__ __forceinline__ void ck_store(float *slot, int lane, const float (&x)[PB][N]) {
+#pragma unroll
+    for (int p = 0; p < PB; ++p)
+#pragma unroll
+        for (int i = 0; i < N; ++i) slot[(p * N + i) * 32 + lane] = x[p][i];
+}
+template <int N, int PB, int AX>
+__device__ __forceinline__ void ck_to_tile(const float *slot, int lane, int t, bool active, float *tiles) {
+    constexpr int WORDS = Geo<N>::WORDS;
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+        float x[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = slot[(p * N + i) * 32 + lane];
+        if (active) st_line<N, AX>(tiles + p * WORDS, t, x);
+    }
+}
+
+// One reversed sweep for the lines this lane owns.
+//   g tile: adjoint in place.  x tile: holds the sweep OUTPUT; if `rebuild`, it is overwritten
+//   with the sweep INPUT  x_in = (1 + eps) x - r * (L x).
+//   Per-pixel gradient: v_i = sum_p lambda_i (L x)_i  ->  smoothing^T, clamp mask, weights
+//   (scale, scale * t) into the lane-private accumulator lines acc0 / acc1.
+template <int N, int PB, int AX>
+__device__ __forceinline__ void reverse_sweep(float *gt, float *xt, float *acc0, float *acc1, int t,
+                                              bool active, const Tables &T, size_t o, float scale, float tt,
+                                              float onepe, bool smooth, bool rebuild) {
+    constexpr int WORDS = Geo<N>::WORDS;
+    const float4 *tr = reinterpret_cast<const float4 *>(T.r) + o;
+    const float4 *tinv = reinterpret_cast<const float4 *>(T.inv) + o;
+    const float4 *te = reinterpret_cast<const float4 *>(T.e) + o;
+    const float4 *tm = reinterpret_cast<const float4 *>(T.msk) + o;
+    float g[PB][N];
+#pragma unroll
+    for (int p = 0; p < PB; ++p) ld_line<N, AX>(gt + p * WORDS, t, g[p]);
+    thomas_solve_adjoint<N, PB>(g, tr, tinv, te);
+    if (active) {
+#pragma unroll
+        for (int p = 0; p < PB; ++p) st_line<N, AX>(gt + p * WORDS, t, g[p]);
+    }
+    float v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = 0.0f;
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+        float x[N];
+        ld_line<N, AX>(xt + p * WORDS, t, x);
+        float xin[N];
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rebuild) rv = __ldg(tr + q * N);
+            const float rvs[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = 4 * q + k;
+                float lx;
+                if (i == 0)
+                    lx = x[1] - x[0];
+                else if (i == N - 1)
+                    lx = x[N - 2] - x[N - 1];
+                else
+                    lx = (x[i - 1] - x[i]) + (x[i + 1] - x[i]);
+                v[i] = fmaf(g[p][i], lx, v[i]);
+                xin[i] = fmaf(-rvs[k], lx, onepe * x[i]);
+            }
+        }
+        if (rebuild && active) st_line<N, AX>(xt + p * WORDS, t, xin);
+    }
+    // smoothing^T along the line (replicate padding puts the end taps back on the end cells)
+    float z[N];
+    if (smooth) {
+        const float third = 1.0f / 3.0f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const float lo = (i == 0) ? v[0] : v[i - 1];
+            const float hi = (i == N - 1) ? v[N - 1] : v[i + 1];
+            z[i] = ((lo + v[i]) + hi) * (third * scale);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) z[i] = v[i] * scale;
+    }
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            const float4 m = __ldg(tm + q * N);
+            float4 a0 = ld4<N, AX>(acc0, t, q), a1 = ld4<N, AX>(acc1, t, q);
+            const float z0 = m.x * z[4 * q], z1 = m.y * z[4 * q + 1], z2 = m.z * z[4 * q + 2], z3 = m.w * z[4 * q + 3];
+            a0.x += z0; a0.y += z1; a0.z += z2; a0.w += z3;
+            a1.x = fmaf(tt, z0, a1.x); a1.y = fmaf(tt, z1, a1.y); a1.z = fmaf(tt, z2, a1.z); a1.w = fmaf(tt, z3, a1.w);
+            st4<N, AX>(acc0, t, q, a0);
+            st4<N, AX>(acc1, t, q, a1);
+        }
+    }
+}
+
+// Adjoint of a channel op on the group's g tiles (rows), using the op's INPUT state in the x
+// tiles:  gm[dd] += sum g_c * x_dd ;  g_c <- sum_c' mat[c'][c] g_c'.
+template <int N, int PB>
+__device__ __forceinline__ void chan_adjoint(float *ggt, float *gxt, int C, int c, int group,
+                                             const float *__restrict__ mat, int t, bool active,
+                                             float (&gm)[PDE_MAX_CHANNELS]) {
+    constexpr int WORDS = Geo<N>::WORDS;
+    group_sync(C, group);
+    if (active) {
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            float g[N];
+            ld_line<N, 0>(ggt + ((size_t)c * PB + p) * WORDS, t, g);
+            for (int dd = 0; dd < C; ++dd) {
+                float x[N];
+                ld_line<N, 0>(gxt + ((size_t)dd * PB + p) * WORDS, t, x);
+                float acc = 0.0f;
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc = fmaf(g[i], x[i], acc);
+                gm[dd] += acc;
+            }
+        }
+    }
+    float gn[PB][N];
+    mix_rows<N, PB>(ggt, PB, C, mat + c, C, t, gn);
+    group_sync(C, group);
+    if (active) {
+#pragma unroll
+        for (int p = 0; p < PB; ++p) st_line<N, 0>(ggt + ((size_t)c * PB + p) * WORDS, t, gn[p]);
+    }
+    __syncwarp();
+}
+
+template <int N, int PB>
+__global__ void bwd_kernel(const Args a) {
+    constexpr int WORDS = Geo<N>::WORDS;
+    extern __shared__ __align__(16) float smem[];
+    const pde_adi_desc &d = a.d;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int C = d.C, group = warp / C, c = warp % C;
+    const bool active = lane < N;
+    const int t = active ? lane : N - 1;
+    // shared layout: x tiles [G][C][PB], g tiles [G][C][PB], accumulators [warps][4]
+    float *gxt = smem + (size_t)group * C * PB * WORDS;
+    float *ggt = smem + (size_t)a.G * C * PB * WORDS + (size_t)group * C * PB * WORDS;
+    float *xt = gxt + (size_t)c * PB * WORDS, *gt = ggt + (size_t)c * PB * WORDS;
+    float *acc = smem + (size_t)2 * a.G * C * PB * WORDS + (size_t)warp * 4 * WORDS;
+    for (int i = lane; i < 4 * WORDS; i += 32) acc[i] = 0.0f;
+    __syncwarp();
+    const Tables T = split_tables(a.tables, d);
+    const bool exact = T.hdr->mode_exact != 0;
+    const size_t plane = (size_t)N * N;
+    const int wg = blockIdx.x * nwarps + warp;
+    float *scratch = a.scratch + (size_t)wg * a.S * (PB * N * 32);
+    constexpr int SLOT = PB * N * 32;
+    float sig = 0.0f;
+    if (d.skip) sig = 1.0f / (1.0f + expf(-__ldg(a.skipw)));
+    const float om = 1.0f - sig;
+    const float onepe = 1.0f + d.eps;
+    const bool smooth = d.smooth != 0;
+    float gm[PDE_MAX_CHANNELS] = {0.f, 0.f, 0.f, 0.f};
+    float gw = 0.0f;
+    const int sps = a.sps, S = a.S;
+    const int last_ax = (sps == 3) ? 0 : 1;  // orientation of the state after the last sweep of a step
+
+    for (int item = blockIdx.x * a.G + group; item < a.nitems; item += gridDim.x * a.G) {
+        const int b0 = item * PB;
+        // ------------------------------ phase 1: forward trajectory with checkpoints
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            const bool valid = b0 + p < d.B;
+            plane_to_tile<N>(a.u + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, xt + p * WORDS, lane, valid);
+        }
+        __syncwarp();
+        {
+            float x[PB][N];
+            bool in_regs = false;
+            for (int step = 0; step < d.steps; ++step) {
+                const int s0 = step * sps;
+                if (d.chan_op == 1) {
+                    if (in_regs && active) {
+#pragma unroll
+                        for (int p = 0; p < PB; ++p) st_line<N, 0>(xt + p * WORDS, t, x[p]);
+                    }
+                    group_sync(C, group);
+                    mix_rows<N, PB>(gxt, PB, C, a.chan + c * C, 1, t, x);
+                    group_sync(C, group);
+                } else if (!in_regs) {
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) ld_line<N, 0>(xt + p * WORDS, t, x[p]);
+                }
+                {
+                    const size_t o = ((size_t)s0 * C + c) * (N / 4) * N + t;
+                    thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
+                                        reinterpret_cast<const float4 *>(T.e) + o);
+                }
+                if (exact) ck_store<N, PB>(scratch + (size_t)s0 * SLOT, lane, x);
+                if (active) {
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) st_line<N, 0>(xt + p * WORDS, t, x[p]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int p = 0; p < PB; ++p) ld_line<N, 1>(xt + p * WORDS, t, x[p]);
+                {
+                    const size_t o = ((size_t)(s0 + 1) * C + c) * (N / 4) * N + t;
+                    thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
+                                        reinterpret_cast<const float4 *>(T.e) + o);
+                }
+                if (exact || sps == 2) ck_store<N, PB>(scratch + (size_t)(s0 + 1) * SLOT, lane, x);
+                if (active) {
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) st_line<N, 1>(xt + p * WORDS, t, x[p]);
+                }
+                __syncwarp();
+                in_regs = false;
+                if (sps == 3) {
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) ld_line<N, 0>(xt + p * WORDS, t, x[p]);
+                    const size_t o = ((size_t)(s0 + 2) * C + c) * (N / 4) * N + t;
+                    thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
+                                        reinterpret_cast<const float4 *>(T.e) + o);
+                    ck_store<N, PB>(scratch + (size_t)(s0 + 2) * SLOT, lane, x);
+                    in_regs = true;
+                }
+                if (d.chan_op == 2) {
+                    if (in_regs && active) {
+#pragma unroll
+                        for (int p = 0; p < PB; ++p) st_line<N, 0>(xt + p * WORDS, t, x[p]);
+                    }
+                    group_sync(C, group);
+                    mix_rows<N, PB>(gxt, PB, C, a.chan + c * C, 1, t, x);
+                    group_sync(C, group);
+                    in_regs = true;
+                }
+            }
+        }
+        __syncwarp();
+        // ------------------------------ phase 2: reverse
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            const bool valid = b0 + p < d.B;
+            plane_to_tile<N>(a.gout + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, gt + p * WORDS, lane, valid);
+        }
+        bool xt_valid = false;
+        if (d.skip) {
+            // out = sig u0 + om uF:  dL/dw += sig' * sum gout (u0 - uF),  g <- om * gout
+            if (S > 0) {
+                if (last_ax == 0)
+                    ck_to_tile<N, PB, 0>(scratch + (size_t)(S - 1) * SLOT, lane, t, active, xt);
+                else
+                    ck_to_tile<N, PB, 1>(scratch + (size_t)(S - 1) * SLOT, lane, t, active, xt);
+                xt_valid = true;
+            }
+            __syncwarp();
+            float accw = 0.0f;
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                if (b0 + p < d.B && active) {
+                    const float4 *u4 = reinterpret_cast<const float4 *>(a.u + ((size_t)(b0 + p) * C + c) * plane + (size_t)t * N);
+#pragma unroll
+                    for (int q = 0; q < N / 4; ++q) {
+                        float4 g4 = ld4<N, 0>(gt + p * WORDS, t, q);
+                        const float4 uf = (S > 0) ? ld4<N, 0>(xt + p * WORDS, t, q) : __ldg(u4 + q);
+                        const float4 u0 = __ldg(u4 + q);
+                        accw = fmaf(g4.x, u0.x - uf.x, accw);
+                        accw = fmaf(g4.y, u0.y - uf.y, accw);
+                        accw = fmaf(g4.z, u0.z - uf.z, accw);
+                        accw = fmaf(g4.w, u0.w - uf.w, accw);
+                        g4.x *= om; g4.y *= om; g4.z *= om; g4.w *= om;
+                        st4<N, 0>(gt + p * WORDS, t, q, g4);
+                    }
+                }
+            }
+            gw += accw;
+        }
+        __syncwarp();
+        for (int step = d.steps - 1; step >= 0; --step) {
+            const int sl = step * sps + sps - 1;
+            if (!xt_valid) {
+                if (last_ax == 0)
+                    ck_to_tile<N, PB, 0>(scratch + (size_t)sl * SLOT, lane, t, active, xt);
+                else
+                    ck_to_tile<N, PB, 1>(scratch + (size_t)sl * SLOT, lane, t, active, xt);
+                __syncwarp();
+            }
+            xt_valid = false;
+            if (d.chan_op == 2) chan_adjoint<N, PB>(ggt, gxt, C, c, group, a.chan, t, active, gm);
+            for (int k = sps - 1; k >= 0; --k) {
+                const int s = step * sps + k;
+                const int ax = sweep_axis(k);
+                if (exact && k != sps - 1) {
+                    if (ax == 0)
+                        ck_to_tile<N, PB, 0>(scratch + (size_t)s * SLOT, lane, t, active, xt);
+                    else
+                        ck_to_tile<N, PB, 1>(scratch + (size_t)s * SLOT, lane, t, active, xt);
+                    __syncwarp();
+                }
+                const size_t o = ((size_t)s * C + c) * (N / 4) * N + t;
+                const float scale = T.hdr->scale[s], tt = T.hdr->t[s];
+                const bool rebuild = !exact && k > 0;
+                if (ax == 0)
+                    reverse_sweep<N, PB, 0>(gt, xt, acc, acc + WORDS, t, active, T, o, scale, tt, onepe, smooth, rebuild);
+                else
+                    reverse_sweep<N, PB, 1>(gt, xt, acc + 2 * WORDS, acc + 3 * WORDS, t, active, T, o, scale, tt, onepe, smooth, rebuild);
+                __syncwarp();
+            }
+            if (d.chan_op == 1) {
+                // input of the mix = state before this step = checkpoint of the previous step (or u)
+                if (step > 0) {
+                    if (last_ax == 0)
+                        ck_to_tile<N, PB, 0>(scratch + (size_t)(step * sps - 1) * SLOT, lane, t, active, xt);
+                    else
+                        ck_to_tile<N, PB, 1>(scratch + (size_t)(step * sps - 1) * SLOT, lane, t, active, xt);
+                    xt_valid = true;
+                } else {
+#pragma unroll
+                    for (int p = 0; p < PB; ++p) {
+                        const bool valid = b0 + p < d.B;
+                        plane_to_tile<N>(a.u + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, xt + p * WORDS, lane, valid);
+                    }
+                }
+                __syncwarp();
+                chan_adjoint<N, PB>(ggt, gxt, C, c, group, a.chan, t, active, gm);
+            }
+        }
+        if (a.need_gin) {
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                if (b0 + p < d.B) {
+                    const size_t off = ((size_t)(b0 + p) * C + c) * plane;
+                    tile_to_plane<N>(gt + p * WORDS, a.gin + off, lane, d.skip ? a.gout + off : nullptr, sig, 1.0f);
+                }
+            }
+        }
+        __syncwarp();
+        // the next item's phase 1 mixes through the group's x tiles: nobody may still read them
+        if (d.chan_op != 0) group_sync(C, group);
+    }
+    // ------------------------------ per-warp partials
+    __syncwarp();
+    float *pm = a.part_maps + (size_t)wg * 4 * plane;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) tile_to_plane<N>(acc + kk * WORDS, pm + kk * plane, lane, nullptr, 0.f, 1.f);
+#pragma unroll
+    for (int dd = 0; dd < PDE_MAX_CHANNELS; ++dd) {
+        const float sgm = warp_sum(active ? gm[dd] : 0.0f);
+        if (lane == 0) a.part_chan[(size_t)wg * PDE_MAX_CHANNELS + dd] = sgm;
+    }
+    const float sgw = warp_sum(gw);
+    if (lane == 0) a.part_skip[wg] = sgw;
+}
+
+// Sum the per-warp partials (double accumulation, fixed order => deterministic).
+__global__ void finish_kernel(pde_adi_desc d, int nwarps_total, const float *__restrict__ part_maps,
+                              const float *__restrict__ part_chan, const float *__restrict__ part_skip,
+                              const float *__restrict__ skipw, float *g_ab, float *g_atc, float *g_bb,
+                              float *g_btc, float *g_chan, float *g_skip) {
+    const int C = d.C, N = d.N;
+    const size_t plane = (size_t)N * N;
+    const size_t total = 4 * (size_t)C * plane;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < total) {
+        const int kind = (int)(idx / (C * plane));
+        const int c = (int)((idx / plane) % C);
+        const size_t cell = idx % plane;
+        double acc = 0.0;
+        for (int w = c; w < nwarps_total; w += C) acc += (double)part_maps[((size_t)w * 4 + kind) * plane + cell];
+        float *dst = kind == 0 ? g_ab : kind == 1 ? g_atc : kind == 2 ? g_bb : g_btc;
+        dst[(size_t)c * plane + cell] = (float)acc;
+    }
+    if (blockIdx.x == 0) {
+        if (g_chan && threadIdx.x < C * C) {
+            const int c = threadIdx.x / C, dd = threadIdx.x % C;
+            double acc = 0.0;
+            for (int w = c; w < nwarps_total; w += C) acc += (double)part_chan[(size_t)w * PDE_MAX_CHANNELS + dd];
+            g_chan[c * C + dd] = (float)acc;
+        }
+        if (g_skip && threadIdx.x == 32) {
+            double acc = 0.0;
+            for (int w = 0; w < nwarps_total; ++w) acc += (double)part_skip[w];
+            const double sg = 1.0 / (1.0 + exp(-(double)skipw[0]));
+            g_skip[0] = (float)(acc * sg * (1.0 - sg));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int validate(const pde_adi_desc *d) {
+    if (!d) return PDE_ERR_INVALID;
+    if (d->B < 0 || d->C < 1 || d->N < 2 || d->steps < 0) return PDE_ERR_INVALID;
+    if (d->chan_op < 0 || d->chan_op > 2) return PDE_ERR_INVALID;
+    if (d->steps * sweeps_per_step(*d) > PDE_MAX_SWEEPS) return PDE_ERR_UNSUPPORTED;
+    if (d->C > PDE_MAX_CHANNELS) return PDE_ERR_UNSUPPORTED;
+    switch (d->N) {
+        case 8: case 12: case 16: case 28: case 32: break;
+        default: return PDE_ERR_UNSUPPORTED;
+    }
+    return PDE_OK;
+}
+
+static int groups_per_block(int C) { return C >= 3 ? 1 : (C == 2 ? 2 : 4); }
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoi(v);
+}
+
+static int tile_words(int N) { return N * ((N % 8 == 4) ? N : N + 4); }
+
+struct BwdPlan {
+    int PB, G, warps, blocks_per_sm, grid, nitems;
+    size_t smem, scratch_floats, maps_floats, chan_floats, skip_floats;
+};
+
+static int bwd_pb(const pde_adi_desc *d) {
+    int pb = env_int("PDE_B200_BWD_PB", 1);
+    return pb == 2 ? 2 : 1;
+}
+
+static int plan_bwd(const pde_adi_desc *d, BwdPlan *p) {
+    DeviceProps props;
+    int rc = query_props(&props);
+    if (rc) return rc;
+    p->PB = bwd_pb(d);
+    p->G = groups_per_block(d->C);
+    p->warps = p->G * d->C;
+    p->smem = ((size_t)2 * p->warps * p->PB + (size_t)4 * p->warps) * tile_words(d->N) * sizeof(float);
+    if (p->smem > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
+    // registers cap residency at 65536 / (255 * 32) = 8 warps in the worst case; shared memory
+    // caps it at 227 KB / smem.  The occupancy API is not used so the plan (and therefore the
+    // workspace size) is a pure function of the descriptor and the device.
+    int by_smem = (int)((size_t)(227 * 1024) / (p->smem + 1024));
+    int by_warps = 16 / p->warps;
+    p->blocks_per_sm = by_smem < by_warps ? by_smem : by_warps;
+    if (p->blocks_per_sm < 1) p->blocks_per_sm = 1;
+    p->nitems = (d->B + p->PB - 1) / p->PB;
+    int want = (p->nitems + p->G - 1) / p->G;
+    int cap = props.sm_count * p->blocks_per_sm;
+    p->grid = want < cap ? want : cap;
+    if (p->grid < 1) p->grid = 1;
+    const size_t S = (size_t)d->steps * sweeps_per_step(*d);
+    const size_t nw = (size_t)p->grid * p->warps;
+    p->scratch_floats = nw * (S > 0 ? S : 1) * p->PB * d->N * 32;
+    p->maps_floats = nw * 4 * d->N * d->N;
+    p->chan_floats = nw * PDE_MAX_CHANNELS;
+    p->skip_floats = nw;
+    return PDE_OK;
+}
+
+template <int N>
+static int launch_fwd(const Args &a, int PB, int grid, int threads, size_t smem, cudaStream_t st) {
+    auto go = [&](auto kern) -> int {
+        PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, st>>>(a);
+        return cuda_last_error();
+    };
+    switch (PB) {
+        case 1: return go(fwd_kernel<N, 1>);
+        case 2: return go(fwd_kernel<N, 2>);
+        default: return go(fwd_kernel<N, 4>);
+    }
+}
+
+template <int N>
+static int launch_bwd(const Args &a, int PB, int grid, int threads, size_t smem, cudaStream_t st) {
+    auto go = [&](auto kern) -> int {
+        PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, st>>>(a);
+        return cuda_last_error();
+    };
+    return PB == 2 ? go(bwd_kernel<N, 2>) : go(bwd_kernel<N, 1>);
+}
+
+#define PDE_DISPATCH_N(N_, CALL)                     \
+    switch (N_) {                                    \
+        case 8: rc = CALL<8>; break;                 \
+        case 12: rc = CALL<12>; break;               \
+        case 16: rc = CALL<16>; break;               \
+        case 28: rc = CALL<28>; break;               \
+        case 32: rc = CALL<32>; break;               \
+        default: rc = PDE_ERR_UNSUPPORTED;           \
+    }
+
+}  // namespace adi
+}  // namespace pde
+
+using namespace pde;
+using namespace pde::adi;
+
+extern "C" size_t pde_adi_tables_bytes(const pde_adi_desc *d) {
+    if (validate(d) != PDE_OK) return 0;
+    return (size_t)kHeaderBytes + 4 * table_elems(*d) * sizeof(float);
+}
+
+extern "C" size_t pde_adi_backward_workspace_bytes(const pde_adi_desc *d) {
+    if (validate(d) != PDE_OK) return 0;
+    BwdPlan p;
+    if (plan_bwd(d, &p) != PDE_OK) return 0;
+    return (p.scratch_floats + p.maps_floats + p.chan_floats + p.skip_floats) * sizeof(float) + 256;
+}
+
+extern "C" int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sched, const float *ab,
+                               const float *bb, const float *atc, const float *btc, void *tables,
+                               void *stream) {
+    int rc = validate(d);
+    if (rc) return rc;
+    if (!sched || !ab || !bb || !atc || !btc || !tables) return PDE_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(tables) & 255u) return PDE_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PDE_CUDA_TRY(cudaMemsetAsync(tables, 0, kHeaderBytes, st));
+    const int S = d->steps * sweeps_per_step(*d);
+    const int n = S * d->C * d->N;
+    if (n > 0) {
+        tables_kernel<<<(n + 127) / 128, 128, 0, st>>>(*d, *sched, ab, bb, atc, btc, static_cast<char *>(tables));
+        rc = cuda_last_error();
+        if (rc) return rc;
+    }
+    header_kernel<<<1, 1, 0, st>>>(*d, *sched, static_cast<char *>(tables));
+    return cuda_last_error();
+}
+
+extern "C" int pde_adi_forward(const pde_adi_desc *d, const void *tables, const float *u, const float *chan,
+                               const float *skipw, float *out, void *stream) {
+    int rc = validate(d);
+    if (rc) return rc;
+    if (!tables || !u || !out) return PDE_ERR_INVALID;
+    if (d->chan_op && !chan) return PDE_ERR_INVALID;
+    if (d->skip && !skipw) return PDE_ERR_INVALID;
+    if (!aligned16(u) || !aligned16(out)) return PDE_ERR_INVALID;
+    if (d->B == 0) return PDE_OK;
+    DeviceProps props;
+    rc = query_props(&props);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Args a{};
+    a.d = *d;
+    a.sps = sweeps_per_step(*d);
+    a.S = d->steps * a.sps;
+    a.G = groups_per_block(d->C);
+    int PB = env_int("PDE_B200_FWD_PB", 2);
+    if (PB != 1 && PB != 2) PB = 4;
+    // small batches: spread samples over more warps instead of stacking them in one
+    while (PB > 1 && (d->B + PB - 1) / PB < props.sm_count * 4 * a.G) PB >>= 1;
+    a.nitems = (d->B + PB - 1) / PB;
+    a.tables = static_cast<const char *>(tables);
+    a.u = u; a.chan = chan; a.skipw = skipw; a.out = out;
+    const int warps = a.G * d->C;
+    const size_t smem = (size_t)warps * PB * tile_words(d->N) * sizeof(float);
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    const int by_warps = 32 / warps;
+    if (per_sm > by_warps) per_sm = by_warps;
+    if (per_sm < 1) per_sm = 1;
+    const int want = (a.nitems + a.G - 1) / a.G, cap = props.sm_count * per_sm;
+    const int grid = want < cap ? want : cap;
+#define FWD_CALL launch_fwd
+    switch (d->N) {
+        case 8: rc = launch_fwd<8>(a, PB, grid, warps * 32, smem, st); break;
+        case 12: rc = launch_fwd<12>(a, PB, grid, warps * 32, smem, st); break;
+        case 16: rc = launch_fwd<16>(a, PB, grid, warps * 32, smem, st); break;
+        case 28: rc = launch_fwd<28>(a, PB, grid, warps * 32, smem, st); break;
+        case 32: rc = launch_fwd<32>(a, PB, grid, warps * 32, smem, st); break;
+        default: rc = PDE_ERR_UNSUPPORTED;
+    }
+    return rc;
+}
+
+extern "C" int pde_adi_backward(const pde_adi_desc *d, const void *tables, const float *u, const float *gout,
+                                const float *chan, const float *skipw, float *gin, float *g_ab, float *g_bb,
+                                float *g_atc, float *g_btc, float *g_chan, float *g_skip, void *workspace,
+                                size_t workspace_bytes, void *stream) {
+    int rc = validate(d);
+    if (rc) return rc;
+    if (!tables || !u || !gout || !g_ab || !g_bb || !g_atc || !g_btc) return PDE_ERR_INVALID;
+    if (d->chan_op && (!chan || !g_chan)) return PDE_ERR_INVALID;
+    if (d->skip && (!skipw || !g_skip)) return PDE_ERR_INVALID;
+    if (!aligned16(u) || !aligned16(gout) || (gin && !aligned16(gin))) return PDE_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    BwdPlan p;
+    rc = plan_bwd(d, &p);
+    if (rc) return rc;
+    const size_t need = (p.scratch_floats + p.maps_floats + p.chan_floats + p.skip_floats) * sizeof(float) + 256;
+    if (!workspace || workspace_bytes < need) return PDE_ERR_WORKSPACE;
+    float *ws = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255u) & ~(uintptr_t)255u);
+    Args a{};
+    a.d = *d;
+    a.sps = sweeps_per_step(*d);
+    a.S = d->steps * a.sps;
+    a.G = p.G;
+    a.nitems = p.nitems;
+    a.need_gin = gin != nullptr;
+    a.tables = static_cast<const char *>(tables);
+    a.u = u; a.gout = gout; a.chan = chan; a.skipw = skipw; a.gin = gin;
+    a.scratch = ws;
+    a.part_maps = ws + p.scratch_floats;
+    a.part_chan = a.part_maps + p.maps_floats;
+    a.part_skip = a.part_chan + p.chan_floats;
+    const int nw = p.grid * p.warps;
+    if (d->B == 0) {
+        // empty batch: every gradient is exactly zero
+        const size_t mapb = (size_t)d->C * d->N * d->N * sizeof(float);
+        PDE_CUDA_TRY(cudaMemsetAsync(g_ab, 0, mapb, st));
+        PDE_CUDA_TRY(cudaMemsetAsync(g_bb, 0, mapb, st));
+        PDE_CUDA_TRY(cudaMemsetAsync(g_atc, 0, mapb, st));
+        PDE_CUDA_TRY(cudaMemsetAsync(g_btc, 0, mapb, st));
+        if (g_chan) PDE_CUDA_TRY(cudaMemsetAsync(g_chan, 0, (size_t)d->C * d->C * sizeof(float), st));
+        if (g_skip) PDE_CUDA_TRY(cudaMemsetAsync(g_skip, 0, sizeof(float), st));
+        return PDE_OK;
+    }
+    switch (d->N) {
+        case 8: rc = launch_bwd<8>(a, p.PB, p.grid, p.warps * 32, p.smem, st); break;
+        case 12: rc = launch_bwd<12>(a, p.PB, p.grid, p.warps * 32, p.smem, st); break;
+        case 16: rc = launch_bwd<16>(a, p.PB, p.grid, p.warps * 32, p.smem, st); break;
+        case 28: rc = launch_bwd<28>(a, p.PB, p.grid, p.warps * 32, p.smem, st); break;
+        case 32: rc = launch_bwd<32>(a, p.PB, p.grid, p.warps * 32, p.smem, st); break;
+        default: rc = PDE_ERR_UNSUPPORTED;
+    }
+    if (rc) return rc;
+    const size_t total = 4 * (size_t)d->C * d->N * d->N;
+    finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(*d, nw, a.part_maps, a.part_chan, a.part_skip,
+                                                                  skipw, g_ab, g_atc, g_bb, g_btc, g_chan, g_skip);
+    return cuda_last_error();
+}

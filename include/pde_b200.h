@@ -1,0 +1,143 @@
+/*
+ * include/pde_b200.h -- C ABI of libpde_b200.so, the sm_100a implementation of the PDE
+ * block of MariMamgo/CNN-with-PDE (forward + hand-derived adjoint).
+ *
+ * The reference has no native code and therefore no FFI: the interface these entry points
+ * replace is the `forward` of its seven nn.Module classes plus the autograd graph PyTorch
+ * records under them.  Each group below names the reference code it stands in for; the
+ * Python binding a maintainer adds (ctypes) is shown in INTEGRATION.md and implemented in
+ * cnn-with-pde_b200/_cabi.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every tensor pointer is a DEVICE pointer to contiguous
+ *     fp32 NCHW data owned by the caller (torch's caching allocator); nothing is allocated
+ *     or freed inside the library; workspaces are caller-provided;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no call
+ *     synchronises the device;
+ *   - return value: 0 on success, a negative PDE_ERR_* for argument errors, a positive
+ *     cudaError_t if the CUDA runtime reported one.  No exceptions cross the boundary;
+ *   - no global mutable state: re-entrant across host threads and streams;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PDE_B200_H
+#define PDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDE_B200_ABI_VERSION 1
+
+#define PDE_OK 0
+#define PDE_ERR_INVALID (-1)      /* NULL pointer, negative size, inconsistent descriptor   */
+#define PDE_ERR_UNSUPPORTED (-2)  /* valid for the reference but not built here (see DESIGN) */
+#define PDE_ERR_WORKSPACE (-3)    /* workspace / table buffer too small or misaligned       */
+
+#define PDE_MAX_SWEEPS 192        /* 64 Strang steps or 96 Lie steps                        */
+#define PDE_MAX_CHANNELS 4        /* channel-mix registers per thread                       */
+
+int pde_b200_abi_version(void);
+const char *pde_b200_error_string(int code);
+/* SM count, compute capability and L2 size of the current device (for the bench harness). */
+int pde_b200_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes);
+
+/* ---------------------------------------------------------------------------------------
+ * Implicit ADI family.  Replaces DiffusionLayer.forward  mnist_test.py:44-65,
+ * fashion_mnist.py:48-69, SVHN.py:49-76; EnhancedDiffusionLayer.forward cifar10.py:74-114;
+ * LearnableDiffusionLayer.forward cifar_2version.py:70-104, and everything they call
+ * (get_alpha_beta_at_time, diffuse_{x,y}_vectorized[_parallel], smooth_coefficients,
+ * thomas_solver_batch[_optimized], apply_channel_{mixing,coupling}).
+ * ------------------------------------------------------------------------------------- */
+typedef struct pde_adi_desc {
+    int32_t B, C, N;          /* batch, channels (<= PDE_MAX_CHANNELS), plane edge H == W == N */
+    int32_t steps;            /* num_steps                                                   */
+    int32_t lie;              /* 0 Strang x(dt/2) y(dt) x(dt/2); 1 Lie x(dt/2) y(dt/2)        */
+    int32_t smooth;           /* 3-tap replicate smoothing of the clamped map along the sweep */
+    int32_t has_max;          /* clamp(min,max) instead of clamp(min)                        */
+    int32_t chan_op;          /* 0 none, 1 pre-step u<-M u (cifar), 2 post-step u<-K u (SVHN) */
+    int32_t skip;             /* out = sigmoid(w) u0 + (1-sigmoid(w)) u   (SVHN.py:74)        */
+    float cmin, cmax, eps;    /* clamp bounds, stability_eps added to every Thomas pivot      */
+} pde_adi_desc;
+
+/* Per-sweep schedule, built by the host exactly as the reference accumulates it in Python
+ * double (current_time += dt/2) and rounded to fp32 the way ATen rounds a Python scalar:
+ * t[s] = time at which the coefficient maps are evaluated, dts[s] = time step of the sweep,
+ * h2[s] = (spacing**2) of the sweep.  Length = steps * (lie ? 2 : 3) <= PDE_MAX_SWEEPS. */
+typedef struct pde_adi_schedule {
+    float t[PDE_MAX_SWEEPS];
+    float dts[PDE_MAX_SWEEPS];
+    float h2[PDE_MAX_SWEEPS];
+} pde_adi_schedule;
+
+/* Bytes of device memory for the factorised coefficient tables of one layer call. */
+size_t pde_adi_tables_bytes(const pde_adi_desc *d);
+/* Bytes of device workspace pde_adi_backward needs (step checkpoints + gradient partials). */
+size_t pde_adi_backward_workspace_bytes(const pde_adi_desc *d);
+
+/* Coefficient maps -> clamp -> smoothing -> r -> Thomas pivots, once per call and shared by
+ * the whole batch.  Maps are [C][N][N] ((N,N) for the single-channel layers).  `tables`
+ * must hold pde_adi_tables_bytes(d) bytes, 256-byte aligned. */
+int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sched,
+                    const float *alpha_base, const float *beta_base,
+                    const float *alpha_time_coeff, const float *beta_time_coeff,
+                    void *tables, void *stream);
+
+/* u, out: [B][C][N][N].  chan: [C][C] or NULL (chan_op == 0).  skip_weight: 1 value or NULL. */
+int pde_adi_forward(const pde_adi_desc *d, const void *tables, const float *u,
+                    const float *chan, const float *skip_weight, float *out, void *stream);
+
+/* gin may be NULL (the layer is the first op of every reference model, so grad_input is
+ * normally not needed).  Gradient outputs are OVERWRITTEN (not accumulated): four maps
+ * [C][N][N], g_chan [C][C] (or NULL), g_skip_weight 1 value (or NULL). */
+int pde_adi_backward(const pde_adi_desc *d, const void *tables, const float *u, const float *gout,
+                     const float *chan, const float *skip_weight, float *gin,
+                     float *g_alpha_base, float *g_beta_base,
+                     float *g_alpha_time_coeff, float *g_beta_time_coeff,
+                     float *g_chan, float *g_skip_weight,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Explicit family, frozen reflected ghost ring.  Replaces PDELayer.forward / alpha / beta
+ * emotion_recognition.py:76-97.
+ * ------------------------------------------------------------------------------------- */
+typedef struct pde_emo_desc {
+    int32_t B, N, Nt;         /* batch, plane edge (Nx == Ny == N <= 64), int(T/dt)           */
+    float half_dt;            /* fp32(0.5*dt)      (scalar in alpha())                       */
+    float dt;                 /* fp32(dt)          (scalar in beta())                        */
+    float dx2, dy2;           /* fp32(dx**2), fp32(dy**2)                                    */
+} pde_emo_desc;
+
+size_t pde_emotion_backward_workspace_bytes(const pde_emo_desc *d);
+/* w6 = {alpha_w1, alpha_w2, alpha_w3, beta_w1, beta_w2, beta_w3}; xs, ys: the registered
+ * buffers x (N,), y (N,).  u0, out: [B][1][N][N]. */
+int pde_emotion_forward(const pde_emo_desc *d, const float *u0, const float *w6, const float *xs,
+                        const float *ys, float *out, void *stream);
+int pde_emotion_backward(const pde_emo_desc *d, const float *u0, const float *gout, const float *w6,
+                         const float *xs, const float *ys, float *gin, float *g_w6,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Explicit family, zero ghosts, per-channel scalars.  Replaces ImprovedDiffusionLayer.forward
+ * and simple_diffusion_step, tiny_imagenet.py:34-72.
+ * ------------------------------------------------------------------------------------- */
+typedef struct pde_tiny_desc {
+    int32_t B, C, H, W, steps;
+    float dt, cmin, cmax, blend;  /* blend = 0.1 (tiny_imagenet.py:49)                        */
+} pde_tiny_desc;
+
+size_t pde_tiny_backward_workspace_bytes(const pde_tiny_desc *d);
+int pde_tiny_forward(const pde_tiny_desc *d, const float *u, const float *alpha_base,
+                     const float *channel_scaling, float *out, void *stream);
+/* g_alpha_base, g_channel_scaling: [C], overwritten.  gin may be NULL. */
+int pde_tiny_backward(const pde_tiny_desc *d, const float *u, const float *gout,
+                      const float *alpha_base, const float *channel_scaling, float *gin,
+                      float *g_alpha_base, float *g_channel_scaling,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDE_B200_H */

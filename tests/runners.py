@@ -149,3 +149,46 @@ def compare(got: Dict[str, np.ndarray], want: Dict[str, np.ndarray], keys=None) 
             continue
         res[k] = max(rel_l2(got[k], want[k]), rel_max(got[k], want[k]))
     return res
+
+
+# ---------------------------------------------------------------------------- CUDA product
+OUR_CLASS = {
+    "mnist": ("mnist_test", "DiffusionLayer"),
+    "fashion": ("fashion_mnist", "DiffusionLayer"),
+    "svhn": ("SVHN", "DiffusionLayer"),
+    "cifar10": ("cifar10", "EnhancedDiffusionLayer"),
+    "cifar2": ("cifar_2version", "LearnableDiffusionLayer"),
+    "emotion": ("emotion_recognition", "PDELayer"),
+    "tiny": ("tiny_imagenet", "ImprovedDiffusionLayer"),
+}
+
+
+def make_cuda_layer(c: K.Case, params=None, device="cuda"):
+    import importlib
+    import torch
+    import cnn_with_pde_b200  # noqa: F401
+    mod_name, cls = OUR_CLASS[c.kind]
+    mod = importlib.import_module("cnn_with_pde_b200." + mod_name)
+    layer = getattr(mod, cls)(**c.ctor)
+    params = params if params is not None else K.make_params(c)
+    sd = layer.state_dict()
+    for k, v in params.items():
+        sd[k] = torch.from_numpy(np.asarray(v)).reshape(sd[k].shape)
+    layer.load_state_dict(sd)
+    return layer.to(device)
+
+
+def run_cuda(c: K.Case, params=None, io=None, need_gin=True) -> Dict[str, np.ndarray]:
+    """Forward + backward of OUR module on cuda:0, through the C ABI."""
+    import torch
+    layer = make_cuda_layer(c, params)
+    u, g = io if io is not None else K.make_io(c)
+    x = torch.from_numpy(u).cuda().requires_grad_(need_gin)
+    y = layer(x)
+    y.backward(torch.from_numpy(g).cuda())
+    torch.cuda.synchronize()
+    out = {"y": y.detach().cpu().numpy(), "gin": x.grad.detach().cpu().numpy() if need_gin else None}
+    for k, p in layer.named_parameters():
+        if p.grad is not None:
+            out["g_" + k] = p.grad.detach().cpu().numpy()
+    return out

@@ -1,0 +1,112 @@
+"""Parity of the CUDA path (through the C ABI) against the reference fixtures and the oracle.
+
+Bar (BASELINE.json north_star): rel-err <= 1e-5 in fp32 for the output, grad_input and every
+parameter gradient -- measured both as rel-L2 and as max-abs / max-ref -- and no further from
+the fp64 oracle than the fp32 reference path is, plus 1e-5.
+"""
+import numpy as np
+import pytest
+
+from . import cases as K
+from . import golden_io, runners
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5  # north_star tolerance for fp32
+
+
+def _assert_close(got, want, tol, what):
+    errs = runners.compare(got, want)
+    assert set(errs) == {k for k, v in want.items() if v is not None}, (sorted(errs), sorted(want))
+    bad = {k: e for k, e in errs.items() if not e <= tol}
+    assert not bad, f"{what}: {bad}"
+    return errs
+
+
+@pytest.mark.parametrize("c", K.GOLDEN_CASES, ids=lambda c: c.name)
+def test_cuda_matches_reference_fixture(c):
+    params, io, ref = golden_io.load(c)
+    got = runners.run_cuda(c, params=params, io=io)
+    _assert_close(got, ref, TOL, c.name + " vs reference fixture")
+
+
+@pytest.mark.parametrize("c", K.CONFIG_CASES, ids=lambda c: c.name)
+def test_cuda_matches_oracle_at_config_shape(c):
+    params, io = K.make_params(c), K.make_io(c)
+    got = runners.run_cuda(c, params=params, io=io)
+    o32 = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+    o64 = runners.run_oracle(c, params=params, io=io, dtype=np.float64)
+    _assert_close(got, o32, TOL, c.name + " vs oracle fp32")
+    e_cuda = runners.compare(got, o64)
+    e_ref = runners.compare(o32, o64)
+    bad = {k: (e_cuda[k], e_ref[k]) for k in e_cuda if not e_cuda[k] <= e_ref[k] + TOL}
+    assert not bad, f"{c.name}: further from fp64 than the fp32 oracle + 1e-5: {bad}"
+
+
+@pytest.mark.parametrize("c", [K.CONFIG_CASES[1], K.CONFIG_CASES[3], K.CONFIG_CASES[7], K.CONFIG_CASES[9]],
+                         ids=lambda c: c.name)
+def test_cuda_without_grad_input(c):
+    """The layer is the first op of every reference model: grad_input is normally not needed."""
+    params, io = K.make_params(c), K.make_io(c)
+    got = runners.run_cuda(c, params=params, io=io, need_gin=False)
+    o32 = runners.run_oracle(c, params=params, io=io, dtype=np.float32, need_gin=False)
+    assert got["gin"] is None
+    _assert_close(got, o32, TOL, c.name)
+
+
+def test_cuda_edge_cases():
+    # batch of one (mnist_test.py:420 calls the layer on images[i:i+1]) and odd batches
+    for B in (1, 3, 5):
+        for kind, ctor in (("mnist", {}), ("cifar10", K.SCRIPT_INSTANCES["cifar10_pde3"]),
+                           ("svhn", dict(size=16, channels=3, num_steps=3)), ("emotion", {}),
+                           ("tiny", dict(size=16, channels=3, num_steps=2))):
+            c = K.case(f"edge_{kind}_b{B}", kind, B=B, **ctor)
+            params, io = K.make_params(c), K.make_io(c)
+            got = runners.run_cuda(c, params=params, io=io)
+            want = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+            _assert_close(got, want, TOL, c.name)
+    # zero steps: identity
+    c0 = K.case("edge_steps0", "cifar10", B=2, size=16, channels=3, num_steps=0)
+    got = runners.run_cuda(c0)
+    u, g = K.make_io(c0)
+    np.testing.assert_array_equal(got["y"], u)
+    np.testing.assert_array_equal(got["gin"], g)
+
+
+def test_cuda_exact_mode_for_large_coefficients():
+    """dt large enough that rebuilding sweep inputs would amplify rounding noise: the kernel must
+    switch to per-sweep checkpoints on its own (DESIGN.md 'reverse reconstruction')."""
+    c = K.case("fashion_dt5", "fashion", B=8, perturb=False, dt=5.0)
+    params, io = K.make_params(c), K.make_io(c)
+    got = runners.run_cuda(c, params=params, io=io)
+    o32 = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+    _assert_close(got, o32, TOL, c.name)
+
+
+def test_cuda_large_batch_properties():
+    """At a batch the oracle would take long for: linearity in u and the adjoint identity
+    <J v, w> = <v, J^T w> between our forward and backward kernels."""
+    import torch
+    c = K.case("prop", "cifar10", B=4096, **K.SCRIPT_INSTANCES["cifar10_pde1"])
+    layer = runners.make_cuda_layer(c)
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    v = torch.randn(c.B, *c.shape, device="cuda", generator=gen)
+    w = torch.randn(c.B, *c.shape, device="cuda", generator=gen)
+    x = v.clone().requires_grad_(True)
+    y = layer(x)
+    (gin,) = torch.autograd.grad(y, x, w)
+    lhs = (y.double() * w.double()).sum().item()
+    rhs = (v.double() * gin.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+    with torch.no_grad():
+        y2 = layer(2.5 * v)
+    assert runners.rel_l2(y2.cpu().numpy(), 2.5 * y.detach().cpu().numpy()) <= 1e-6
+
+
+def test_cuda_rejects_cpu_tensors_and_bad_shapes():
+    import torch
+    from cnn_with_pde_b200.mnist_test import DiffusionLayer
+    layer = DiffusionLayer().cuda()
+    with pytest.raises(RuntimeError):
+        layer(torch.zeros(2, 1, 28, 28))
+    with pytest.raises(ValueError):
+        layer(torch.zeros(2, 3, 28, 28, device="cuda"))

@@ -1,0 +1,483 @@
+#!/usr/bin/env python
+"""bench.py -- PDE-layer forward+backward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--layer NAME]
+
+One "step" = one forward + backward pass of the PDE layer over one batch of synthetic input
+(u, g_out ~ N(0,1), seeded).  Headline workload: fashion_mnist.DiffusionLayer (BASELINE.json
+configs[1]: 1x28x28, dt=0.3, 4 Strang steps) at a batch whose tensors exceed the L2 (126 MB),
+because at the script's batch of 256 the whole tensor (0.8 MB) sits in L2 and a call is launch
+latency; the config-batch latency is reported beside it.  Unit: cell-updates = B*C*H*W*num_steps
+per step.  Under torchrun every rank runs its own batch (weak scaling; the only exchange is the
+all-reduce of the coefficient gradients) and rank 0 prints ONE JSON line.
+
+--impl reference times the CPU restatement (oracle/, C + OpenMP on all host cores; the
+reference itself is pure Python and does not travel to the GPU box) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pde_layer_fwd_bwd_cell_updates_per_s"
+UNIT = "Gcell-updates/s"
+
+# layer -> (kind, ctor kwargs, roofline-size batch (one fp32 tensor ~0.8-1 GB), script batch)
+LAYERS = {
+    "fashion": ("fashion", dict(), 262144, 256),
+    "mnist": ("mnist", dict(), 262144, 64),
+    "cifar10_pde1": ("cifar10", dict(size=32, channels=3, dt=0.001, num_steps=5, dx=1.0, dy=1.0), 65536, 512),
+    "cifar10_pde2": ("cifar10", dict(size=32, channels=3, dt=0.002, num_steps=8, dx=2.0, dy=2.0), 65536, 512),
+    "cifar2_diffusion1": ("cifar2", dict(size=32, channels=3, dt=0.001, num_steps=8), 65536, 512),
+    "svhn": ("svhn", dict(size=32, channels=3), 65536, 256),
+    "emotion": ("emotion", dict(Nx=48, Ny=48), 98304, 64),
+    "tiny": ("tiny", dict(size=64, channels=3, num_steps=1, use_implicit=False), 16384, 32),
+}
+
+
+def _steps_of(kind, ctor):
+    if kind == "emotion":
+        return int(ctor.get("T", 0.01) / ctor.get("dt", 0.001))
+    dflt = {"fashion": 4, "tiny": 1}.get(kind, 10)
+    return ctor.get("num_steps", dflt)
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _profile_traffic(layer):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(layer)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index=0, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+            return self
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1.0)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ b200
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tests import cases as K
+    from tests import runners
+    import cnn_with_pde_b200 as P
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    kind, ctor, big_b, script_b = LAYERS[args.layer]
+    B = args.batch or big_b
+    c = K.case("bench_" + args.layer, kind, B=B, perturb=False, **ctor)
+    C, H, W = c.shape
+    nsteps = _steps_of(kind, ctor)
+    cells = B * C * H * W
+    layer = runners.make_cuda_layer(c, device=dev)
+    params = [p for p in layer.parameters()]
+    nparam = sum(p.numel() for p in params if p.requires_grad)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    u = torch.randn(B, C, H, W, device=dev, generator=gen)
+    g = torch.randn(B, C, H, W, device=dev, generator=gen)
+    info = P._cabi.device_info()
+
+    def grads():
+        return [p.grad for p in params if p.grad is not None]
+
+    def step(x):
+        for p in params:
+            p.grad = None
+        y = layer(x)
+        y.backward(g)
+        if world > 1:
+            flat = torch.cat([t.reshape(-1) for t in grads()])
+            dist.all_reduce(flat)
+        return y
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- kernel-only (HBM-resident)
+    x = u.clone().requires_grad_(True)
+    for _ in range(max(args.warmup, 3)):
+        step(x)
+    sync_all()
+    sampler = ClockSampler(index=local).start() if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * cells * nsteps / (ms_per_step * 1e-3) / 1e9
+
+    # ----------------------------------------- per-kernel timing through the C ABI (roofline)
+    def time_phase(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    n_k = max(5, min(args.steps, 20))
+    with torch.no_grad():
+        fwd_ms = time_phase(lambda: layer(u), n_k)
+    y = layer(x)
+    bwd_ms = time_phase(lambda: torch.autograd.grad(y, [x] + [p for p in params if p.requires_grad], g,
+                                                    retain_graph=True, allow_unused=True), n_k)
+    xn = u.clone()  # no grad_input: what real training needs (the layer is the first op)
+    yn = layer(xn)
+    bwd_nogin_ms = time_phase(lambda: torch.autograd.grad(yn, [p for p in params if p.requires_grad], g,
+                                                          retain_graph=True, allow_unused=True), n_k)
+    peak, peak_src = _peaks()
+    bwd_bytes = 12 * cells + 4 * nparam       # read u, read g_out, write g_in, write coefficient grads
+    fwd_bytes = 8 * cells + 4 * nparam        # read u, write out, read coefficient maps
+    bwd_gbs = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+    fwd_gbs = fwd_bytes / (fwd_ms * 1e-3) / 1e9
+
+    # ---------------------------------------------------------------- end to end (host buffers)
+    # Per step: H2D of the step's input batch from pinned memory (chunked, copy stream overlaps
+    # compute), forward + backward through the nn.Module, D2H of the coefficient gradients.
+    # g_out stays on the device: in training it is produced there by the classifier's backward.
+    nchunk = 8 if B >= 8 * 1024 else 1
+    cb = (B + nchunk - 1) // nchunk
+    host_u = torch.empty((B, C, H, W), dtype=torch.float32).pin_memory()
+    host_u.copy_(u)
+    host_g = torch.empty(nparam, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_bufs = [torch.empty((cb, C, H, W), device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_step():
+        for p in params:
+            p.grad = None
+        main = torch.cuda.current_stream()
+        for i in range(nchunk):
+            lo, hi = i * cb, min(B, (i + 1) * cb)
+            buf = dev_bufs[i % 2][: hi - lo]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[i % 2])
+                buf.copy_(host_u[lo:hi], non_blocking=True)
+                ready[i % 2].record(copy_stream)
+            main.wait_event(ready[i % 2])
+            yy = layer(buf)
+            yy.backward(g[lo:hi])
+            freed[i % 2].record(main)
+        flat = torch.cat([t.reshape(-1) for t in grads()])
+        if world > 1:
+            dist.all_reduce(flat)
+        host_g.copy_(flat, non_blocking=True)
+
+    for ev in freed:
+        ev.record(torch.cuda.current_stream())
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    k_e2e = max(3, min(args.steps, 10))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(k_e2e):
+        e2e_step()
+    b.record()
+    sync_all()
+    t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / k_e2e
+    e2e_value = world * cells * nsteps / (e2e_ms * 1e-3) / 1e9
+
+    # ------------------------------------------------------- latency at the script's own batch
+    cs = K.case("bench_small", kind, B=script_b, perturb=False, **ctor)
+    us = torch.randn(script_b, C, H, W, device=dev, generator=gen)
+    gs = torch.randn(script_b, C, H, W, device=dev, generator=gen)
+    xs = us.clone().requires_grad_(True)
+
+    def small():
+        for p in params:
+            p.grad = None
+        layer(xs).backward(gs)
+
+    small_ms = time_phase(small, 50)
+
+    out = None
+    if rank == 0:
+        cpu = cpu_baseline(args.layer, budget_s=args.cpu_seconds)
+        others = {}
+        if args.all_layers and world == 1:
+            del x, y, yn, xn, host_u, dev_bufs
+            torch.cuda.empty_cache()
+            for name in LAYERS:
+                if name != args.layer:
+                    try:
+                        others[name] = _quick_layer(name, dev, peak)
+                    except Exception as ex:  # keep the headline line even if a side measurement fails
+                        others[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        out = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{args.layer} PDE layer forward+backward (grad_input + coefficient grads), "
+                            f"{C}x{H}x{W}, num_steps={nsteps}, batch {B} per GPU "
+                            f"(script batch {script_b} scaled so every tensor ({cells * 4 / 1e6:.0f} MB) exceeds L2)",
+                "layer": args.layer, "batch_per_gpu": B, "shape": [C, H, W], "num_steps": nsteps,
+                "l2": f"inputs {cells * 4 / 1e6:.0f} MB each > L2 {info['l2_bytes'] / 1e6:.0f} MB; no flush needed",
+                "parallelism": f"dp{world} (batch sharded, coefficient grads all-reduced)" if world > 1 else "single GPU",
+            },
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": cells * 4,
+                    "d2h_bytes_per_step": nparam * 4, "ms_per_step": round(e2e_ms, 4), "chunks": nchunk,
+                    "note": "pinned host input -> H2D -> nn.Module forward+backward -> D2H coefficient grads; PCIe bound"},
+            "gpu_launches": (5 * args.steps),
+            "gpu_launches_per_step": {"tables_kernel": 1, "header_kernel": 1, "fwd_kernel": 1, "bwd_kernel": 1,
+                                      "finish_kernel": 1} if kind not in ("emotion", "tiny") else
+                                     {"fwd_kernel": 1, "bwd_kernel": 1, "finish_kernel": 1},
+            "roofline": {"bound": "hbm", "kernel": "backward (adjoint + coefficient-gradient reduction)",
+                         "achieved": round(bwd_gbs, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": round(bwd_gbs / peak, 4), "traffic": _profile_traffic(args.layer),
+                         "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": round(bwd_ms, 4)},
+            "roofline_fwd": {"bound": "hbm", "achieved": round(fwd_gbs, 1), "peak": peak, "unit": "GB/s",
+                             "frac": round(fwd_gbs / peak, 4), "algorithmic_bytes_per_launch": fwd_bytes,
+                             "ms_per_launch": round(fwd_ms, 4)},
+            "fwd_bwd_hbm_frac": round((fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak, 4),
+            "bwd_no_grad_input_ms": round(bwd_nogin_ms, 4),
+            "script_batch_latency_us": round(small_ms * 1e3, 1),
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "device": info,
+        }
+        if others:
+            out["other_layers"] = others
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def _quick_layer(name, dev, peak):
+    """fwd / bwd Gcell-updates/s and HBM fraction of another layer at its roofline batch."""
+    import torch
+    from tests import cases as K
+    from tests import runners
+    kind, ctor, big_b, _ = LAYERS[name]
+    c = K.case("q_" + name, kind, B=big_b, perturb=False, **ctor)
+    C, H, W = c.shape
+    nsteps = _steps_of(kind, ctor)
+    cells = big_b * C * H * W
+    layer = runners.make_cuda_layer(c, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(99)
+    u = torch.randn(big_b, C, H, W, device=dev, generator=gen)
+    g = torch.randn(big_b, C, H, W, device=dev, generator=gen)
+    params = [p for p in layer.parameters() if p.requires_grad]
+
+    def t(fn, n=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    with torch.no_grad():
+        fwd = t(lambda: layer(u))
+    x = u.clone().requires_grad_(True)
+    y = layer(x)
+    bwd = t(lambda: torch.autograd.grad(y, [x] + params, g, retain_graph=True, allow_unused=True))
+    tot = fwd + bwd
+    res = {"batch": big_b, "num_steps": nsteps, "fwd_ms": round(fwd, 3), "bwd_ms": round(bwd, 3),
+           "fwd_bwd_gcell_updates_per_s": round(cells * nsteps / (tot * 1e-3) / 1e9, 2),
+           "fwd_hbm_frac": round(8 * cells / (fwd * 1e-3) / 1e9 / peak, 4),
+           "bwd_hbm_frac": round(12 * cells / (bwd * 1e-3) / 1e9 / peak, 4),
+           "fwd_bwd_hbm_frac": round(20 * cells / (tot * 1e-3) / 1e9 / peak, 4)}
+    del u, g, x, y
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------- CPU baseline
+def _oracle_step(c, params, io, nthreads):
+    from tests import runners
+    import numpy as np
+    return runners.run_oracle(c, params=params, io=io, dtype=np.float32, nthreads=nthreads)
+
+
+def cpu_baseline(layer, budget_s=12.0, fixed_batch=None, reps=1):
+    """The C oracle (a port: the reference is Python and is not on this box) on all host cores,
+    forward + backward, on a bounded sample of the same workload."""
+    from tests import cases as K
+    kind, ctor, _, script_b = LAYERS[layer]
+    cores = os.cpu_count() or 1
+    nsteps = _steps_of(kind, ctor)
+    b = max(script_b, cores * 8)
+    c = K.case("cpu_" + layer, kind, B=b, perturb=False, **ctor)
+    params, io = K.make_params(c), K.make_io(c)
+    _oracle_step(c, params, io, cores)  # warm (library load, page faults)
+    t0 = time.perf_counter()
+    _oracle_step(c, params, io, cores)
+    dt = time.perf_counter() - t0
+    if fixed_batch is None:
+        scale = max(1.0, min(budget_s / max(dt, 1e-4), 4096.0))
+        b2 = int(b * scale) // cores * cores or b
+    else:
+        b2 = fixed_batch
+    c2 = K.case("cpu_" + layer, kind, B=b2, perturb=False, **ctor)
+    params, io = K.make_params(c2), K.make_io(c2)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        _oracle_step(c2, params, io, cores)
+        times.append(time.perf_counter() - t0)
+    dt2 = min(times)
+    C, H, W = c2.shape
+    val = b2 * C * H * W * nsteps / dt2 / 1e9
+    return {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle/pde_oracle.c (fp32, OpenMP x{cores}) forward+backward of {layer}, batch {b2}, "
+                      f"{dt2:.2f} s", "batch": b2, "seconds": round(dt2, 3)}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores, same metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from tests import cases as K
+    kind, ctor, big_b, script_b = LAYERS[args.layer]
+    cores = os.cpu_count() or 1
+    nsteps = _steps_of(kind, ctor)
+    probe = cpu_baseline(args.layer, budget_s=1.5)
+    # one step ~1.5 s of CPU work so that steps + warmup stay within a few minutes
+    b = probe["batch"]
+    c = K.case("ref_" + args.layer, kind, B=b, perturb=False, **ctor)
+    params, io = K.make_params(c), K.make_io(c)
+    for _ in range(args.warmup):
+        _oracle_step(c, params, io, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _oracle_step(c, params, io, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    C, H, W = c.shape
+    val = b * C * H * W * nsteps / dt / 1e9
+    sample = (f"oracle/pde_oracle.c (C port of the reference's CPU path, fp32, OpenMP x{cores}), "
+              f"forward+backward of {args.layer}, batch {b} per step")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.layer} PDE layer forward+backward, {C}x{H}x{W}, num_steps={nsteps}, "
+                               f"bounded sample: batch {b} per step on the host CPU", "layer": args.layer},
+        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layer", default="fashion", choices=sorted(LAYERS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: roofline-size batch of the layer)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--all-layers", type=int, default=1, help="also time the other layers (N=1 only)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -685,6 +685,12 @@ __global__ void bwd_kernel(const Args a) {
                     in_regs = true;
                 }
             }
+            // the skip epilogue needs the FINAL state (after the last channel coupling): park it
+            // in the x tile as rows
+            if (d.skip && in_regs && active) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) st_line<N, 0>(xt + p * WORDS, t, x[p]);
+            }
         }
         __syncwarp();
         // ------------------------------ phase 2: reverse
@@ -696,13 +702,9 @@ __global__ void bwd_kernel(const Args a) {
         bool xt_valid = false;
         if (d.skip) {
             // out = sig u0 + om uF:  dL/dw += sig' * sum gout (u0 - uF),  g <- om * gout
-            if (S > 0) {
-                if (last_ax == 0)
-                    ck_to_tile<N, PB, 0>(scratch + (size_t)(S - 1) * SLOT, lane, t, active, xt);
-                else
-                    ck_to_tile<N, PB, 1>(scratch + (size_t)(S - 1) * SLOT, lane, t, active, xt);
-                xt_valid = true;
-            }
+            // the x tile holds the final state uF (phase 1 left it there); without a channel
+            // coupling that is also the last checkpoint, so the first reversed step can reuse it
+            xt_valid = S > 0 && d.chan_op != 2;
             __syncwarp();
             float accw = 0.0f;
 #pragma unroll
@@ -712,7 +714,7 @@ __global__ void bwd_kernel(const Args a) {
 #pragma unroll
                     for (int q = 0; q < N / 4; ++q) {
                         float4 g4 = ld4<N, 0>(gt + p * WORDS, t, q);
-                        const float4 uf = (S > 0) ? ld4<N, 0>(xt + p * WORDS, t, q) : __ldg(u4 + q);
+                        const float4 uf = ld4<N, 0>(xt + p * WORDS, t, q);
                         const float4 u0 = __ldg(u4 + q);
                         accw = fmaf(g4.x, u0.x - uf.x, accw);
                         accw = fmaf(g4.y, u0.y - uf.y, accw);

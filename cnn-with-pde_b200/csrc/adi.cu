@@ -36,6 +36,7 @@ struct Header {
     float scale[PDE_MAX_SWEEPS];
     float t[PDE_MAX_SWEEPS];
     unsigned rmax_bits[PDE_MAX_SWEEPS];
+    int clamped[PDE_MAX_SWEEPS];   // 1 if any cell of sweep s sits outside the clamp interval
 };
 static_assert(sizeof(Header) <= kHeaderBytes, "header too large");
 
@@ -134,6 +135,9 @@ __global__ void tables_kernel(pde_adi_desc d, pde_adi_schedule sch, const float 
         rmax = fmaxf(rmax, fabsf(r));
     }
     atomicMax(&hdr->rmax_bits[s], __float_as_uint(rmax));
+    bool any_clamped = false;
+    for (int i = 0; i < N; ++i) any_clamped = any_clamped || msk[i] == 0.0f;
+    if (any_clamped) atomicOr(&hdr->clamped[s], 1);
 }
 
 __global__ void header_kernel(pde_adi_desc d, pde_adi_schedule sch, char *tables) {
@@ -293,7 +297,8 @@ __device__ __forceinline__ void thomas_solve(float (&x)[PB][N], const float4 *__
 //   U^T w = g:        w_i = g_i + e_{i-1} w_{i-1}
 //   L^T lambda = w:   lambda_i = inv_i (w_i + r_{i+1} lambda_{i+1})
 template <int N, int PB>
-__device__ __forceinline__ void thomas_solve_adjoint(float (&g)[PB][N], const float4 *__restrict__ tr,
+__device__ __forceinline__ void thomas_solve_adjoint(float (&g)[PB][N], float (&rr)[N],
+                                                     const float4 *__restrict__ tr,
                                                      const float4 *__restrict__ tinv,
                                                      const float4 *__restrict__ te) {
     float eprev = 0.0f;
@@ -323,6 +328,7 @@ __device__ __forceinline__ void thomas_solve_adjoint(float (&g)[PB][N], const fl
             for (int p = 0; p < PB; ++p)
                 g[p][i] = (i == N - 1) ? g[p][i] * ivs[k] : fmaf(rnext * ivs[k], g[p][i + 1], g[p][i] * ivs[k]);
             rnext = rvs[k];
+            rr[i] = rvs[k];
         }
     }
 }
@@ -330,6 +336,7 @@ __device__ __forceinline__ void thomas_solve_adjoint(float (&g)[PB][N], const fl
 struct Args {
     pde_adi_desc d;
     int S, sps, G, nitems, need_gin;
+    int dbg_table0;  // DEBUG ONLY (timing experiment): every sweep reads the tables of sweep 0
     const char *tables;
     const float *u, *gout, *chan, *skipw;
     float *out, *gin;
@@ -469,83 +476,81 @@ __device__ __forceinline__ void ck_to_tile(const float *slot, int lane, int t, b
     }
 }
 
-// One reversed sweep for the lines this lane owns.
-//   g tile: adjoint in place.  x tile: holds the sweep OUTPUT; if `rebuild`, it is overwritten
-//   with the sweep INPUT  x_in = (1 + eps) x - r * (L x).
+// One reversed sweep on the lines this lane holds IN REGISTERS (orientation AX).
+//   g: adjoint, solved in place.  x: the sweep OUTPUT; if `rebuild`, overwritten in place with
+//   the sweep INPUT  x_in = (1 + eps) x - r * (L x).
 //   Per-pixel gradient: v_i = sum_p lambda_i (L x)_i  ->  smoothing^T, clamp mask, weights
-//   (scale, scale * t) into the lane-private accumulator lines acc0 / acc1.
+//   (scale, scale * t) into the lane-private accumulator lines acc0 / acc1 (shared memory).
 template <int N, int PB, int AX>
-__device__ __forceinline__ void reverse_sweep(float *gt, float *xt, float *acc0, float *acc1, int t,
-                                              bool active, const Tables &T, size_t o, float scale, float tt,
-                                              float onepe, bool smooth, bool rebuild) {
-    constexpr int WORDS = Geo<N>::WORDS;
+__device__ __forceinline__ void reverse_sweep(float (&g)[PB][N], float (&x)[PB][N], float *acc0, float *acc1,
+                                              int t, bool active, const Tables &T, size_t o, float scale,
+                                              float tt, float onepe, bool smooth, bool rebuild, bool clamped) {
     const float4 *tr = reinterpret_cast<const float4 *>(T.r) + o;
     const float4 *tinv = reinterpret_cast<const float4 *>(T.inv) + o;
     const float4 *te = reinterpret_cast<const float4 *>(T.e) + o;
     const float4 *tm = reinterpret_cast<const float4 *>(T.msk) + o;
-    float g[PB][N];
-#pragma unroll
-    for (int p = 0; p < PB; ++p) ld_line<N, AX>(gt + p * WORDS, t, g[p]);
-    thomas_solve_adjoint<N, PB>(g, tr, tinv, te);
-    if (active) {
-#pragma unroll
-        for (int p = 0; p < PB; ++p) st_line<N, AX>(gt + p * WORDS, t, g[p]);
-    }
+    float rr[N];
+    thomas_solve_adjoint<N, PB>(g, rr, tr, tinv, te);
     float v[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = 0.0f;
 #pragma unroll
     for (int p = 0; p < PB; ++p) {
-        float x[N];
-        ld_line<N, AX>(xt + p * WORDS, t, x);
-        float xin[N];
-#pragma unroll
-        for (int q = 0; q < N / 4; ++q) {
-            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rebuild) rv = __ldg(tr + q * N);
-            const float rvs[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = 4 * q + k;
-                float lx;
-                if (i == 0)
-                    lx = x[1] - x[0];
-                else if (i == N - 1)
-                    lx = x[N - 2] - x[N - 1];
-                else
-                    lx = (x[i - 1] - x[i]) + (x[i + 1] - x[i]);
-                v[i] = fmaf(g[p][i], lx, v[i]);
-                xin[i] = fmaf(-rvs[k], lx, onepe * x[i]);
-            }
-        }
-        if (rebuild && active) st_line<N, AX>(xt + p * WORDS, t, xin);
-    }
-    // smoothing^T along the line (replicate padding puts the end taps back on the end cells)
-    float z[N];
-    if (smooth) {
-        const float third = 1.0f / 3.0f;
+        float prev = x[p][0];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const float lo = (i == 0) ? v[0] : v[i - 1];
-            const float hi = (i == N - 1) ? v[N - 1] : v[i + 1];
-            z[i] = ((lo + v[i]) + hi) * (third * scale);
+            const float cur = x[p][i];
+            float lx;
+            if (i == 0)
+                lx = x[p][1] - cur;
+            else if (i == N - 1)
+                lx = prev - cur;
+            else
+                lx = (prev - cur) + (x[p][i + 1] - cur);
+            v[i] = fmaf(g[p][i], lx, v[i]);
+            if (rebuild) x[p][i] = fmaf(-rr[i], lx, onepe * cur);
+            prev = cur;
+        }
+    }
+    // smoothing^T along the line (replicate padding puts the end taps back on the end cells)
+    if (smooth) {
+        const float k3 = scale * (1.0f / 3.0f);
+        float lo = v[0];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const float cur = v[i];
+            const float hi = (i == N - 1) ? cur : v[i + 1];
+            v[i] = ((lo + cur) + hi) * k3;
+            lo = cur;
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < N; ++i) z[i] = v[i] * scale;
+        for (int i = 0; i < N; ++i) v[i] *= scale;
     }
     if (active) {
 #pragma unroll
         for (int q = 0; q < N / 4; ++q) {
-            const float4 m = __ldg(tm + q * N);
+            float z0 = v[4 * q], z1 = v[4 * q + 1], z2 = v[4 * q + 2], z3 = v[4 * q + 3];
+            if (clamped) {
+                const float4 m = __ldg(tm + q * N);
+                z0 *= m.x; z1 *= m.y; z2 *= m.z; z3 *= m.w;
+            }
             float4 a0 = ld4<N, AX>(acc0, t, q), a1 = ld4<N, AX>(acc1, t, q);
-            const float z0 = m.x * z[4 * q], z1 = m.y * z[4 * q + 1], z2 = m.z * z[4 * q + 2], z3 = m.w * z[4 * q + 3];
             a0.x += z0; a0.y += z1; a0.z += z2; a0.w += z3;
             a1.x = fmaf(tt, z0, a1.x); a1.y = fmaf(tt, z1, a1.y); a1.z = fmaf(tt, z2, a1.z); a1.w = fmaf(tt, z3, a1.w);
             st4<N, AX>(acc0, t, q, a0);
             st4<N, AX>(acc1, t, q, a1);
         }
     }
+}
+
+// checkpoint slot -> registers (the slot is stored in the orientation the lane held it in)
+template <int N, int PB>
+__device__ __forceinline__ void ck_load(const float *slot, int lane, float (&x)[PB][N]) {
+#pragma unroll
+    for (int p = 0; p < PB; ++p)
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[p][i] = slot[(p * N + i) * 32 + lane];
 }
 
 // Adjoint of a channel op on the group's g tiles (rows), using the op's INPUT state in the x
@@ -694,17 +699,17 @@ __global__ void bwd_kernel(const Args a) {
         }
         __syncwarp();
         // ------------------------------ phase 2: reverse
+        // g and x travel in registers; the tiles are only used to change orientation (and for the
+        // cross-channel ops).  g_ax / x_ax: orientation held in registers (0 rows, 1 columns) or
+        // -1 when the current value lives in the tile.
 #pragma unroll
         for (int p = 0; p < PB; ++p) {
             const bool valid = b0 + p < d.B;
             plane_to_tile<N>(a.gout + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, gt + p * WORDS, lane, valid);
         }
-        bool xt_valid = false;
         if (d.skip) {
-            // out = sig u0 + om uF:  dL/dw += sig' * sum gout (u0 - uF),  g <- om * gout
-            // the x tile holds the final state uF (phase 1 left it there); without a channel
-            // coupling that is also the last checkpoint, so the first reversed step can reuse it
-            xt_valid = S > 0 && d.chan_op != 2;
+            // out = sig u0 + om uF:  dL/dw += sig' * sum gout (u0 - uF),  g <- om * gout.
+            // The x tile still holds the final state uF from phase 1.
             __syncwarp();
             float accw = 0.0f;
 #pragma unroll
@@ -728,44 +733,90 @@ __global__ void bwd_kernel(const Args a) {
             gw += accw;
         }
         __syncwarp();
+        float g[PB][N], x[PB][N];
+        int g_ax = -1, x_ax = -1;
+        auto g_store = [&](int ax) {
+            if (active) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) {
+                    if (ax == 0) st_line<N, 0>(gt + p * WORDS, t, g[p]);
+                    else st_line<N, 1>(gt + p * WORDS, t, g[p]);
+                }
+            }
+        };
+        auto g_load = [&](int ax) {
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                if (ax == 0) ld_line<N, 0>(gt + p * WORDS, t, g[p]);
+                else ld_line<N, 1>(gt + p * WORDS, t, g[p]);
+            }
+        };
+        auto x_store = [&](int ax) {
+            if (active) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) {
+                    if (ax == 0) st_line<N, 0>(xt + p * WORDS, t, x[p]);
+                    else st_line<N, 1>(xt + p * WORDS, t, x[p]);
+                }
+            }
+        };
+        auto x_load = [&](int ax) {
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                if (ax == 0) ld_line<N, 0>(xt + p * WORDS, t, x[p]);
+                else ld_line<N, 1>(xt + p * WORDS, t, x[p]);
+            }
+        };
         for (int step = d.steps - 1; step >= 0; --step) {
             const int sl = step * sps + sps - 1;
-            if (!xt_valid) {
-                if (last_ax == 0)
-                    ck_to_tile<N, PB, 0>(scratch + (size_t)sl * SLOT, lane, t, active, xt);
-                else
-                    ck_to_tile<N, PB, 1>(scratch + (size_t)sl * SLOT, lane, t, active, xt);
+            // state after the last sweep of this step: straight from the checkpoint into registers
+            ck_load<N, PB>(scratch + (size_t)sl * SLOT, lane, x);
+            x_ax = last_ax;
+            if (d.chan_op == 2) {
+                // adjoint of the post-step coupling works on the group's tiles (rows)
+                if (g_ax >= 0) { g_store(g_ax); g_ax = -1; }
+                x_store(x_ax);
                 __syncwarp();
+                chan_adjoint<N, PB>(ggt, gxt, C, c, group, a.chan, t, active, gm);
             }
-            xt_valid = false;
-            if (d.chan_op == 2) chan_adjoint<N, PB>(ggt, gxt, C, c, group, a.chan, t, active, gm);
             for (int k = sps - 1; k >= 0; --k) {
                 const int s = step * sps + k;
                 const int ax = sweep_axis(k);
                 if (exact && k != sps - 1) {
-                    if (ax == 0)
-                        ck_to_tile<N, PB, 0>(scratch + (size_t)s * SLOT, lane, t, active, xt);
-                    else
-                        ck_to_tile<N, PB, 1>(scratch + (size_t)s * SLOT, lane, t, active, xt);
-                    __syncwarp();
+                    ck_load<N, PB>(scratch + (size_t)s * SLOT, lane, x);
+                    x_ax = ax;
                 }
-                const size_t o = ((size_t)s * C + c) * (N / 4) * N + t;
+                if (g_ax != ax) {
+                    if (g_ax >= 0) g_store(g_ax);
+                    __syncwarp();
+                    g_load(ax);
+                    g_ax = ax;
+                }
+                if (x_ax != ax) {
+                    if (x_ax >= 0) x_store(x_ax);
+                    __syncwarp();
+                    x_load(ax);
+                    x_ax = ax;
+                }
+                const size_t o = ((size_t)(a.dbg_table0 ? 0 : s) * C + c) * (N / 4) * N + t;
                 const float scale = T.hdr->scale[s], tt = T.hdr->t[s];
+                const bool clamped = T.hdr->clamped[s] != 0;
                 const bool rebuild = !exact && k > 0;
                 if (ax == 0)
-                    reverse_sweep<N, PB, 0>(gt, xt, acc, acc + WORDS, t, active, T, o, scale, tt, onepe, smooth, rebuild);
+                    reverse_sweep<N, PB, 0>(g, x, acc, acc + WORDS, t, active, T, o, scale, tt, onepe, smooth, rebuild, clamped);
                 else
-                    reverse_sweep<N, PB, 1>(gt, xt, acc + 2 * WORDS, acc + 3 * WORDS, t, active, T, o, scale, tt, onepe, smooth, rebuild);
-                __syncwarp();
+                    reverse_sweep<N, PB, 1>(g, x, acc + 2 * WORDS, acc + 3 * WORDS, t, active, T, o, scale, tt, onepe, smooth, rebuild, clamped);
             }
             if (d.chan_op == 1) {
-                // input of the mix = state before this step = checkpoint of the previous step (or u)
+                // adjoint of the pre-step mix: needs g (rows) and the mix INPUT = state before this
+                // step = checkpoint of the previous step (or u) in the group's tiles
+                g_store(g_ax);
+                g_ax = -1;
                 if (step > 0) {
                     if (last_ax == 0)
                         ck_to_tile<N, PB, 0>(scratch + (size_t)(step * sps - 1) * SLOT, lane, t, active, xt);
                     else
                         ck_to_tile<N, PB, 1>(scratch + (size_t)(step * sps - 1) * SLOT, lane, t, active, xt);
-                    xt_valid = true;
                 } else {
 #pragma unroll
                     for (int p = 0; p < PB; ++p) {
@@ -777,6 +828,8 @@ __global__ void bwd_kernel(const Args a) {
                 chan_adjoint<N, PB>(ggt, gxt, C, c, group, a.chan, t, active, gm);
             }
         }
+        if (g_ax >= 0) g_store(g_ax);
+        __syncwarp();
         if (a.need_gin) {
 #pragma unroll
             for (int p = 0; p < PB; ++p) {
@@ -870,8 +923,8 @@ struct BwdPlan {
 };
 
 static int bwd_pb(const pde_adi_desc *d) {
-    int pb = env_int("PDE_B200_BWD_PB", 1);
-    return pb == 2 ? 2 : 1;
+    int pb = env_int("PDE_B200_BWD_PB", 2);
+    return pb == 1 ? 1 : 2;
 }
 
 static int plan_bwd(const pde_adi_desc *d, BwdPlan *p) {
@@ -1045,6 +1098,7 @@ extern "C" int pde_adi_backward(const pde_adi_desc *d, const void *tables, const
     a.G = p.G;
     a.nitems = p.nitems;
     a.need_gin = gin != nullptr;
+    a.dbg_table0 = env_int("PDE_DEBUG_TABLE0", 0);
     a.tables = static_cast<const char *>(tables);
     a.u = u; a.gout = gout; a.chan = chan; a.skipw = skipw; a.gin = gin;
     a.scratch = ws;

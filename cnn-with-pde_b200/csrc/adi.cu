@@ -21,6 +21,9 @@
 //                       would amplify rounding noise (device-computed bound), the kernel
 //                       switches to exact per-sweep checkpoints instead.
 //   * adi_finish_kernel sums the per-warp gradient partials in double (deterministic).
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pde {
@@ -265,6 +268,27 @@ __device__ __forceinline__ void mix_rows(const float *group_tiles, int tiles_per
     }
 }
 
+// Software prefetch (no register destination): pull the next sweep's table rows into L1 / the next
+// item's planes into L2 while the current sweep computes.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int N>
+__device__ __forceinline__ void prefetch_tables(const float4 *ta, const float4 *tb, const float4 *tc) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+        prefetch_l1(ta + q * N);
+        prefetch_l1(tb + q * N);
+        if (tc) prefetch_l1(tc + q * N);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void prefetch_plane_l2(const float *g, int lane) {
+#pragma unroll
+    for (int off = lane * 32; off < N * N; off += 32 * 32) prefetch_l2(g + off);
+}
+
 // ------------------------------------------------------------------------------------------
 // Thomas solve of (A + eps I) x = d for the PB lines a lane holds (same coefficients for all
 // PB: the factorisation is batch independent).  With inv = 1/pivot and e = r/pivot = -c*:
@@ -274,9 +298,14 @@ template <int N, int PB>
 __device__ __forceinline__ void thomas_solve(float (&x)[PB][N], const float4 *__restrict__ tinv,
                                              const float4 *__restrict__ te) {
     float e[N];
+    float4 iv_n = __ldg(tinv), ev_n = __ldg(te);
 #pragma unroll
     for (int q = 0; q < N / 4; ++q) {
-        const float4 iv = __ldg(tinv + q * N), ev = __ldg(te + q * N);
+        const float4 iv = iv_n, ev = ev_n;
+        if (q + 1 < N / 4) {   // the next chunk's coefficients are in flight while this one computes
+            iv_n = __ldg(tinv + (q + 1) * N);
+            ev_n = __ldg(te + (q + 1) * N);
+        }
         const float ivs[4] = {iv.x, iv.y, iv.z, iv.w}, evs[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -336,7 +365,7 @@ __device__ __forceinline__ void thomas_solve_adjoint(float (&g)[PB][N], float (&
 struct Args {
     pde_adi_desc d;
     int S, sps, G, nitems, need_gin;
-    int dbg_table0;  // DEBUG ONLY (timing experiment): every sweep reads the tables of sweep 0
+    int tile_sets, tmem_cols;
     const char *tables;
     const float *u, *gout, *chan, *skipw;
     float *out, *gin;
@@ -456,13 +485,21 @@ __global__ void fwd_kernel(const Args a) {
 // backward
 // ------------------------------------------------------------------------------------------
 
-// checkpoint a lane's lines: scratch[(p*N + i)*32 + lane] (coalesced 128 B per element index)
+// checkpoint a lane's lines: scratch[(p*N + i)*32 + lane] (coalesced 128 B per element index);
+// a slot is read back in the orientation it was written in
 template <int N, int PB>
 __device__ __forceinline__ void ck_store(float *slot, int lane, const float (&x)[PB][N]) {
 #pragma unroll
     for (int p = 0; p < PB; ++p)
 #pragma unroll
         for (int i = 0; i < N; ++i) slot[(p * N + i) * 32 + lane] = x[p][i];
+}
+template <int N, int PB>
+__device__ __forceinline__ void ck_load(const float *slot, int lane, float (&x)[PB][N]) {
+#pragma unroll
+    for (int p = 0; p < PB; ++p)
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[p][i] = slot[(p * N + i) * 32 + lane];
 }
 template <int N, int PB, int AX>
 __device__ __forceinline__ void ck_to_tile(const float *slot, int lane, int t, bool active, float *tiles) {
@@ -476,40 +513,97 @@ __device__ __forceinline__ void ck_to_tile(const float *slot, int lane, int t, b
     }
 }
 
-// One reversed sweep on the lines this lane holds IN REGISTERS (orientation AX).
-//   g: adjoint, solved in place.  x: the sweep OUTPUT; if `rebuild`, overwritten in place with
-//   the sweep INPUT  x_in = (1 + eps) x - r * (L x).
-//   Per-pixel gradient: v_i = sum_p lambda_i (L x)_i  ->  smoothing^T, clamp mask, weights
-//   (scale, scale * t) into the lane-private accumulator lines acc0 / acc1 (shared memory).
-template <int N, int PB, int AX>
-__device__ __forceinline__ void reverse_sweep(float (&g)[PB][N], float (&x)[PB][N], float *acc0, float *acc1,
-                                              int t, bool active, const Tables &T, size_t o, float scale,
-                                              float tt, float onepe, bool smooth, bool rebuild, bool clamped) {
+// Per-pixel gradient accumulators live in TMEM: 128 columns per warp = {A0, A1, B0, B1} x 32,
+// lane = line.  acc0 += z, acc1 += t * z for the kind (alpha / beta) of the sweep.
+template <int N>
+__device__ __forceinline__ void tmem_accumulate(uint32_t tacc, const float (&z)[N], float tt) {
+    float a[32];
+    tmem_wait_st();
+    tmem_ld16(tacc, a);
+    tmem_ld16(tacc + 16, a + 16);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i] += z[i];
+    tmem_st16(tacc, a);
+    tmem_st16(tacc + 16, a + 16);
+    tmem_ld16(tacc + 32, a);
+    tmem_ld16(tacc + 48, a + 16);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i] = fmaf(tt, z[i], a[i]);
+    tmem_st16(tacc + 32, a);
+    tmem_st16(tacc + 48, a + 16);
+}
+
+// One reversed sweep on the lines this lane holds in registers (either orientation).
+//   g: adjoint; solved in place through the factorisation A = L U:
+//        U^T w = g:        w_i = g_i + e_{i-1} w_{i-1}
+//        L^T lambda = w:   lambda_i = inv_i (w_i + r_{i+1} lambda_{i+1})
+//   x: the sweep OUTPUT; inside the back-substitution loop, while lambda_i is fresh,
+//        (L x)_i, v_i += lambda_i (L x)_i, and (if `rebuild`) the sweep INPUT
+//        x_in,i = (1 + eps) x_i - r_i (L x)_i   written in place.
+//   v -> smoothing^T -> clamp mask -> TMEM accumulators of this sweep's kind.
+template <int N, int PB>
+__device__ __forceinline__ void reverse_sweep(float (&g)[PB][N], float (&x)[PB][N], uint32_t tacc,
+                                              const Tables &T, size_t o, float scale, float tt, float onepe,
+                                              bool smooth, bool rebuild, bool clamped) {
     const float4 *tr = reinterpret_cast<const float4 *>(T.r) + o;
     const float4 *tinv = reinterpret_cast<const float4 *>(T.inv) + o;
     const float4 *te = reinterpret_cast<const float4 *>(T.e) + o;
-    const float4 *tm = reinterpret_cast<const float4 *>(T.msk) + o;
-    float rr[N];
-    thomas_solve_adjoint<N, PB>(g, rr, tr, tinv, te);
+    float eprev = 0.0f;
+    float4 ev_n = __ldg(te);
+    // the back-substitution's first coefficients are requested before the forward pass starts
+    float4 iv_n = __ldg(tinv + (N / 4 - 1) * N), rv_n = __ldg(tr + (N / 4 - 1) * N);
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+        const float4 ev = ev_n;
+        if (q + 1 < N / 4) ev_n = __ldg(te + (q + 1) * N);
+        const float evs[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * q + k;
+            if (i > 0) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) g[p][i] = fmaf(eprev, g[p][i - 1], g[p][i]);
+            }
+            eprev = evs[k];
+        }
+    }
     float v[N];
+    float xnext[PB];   // value of x_{i+1} before it was rebuilt
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = 0.0f;
+    for (int p = 0; p < PB; ++p) xnext[p] = 0.0f;
+    float rnext = 0.0f;
 #pragma unroll
-    for (int p = 0; p < PB; ++p) {
-        float prev = x[p][0];
+    for (int q = N / 4 - 1; q >= 0; --q) {
+        const float4 iv = iv_n, rv = rv_n;
+        if (q > 0) {
+            iv_n = __ldg(tinv + (q - 1) * N);
+            rv_n = __ldg(tr + (q - 1) * N);
+        }
+        const float ivs[4] = {iv.x, iv.y, iv.z, iv.w}, rvs[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const float cur = x[p][i];
-            float lx;
-            if (i == 0)
-                lx = x[p][1] - cur;
-            else if (i == N - 1)
-                lx = prev - cur;
-            else
-                lx = (prev - cur) + (x[p][i + 1] - cur);
-            v[i] = fmaf(g[p][i], lx, v[i]);
-            if (rebuild) x[p][i] = fmaf(-rr[i], lx, onepe * cur);
-            prev = cur;
+        for (int k = 3; k >= 0; --k) {
+            const int i = 4 * q + k;
+            float vi = 0.0f;
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                const float lam = (i == N - 1) ? g[p][i] * ivs[k] : fmaf(rnext * ivs[k], g[p][i + 1], g[p][i] * ivs[k]);
+                g[p][i] = lam;
+                const float cur = x[p][i];
+                float lx;
+                if (i == N - 1)
+                    lx = x[p][N - 2] - cur;
+                else if (i == 0)
+                    lx = xnext[p] - cur;
+                else
+                    lx = (x[p][i - 1] - cur) + (xnext[p] - cur);
+                vi = fmaf(lam, lx, vi);
+                if (rebuild) x[p][i] = fmaf(-rvs[k], lx, onepe * cur);
+                xnext[p] = cur;
+            }
+            v[i] = vi;
+            rnext = rvs[k];
         }
     }
     // smoothing^T along the line (replicate padding puts the end taps back on the end cells)
@@ -527,30 +621,15 @@ __device__ __forceinline__ void reverse_sweep(float (&g)[PB][N], float (&x)[PB][
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] *= scale;
     }
-    if (active) {
+    if (clamped) {
+        const float4 *tm = reinterpret_cast<const float4 *>(T.msk) + o;
 #pragma unroll
         for (int q = 0; q < N / 4; ++q) {
-            float z0 = v[4 * q], z1 = v[4 * q + 1], z2 = v[4 * q + 2], z3 = v[4 * q + 3];
-            if (clamped) {
-                const float4 m = __ldg(tm + q * N);
-                z0 *= m.x; z1 *= m.y; z2 *= m.z; z3 *= m.w;
-            }
-            float4 a0 = ld4<N, AX>(acc0, t, q), a1 = ld4<N, AX>(acc1, t, q);
-            a0.x += z0; a0.y += z1; a0.z += z2; a0.w += z3;
-            a1.x = fmaf(tt, z0, a1.x); a1.y = fmaf(tt, z1, a1.y); a1.z = fmaf(tt, z2, a1.z); a1.w = fmaf(tt, z3, a1.w);
-            st4<N, AX>(acc0, t, q, a0);
-            st4<N, AX>(acc1, t, q, a1);
+            const float4 m = __ldg(tm + q * N);
+            v[4 * q] *= m.x; v[4 * q + 1] *= m.y; v[4 * q + 2] *= m.z; v[4 * q + 3] *= m.w;
         }
     }
-}
-
-// checkpoint slot -> registers (the slot is stored in the orientation the lane held it in)
-template <int N, int PB>
-__device__ __forceinline__ void ck_load(const float *slot, int lane, float (&x)[PB][N]) {
-#pragma unroll
-    for (int p = 0; p < PB; ++p)
-#pragma unroll
-        for (int i = 0; i < N; ++i) x[p][i] = slot[(p * N + i) * 32 + lane];
+    tmem_accumulate<N>(tacc, v, tt);
 }
 
 // Adjoint of a channel op on the group's g tiles (rows), using the op's INPUT state in the x
@@ -586,29 +665,56 @@ __device__ __forceinline__ void chan_adjoint(float *ggt, float *gxt, int C, int 
     __syncwarp();
 }
 
-template <int N, int PB>
-__global__ void bwd_kernel(const Args a) {
+// RB = resident blocks the register allocation must allow for a 192-thread block:
+// 1 -> 255 registers, 2 -> 168, 3 -> 96-112.
+template <int N, int PB, int RB>
+__global__ void __launch_bounds__(192, RB) bwd_kernel(const Args a) {
     constexpr int WORDS = Geo<N>::WORDS;
+    constexpr int SLOT = PB * N * 32;
     extern __shared__ __align__(16) float smem[];
+    __shared__ uint32_t tmem_slot;
     const pde_adi_desc &d = a.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     const int C = d.C, group = warp / C, c = warp % C;
     const bool active = lane < N;
     const int t = active ? lane : N - 1;
-    // shared layout: x tiles [G][C][PB], g tiles [G][C][PB], accumulators [warps][4]
+    // Shared memory is only a transposition medium: one set of PB tiles per warp, two sets when a
+    // cross-channel op (or the skip epilogue) needs the state and the adjoint side by side.
+    const bool shared_set = a.tile_sets == 1;
     float *gxt = smem + (size_t)group * C * PB * WORDS;
-    float *ggt = smem + (size_t)a.G * C * PB * WORDS + (size_t)group * C * PB * WORDS;
+    float *ggt = (shared_set ? smem : smem + (size_t)nwarps * PB * WORDS) + (size_t)group * C * PB * WORDS;
     float *xt = gxt + (size_t)c * PB * WORDS, *gt = ggt + (size_t)c * PB * WORDS;
-    float *acc = smem + (size_t)2 * a.G * C * PB * WORDS + (size_t)warp * 4 * WORDS;
-    for (int i = lane; i < 4 * WORDS; i += 32) acc[i] = 0.0f;
-    __syncwarp();
+
+    // TMEM: 128 columns per warp, lane quadrant = warp % 4
+    if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)a.tmem_cols);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tbase = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+    {
+        float z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0.0f;
+#pragma unroll
+        for (int col = 0; col < 128; col += 16) tmem_st16(tbase + col, z);
+        tmem_wait_st();
+    }
+
     const Tables T = split_tables(a.tables, d);
     const bool exact = T.hdr->mode_exact != 0;
+    // per-sweep scalars (dt/h^2, t, "some cell clamped") are read by every warp every sweep
+    __shared__ float h_scale[PDE_MAX_SWEEPS], h_t[PDE_MAX_SWEEPS];
+    __shared__ int h_clamped[PDE_MAX_SWEEPS];
+    for (int i = threadIdx.x; i < a.S; i += blockDim.x) {
+        h_scale[i] = T.hdr->scale[i];
+        h_t[i] = T.hdr->t[i];
+        h_clamped[i] = T.hdr->clamped[i];
+    }
+    __syncthreads();
     const size_t plane = (size_t)N * N;
     const int wg = blockIdx.x * nwarps + warp;
-    float *scratch = a.scratch + (size_t)wg * a.S * (PB * N * 32);
-    constexpr int SLOT = PB * N * 32;
+    float *scratch = a.scratch + (size_t)wg * a.S * SLOT;
     float sig = 0.0f;
     if (d.skip) sig = 1.0f / (1.0f + expf(-__ldg(a.skipw)));
     const float om = 1.0f - sig;
@@ -616,11 +722,29 @@ __global__ void bwd_kernel(const Args a) {
     const bool smooth = d.smooth != 0;
     float gm[PDE_MAX_CHANNELS] = {0.f, 0.f, 0.f, 0.f};
     float gw = 0.0f;
-    const int sps = a.sps, S = a.S;
+    const int sps = a.sps;
     const int last_ax = (sps == 3) ? 0 : 1;  // orientation of the state after the last sweep of a step
 
     for (int item = blockIdx.x * a.G + group; item < a.nitems; item += gridDim.x * a.G) {
         const int b0 = item * PB;
+        float x[PB][N];
+        int x_ax = -1;   // orientation of x in registers (0 rows, 1 columns), -1: the tile holds it
+        auto x_store = [&](int ax) {
+            if (active) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) {
+                    if (ax == 0) st_line<N, 0>(xt + p * WORDS, t, x[p]);
+                    else st_line<N, 1>(xt + p * WORDS, t, x[p]);
+                }
+            }
+        };
+        auto x_load = [&](int ax) {
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                if (ax == 0) ld_line<N, 0>(xt + p * WORDS, t, x[p]);
+                else ld_line<N, 1>(xt + p * WORDS, t, x[p]);
+            }
+        };
         // ------------------------------ phase 1: forward trajectory with checkpoints
 #pragma unroll
         for (int p = 0; p < PB; ++p) {
@@ -628,89 +752,101 @@ __global__ void bwd_kernel(const Args a) {
             plane_to_tile<N>(a.u + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, xt + p * WORDS, lane, valid);
         }
         __syncwarp();
-        {
-            float x[PB][N];
-            bool in_regs = false;
-            for (int step = 0; step < d.steps; ++step) {
-                const int s0 = step * sps;
-                if (d.chan_op == 1) {
-                    if (in_regs && active) {
-#pragma unroll
-                        for (int p = 0; p < PB; ++p) st_line<N, 0>(xt + p * WORDS, t, x[p]);
-                    }
-                    group_sync(C, group);
-                    mix_rows<N, PB>(gxt, PB, C, a.chan + c * C, 1, t, x);
-                    group_sync(C, group);
-                } else if (!in_regs) {
-#pragma unroll
-                    for (int p = 0; p < PB; ++p) ld_line<N, 0>(xt + p * WORDS, t, x[p]);
-                }
-                {
-                    const size_t o = ((size_t)s0 * C + c) * (N / 4) * N + t;
-                    thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
-                                        reinterpret_cast<const float4 *>(T.e) + o);
-                }
-                if (exact) ck_store<N, PB>(scratch + (size_t)s0 * SLOT, lane, x);
-                if (active) {
-#pragma unroll
-                    for (int p = 0; p < PB; ++p) st_line<N, 0>(xt + p * WORDS, t, x[p]);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int p = 0; p < PB; ++p) ld_line<N, 1>(xt + p * WORDS, t, x[p]);
-                {
-                    const size_t o = ((size_t)(s0 + 1) * C + c) * (N / 4) * N + t;
-                    thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
-                                        reinterpret_cast<const float4 *>(T.e) + o);
-                }
-                if (exact || sps == 2) ck_store<N, PB>(scratch + (size_t)(s0 + 1) * SLOT, lane, x);
-                if (active) {
-#pragma unroll
-                    for (int p = 0; p < PB; ++p) st_line<N, 1>(xt + p * WORDS, t, x[p]);
-                }
-                __syncwarp();
-                in_regs = false;
-                if (sps == 3) {
-#pragma unroll
-                    for (int p = 0; p < PB; ++p) ld_line<N, 0>(xt + p * WORDS, t, x[p]);
-                    const size_t o = ((size_t)(s0 + 2) * C + c) * (N / 4) * N + t;
-                    thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
-                                        reinterpret_cast<const float4 *>(T.e) + o);
-                    ck_store<N, PB>(scratch + (size_t)(s0 + 2) * SLOT, lane, x);
-                    in_regs = true;
-                }
-                if (d.chan_op == 2) {
-                    if (in_regs && active) {
-#pragma unroll
-                        for (int p = 0; p < PB; ++p) st_line<N, 0>(xt + p * WORDS, t, x[p]);
-                    }
-                    group_sync(C, group);
-                    mix_rows<N, PB>(gxt, PB, C, a.chan + c * C, 1, t, x);
-                    group_sync(C, group);
-                    in_regs = true;
-                }
+        for (int step = 0; step < d.steps; ++step) {
+            if (d.chan_op == 1) {
+                if (x_ax >= 0) x_store(x_ax);
+                group_sync(C, group);
+                mix_rows<N, PB>(gxt, PB, C, a.chan + c * C, 1, t, x);
+                group_sync(C, group);
+                x_ax = 0;
             }
-            // the skip epilogue needs the FINAL state (after the last channel coupling): park it
-            // in the x tile as rows
-            if (d.skip && in_regs && active) {
-#pragma unroll
-                for (int p = 0; p < PB; ++p) st_line<N, 0>(xt + p * WORDS, t, x[p]);
+            // straight-line x, y, (x) sweeps: a loop over the sweeps of a step keeps ptxas from
+            // scheduling the next sweep's coefficient loads across the transposition
+            const int s0 = step * sps;
+            const size_t o0 = ((size_t)s0 * C + c) * (N / 4) * N + t, ostride = (size_t)C * (N / 4) * N;
+            auto tab = [&](const float *base, size_t o) { return reinterpret_cast<const float4 *>(base) + o; };
+            if (x_ax != 0) {
+                if (x_ax >= 0) {
+                    x_store(x_ax);
+                    __syncwarp();
+                }
+                x_load(0);
             }
+            prefetch_tables<N>(tab(T.inv, o0 + ostride), tab(T.e, o0 + ostride), nullptr);
+            thomas_solve<N, PB>(x, tab(T.inv, o0), tab(T.e, o0));
+            if (exact) ck_store<N, PB>(scratch + (size_t)s0 * SLOT, lane, x);
+            x_store(0);
+            __syncwarp();
+            x_load(1);
+            if (s0 + 2 < a.S)
+                prefetch_tables<N>(tab(T.inv, o0 + 2 * ostride), tab(T.e, o0 + 2 * ostride), nullptr);
+            else
+                prefetch_tables<N>(tab(T.r, o0 + ostride), tab(T.r, o0 + ostride), nullptr);
+            thomas_solve<N, PB>(x, tab(T.inv, o0 + ostride), tab(T.e, o0 + ostride));
+            x_ax = 1;
+            if (exact || sps == 2) ck_store<N, PB>(scratch + (size_t)(s0 + 1) * SLOT, lane, x);
+            if (sps == 3) {
+                x_store(1);
+                __syncwarp();
+                x_load(0);
+                if (s0 + 3 < a.S)
+                    prefetch_tables<N>(tab(T.inv, o0 + 3 * ostride), tab(T.e, o0 + 3 * ostride), nullptr);
+                else
+                    prefetch_tables<N>(tab(T.r, o0 + 2 * ostride), tab(T.r, o0 + 2 * ostride), nullptr);
+                thomas_solve<N, PB>(x, tab(T.inv, o0 + 2 * ostride), tab(T.e, o0 + 2 * ostride));
+                x_ax = 0;
+                ck_store<N, PB>(scratch + (size_t)(s0 + 2) * SLOT, lane, x);
+            }
+            if (d.chan_op == 2) {
+                x_store(x_ax);
+                group_sync(C, group);
+                mix_rows<N, PB>(gxt, PB, C, a.chan + c * C, 1, t, x);
+                group_sync(C, group);
+                x_ax = 0;
+            }
+        }
+        // the skip epilogue needs the FINAL state (after the last coupling): park it in the x tile
+        if (d.skip && x_ax >= 0) {
+            if (x_ax == 1) __syncwarp();
+            x_store(x_ax);
         }
         __syncwarp();
         // ------------------------------ phase 2: reverse
-        // g and x travel in registers; the tiles are only used to change orientation (and for the
-        // cross-channel ops).  g_ax / x_ax: orientation held in registers (0 rows, 1 columns) or
-        // -1 when the current value lives in the tile.
+        {   // the next item's input planes start their trip from HBM to L2 now
+            const int nb0 = (item + gridDim.x * a.G) * PB;
+#pragma unroll
+            for (int p = 0; p < PB; ++p)
+                if (nb0 + p < d.B) {
+                    prefetch_plane_l2<N>(a.u + ((size_t)(nb0 + p) * C + c) * plane, lane);
+                    prefetch_plane_l2<N>(a.gout + ((size_t)(nb0 + p) * C + c) * plane, lane);
+                }
+        }
+        float g[PB][N];
+        int g_ax = -1;
+        auto g_store = [&](int ax) {
+            if (active) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) {
+                    if (ax == 0) st_line<N, 0>(gt + p * WORDS, t, g[p]);
+                    else st_line<N, 1>(gt + p * WORDS, t, g[p]);
+                }
+            }
+        };
+        auto g_load = [&](int ax) {
+#pragma unroll
+            for (int p = 0; p < PB; ++p) {
+                if (ax == 0) ld_line<N, 0>(gt + p * WORDS, t, g[p]);
+                else ld_line<N, 1>(gt + p * WORDS, t, g[p]);
+            }
+        };
 #pragma unroll
         for (int p = 0; p < PB; ++p) {
             const bool valid = b0 + p < d.B;
             plane_to_tile<N>(a.gout + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, gt + p * WORDS, lane, valid);
         }
+        __syncwarp();
         if (d.skip) {
-            // out = sig u0 + om uF:  dL/dw += sig' * sum gout (u0 - uF),  g <- om * gout.
-            // The x tile still holds the final state uF from phase 1.
-            __syncwarp();
+            // out = sig u0 + om uF:  dL/dw += sig' * sum gout (u0 - uF),  g <- om * gout
             float accw = 0.0f;
 #pragma unroll
             for (int p = 0; p < PB; ++p) {
@@ -731,42 +867,8 @@ __global__ void bwd_kernel(const Args a) {
                 }
             }
             gw += accw;
+            __syncwarp();
         }
-        __syncwarp();
-        float g[PB][N], x[PB][N];
-        int g_ax = -1, x_ax = -1;
-        auto g_store = [&](int ax) {
-            if (active) {
-#pragma unroll
-                for (int p = 0; p < PB; ++p) {
-                    if (ax == 0) st_line<N, 0>(gt + p * WORDS, t, g[p]);
-                    else st_line<N, 1>(gt + p * WORDS, t, g[p]);
-                }
-            }
-        };
-        auto g_load = [&](int ax) {
-#pragma unroll
-            for (int p = 0; p < PB; ++p) {
-                if (ax == 0) ld_line<N, 0>(gt + p * WORDS, t, g[p]);
-                else ld_line<N, 1>(gt + p * WORDS, t, g[p]);
-            }
-        };
-        auto x_store = [&](int ax) {
-            if (active) {
-#pragma unroll
-                for (int p = 0; p < PB; ++p) {
-                    if (ax == 0) st_line<N, 0>(xt + p * WORDS, t, x[p]);
-                    else st_line<N, 1>(xt + p * WORDS, t, x[p]);
-                }
-            }
-        };
-        auto x_load = [&](int ax) {
-#pragma unroll
-            for (int p = 0; p < PB; ++p) {
-                if (ax == 0) ld_line<N, 0>(xt + p * WORDS, t, x[p]);
-                else ld_line<N, 1>(xt + p * WORDS, t, x[p]);
-            }
-        };
         for (int step = d.steps - 1; step >= 0; --step) {
             const int sl = step * sps + sps - 1;
             // state after the last sweep of this step: straight from the checkpoint into registers
@@ -774,38 +876,47 @@ __global__ void bwd_kernel(const Args a) {
             x_ax = last_ax;
             if (d.chan_op == 2) {
                 // adjoint of the post-step coupling works on the group's tiles (rows)
-                if (g_ax >= 0) { g_store(g_ax); g_ax = -1; }
+                if (g_ax >= 0) {
+                    g_store(g_ax);
+                    g_ax = -1;
+                }
                 x_store(x_ax);
                 __syncwarp();
                 chan_adjoint<N, PB>(ggt, gxt, C, c, group, a.chan, t, active, gm);
             }
             for (int k = sps - 1; k >= 0; --k) {
-                const int s = step * sps + k;
-                const int ax = sweep_axis(k);
+                const int s = step * sps + k, ax = sweep_axis(k);
                 if (exact && k != sps - 1) {
                     ck_load<N, PB>(scratch + (size_t)s * SLOT, lane, x);
                     x_ax = ax;
                 }
                 if (g_ax != ax) {
-                    if (g_ax >= 0) g_store(g_ax);
+                    if (g_ax >= 0) {
+                        if (shared_set) __syncwarp();
+                        g_store(g_ax);
+                    }
                     __syncwarp();
                     g_load(ax);
                     g_ax = ax;
                 }
                 if (x_ax != ax) {
-                    if (x_ax >= 0) x_store(x_ax);
+                    if (shared_set) __syncwarp();
+                    x_store(x_ax);
                     __syncwarp();
                     x_load(ax);
                     x_ax = ax;
                 }
-                const size_t o = ((size_t)(a.dbg_table0 ? 0 : s) * C + c) * (N / 4) * N + t;
-                const float scale = T.hdr->scale[s], tt = T.hdr->t[s];
-                const bool clamped = T.hdr->clamped[s] != 0;
+                const size_t o = ((size_t)s * C + c) * (N / 4) * N + t;
+                if (s > 0) {
+                    const size_t op = o - (size_t)C * (N / 4) * N;   // tables of the sweep reversed next -> L1
+                    prefetch_tables<N>(reinterpret_cast<const float4 *>(T.inv) + op,
+                                       reinterpret_cast<const float4 *>(T.e) + op,
+                                       reinterpret_cast<const float4 *>(T.r) + op);
+                }
+                const float scale = h_scale[s], tt = h_t[s];
+                const bool clamped = h_clamped[s] != 0;
                 const bool rebuild = !exact && k > 0;
-                if (ax == 0)
-                    reverse_sweep<N, PB, 0>(g, x, acc, acc + WORDS, t, active, T, o, scale, tt, onepe, smooth, rebuild, clamped);
-                else
-                    reverse_sweep<N, PB, 1>(g, x, acc + 2 * WORDS, acc + 3 * WORDS, t, active, T, o, scale, tt, onepe, smooth, rebuild, clamped);
+                reverse_sweep<N, PB>(g, x, tbase + (uint32_t)(ax * 64), T, o, scale, tt, onepe, smooth, rebuild, clamped);
             }
             if (d.chan_op == 1) {
                 // adjoint of the pre-step mix: needs g (rows) and the mix INPUT = state before this
@@ -828,7 +939,10 @@ __global__ void bwd_kernel(const Args a) {
                 chan_adjoint<N, PB>(ggt, gxt, C, c, group, a.chan, t, active, gm);
             }
         }
-        if (g_ax >= 0) g_store(g_ax);
+        if (g_ax >= 0) {
+            if (shared_set) __syncwarp();
+            g_store(g_ax);
+        }
         __syncwarp();
         if (a.need_gin) {
 #pragma unroll
@@ -843,11 +957,26 @@ __global__ void bwd_kernel(const Args a) {
         // the next item's phase 1 mixes through the group's x tiles: nobody may still read them
         if (d.chan_op != 0) group_sync(C, group);
     }
-    // ------------------------------ per-warp partials
-    __syncwarp();
+    // ------------------------------ per-warp partials: TMEM -> tile (line orientation) -> global
+    tmem_wait_st();
     float *pm = a.part_maps + (size_t)wg * 4 * plane;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) tile_to_plane<N>(acc + kk * WORDS, pm + kk * plane, lane, nullptr, 0.f, 1.f);
+    for (int kk = 0; kk < 4; ++kk) {
+        float av[32];
+        tmem_ld16(tbase + kk * 32, av);
+        tmem_ld16(tbase + kk * 32 + 16, av + 16);
+        tmem_wait_ld();
+        float ln[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) ln[i] = av[i];
+        __syncwarp();
+        if (active) {
+            if (kk < 2) st_line<N, 0>(xt, t, ln);
+            else st_line<N, 1>(xt, t, ln);
+        }
+        __syncwarp();
+        tile_to_plane<N>(xt, pm + kk * plane, lane, nullptr, 0.f, 1.f);
+    }
 #pragma unroll
     for (int dd = 0; dd < PDE_MAX_CHANNELS; ++dd) {
         const float sgm = warp_sum(active ? gm[dd] : 0.0f);
@@ -855,6 +984,9 @@ __global__ void bwd_kernel(const Args a) {
     }
     const float sgw = warp_sum(gw);
     if (lane == 0) a.part_skip[wg] = sgw;
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, (uint32_t)a.tmem_cols);
 }
 
 // Sum the per-warp partials (double accumulation, fixed order => deterministic).
@@ -918,30 +1050,70 @@ static int env_int(const char *name, int dflt) {
 static int tile_words(int N) { return N * ((N % 8 == 4) ? N : N + 4); }
 
 struct BwdPlan {
-    int PB, G, warps, blocks_per_sm, grid, nitems;
+    int PB, RB, G, warps, blocks_per_sm, grid, nitems, tile_sets, tmem_cols;
     size_t smem, scratch_floats, maps_floats, chan_floats, skip_floats;
 };
 
-static int bwd_pb(const pde_adi_desc *d) {
+static int bwd_pb() {
     int pb = env_int("PDE_B200_BWD_PB", 2);
     return pb == 1 ? 1 : 2;
+}
+// Two builds of the backward kernel: {PB = 2, 255 registers, 8 warps / SM} (default: fastest on
+// every layer measured) and {PB = 1, 168 registers, 12 warps / SM} (PDE_B200_BWD_PB=1).
+static int bwd_rb(int PB) { return PB == 2 ? 1 : 2; }
+
+static int bwd_groups(int C) { return C == 1 ? 4 : (C == 2 ? 2 : (C == 3 ? 2 : 1)); }
+
+template <int N>
+static const void *bwd_kernel_ptr(int PB, int RB) {
+    (void)RB;
+    return PB == 2 ? reinterpret_cast<const void *>(bwd_kernel<N, 2, 1>) : reinterpret_cast<const void *>(bwd_kernel<N, 1, 2>);
+}
+
+static const void *bwd_kernel_for(int N, int PB, int RB) {
+    switch (N) {
+        case 8: return bwd_kernel_ptr<8>(PB, RB);
+        case 12: return bwd_kernel_ptr<12>(PB, RB);
+        case 16: return bwd_kernel_ptr<16>(PB, RB);
+        case 28: return bwd_kernel_ptr<28>(PB, RB);
+        case 32: return bwd_kernel_ptr<32>(PB, RB);
+        default: return nullptr;
+    }
 }
 
 static int plan_bwd(const pde_adi_desc *d, BwdPlan *p) {
     DeviceProps props;
     int rc = query_props(&props);
     if (rc) return rc;
-    p->PB = bwd_pb(d);
-    p->G = groups_per_block(d->C);
+    p->PB = bwd_pb();
+    p->G = bwd_groups(d->C);
     p->warps = p->G * d->C;
-    p->smem = ((size_t)2 * p->warps * p->PB + (size_t)4 * p->warps) * tile_words(d->N) * sizeof(float);
-    if (p->smem > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
-    // registers cap residency at 65536 / (255 * 32) = 8 warps in the worst case; shared memory
-    // caps it at 227 KB / smem.  The occupancy API is not used so the plan (and therefore the
-    // workspace size) is a pure function of the descriptor and the device.
-    int by_smem = (int)((size_t)(227 * 1024) / (p->smem + 1024));
-    int by_warps = 16 / p->warps;
-    p->blocks_per_sm = by_smem < by_warps ? by_smem : by_warps;
+    p->tile_sets = (d->chan_op != 0 || d->skip) ? 2 : 1;
+    p->tmem_cols = p->warps <= 4 ? 128 : (p->warps <= 8 ? 256 : 512);
+    p->smem = (size_t)p->tile_sets * p->warps * p->PB * tile_words(d->N) * sizeof(float);
+    if (p->smem > (size_t)props.max_smem_optin || p->warps > 16) return PDE_ERR_UNSUPPORTED;
+    p->RB = bwd_rb(p->PB);
+    const void *kern = bwd_kernel_for(d->N, p->PB, p->RB);
+    if (!kern) return PDE_ERR_UNSUPPORTED;
+    PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    // Residency from first principles: the occupancy calculator answers 1 block / SM for kernels
+    // that allocate tensor memory, whatever their footprint.
+    cudaFuncAttributes fa;
+    PDE_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+    const int threads = p->warps * 32;
+    const int regs_per_warp = ((fa.numRegs + 7) / 8) * 8 * 32;
+    const int by_regs = 65536 / (regs_per_warp * p->warps);
+    const int by_smem = (int)((size_t)(228 * 1024) / (p->smem + fa.sharedSizeBytes + 1024));
+    const int by_threads = 2048 / threads;
+    const int by_tmem = 512 / p->tmem_cols;
+    int occ = by_regs;
+    if (by_smem < occ) occ = by_smem;
+    if (by_threads < occ) occ = by_threads;
+    if (by_tmem < occ) occ = by_tmem;
+    p->blocks_per_sm = occ;
+    if (env_int("PDE_B200_DEBUG", 0))
+        fprintf(stderr, "[pde_b200] bwd plan: N=%d C=%d PB=%d RB=%d warps=%d smem=%zu regs=%d by_regs=%d by_smem=%d by_tmem=%d\n",
+                d->N, d->C, p->PB, p->RB, p->warps, p->smem, fa.numRegs, by_regs, by_smem, by_tmem);
     if (p->blocks_per_sm < 1) p->blocks_per_sm = 1;
     p->nitems = (d->B + p->PB - 1) / p->PB;
     int want = (p->nitems + p->G - 1) / p->G;
@@ -971,14 +1143,12 @@ static int launch_fwd(const Args &a, int PB, int grid, int threads, size_t smem,
     }
 }
 
-template <int N>
-static int launch_bwd(const Args &a, int PB, int grid, int threads, size_t smem, cudaStream_t st) {
-    auto go = [&](auto kern) -> int {
-        PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, st>>>(a);
-        return cuda_last_error();
-    };
-    return PB == 2 ? go(bwd_kernel<N, 2>) : go(bwd_kernel<N, 1>);
+static int launch_bwd(const Args &a, const BwdPlan &p, cudaStream_t st) {
+    const void *kern = bwd_kernel_for(a.d.N, p.PB, p.RB);
+    if (!kern) return PDE_ERR_UNSUPPORTED;
+    void *params[] = {const_cast<Args *>(&a)};
+    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(p.grid), dim3(p.warps * 32), params, p.smem, st));
+    return cuda_last_error();
 }
 
 #define PDE_DISPATCH_N(N_, CALL)                     \
@@ -1098,7 +1268,8 @@ extern "C" int pde_adi_backward(const pde_adi_desc *d, const void *tables, const
     a.G = p.G;
     a.nitems = p.nitems;
     a.need_gin = gin != nullptr;
-    a.dbg_table0 = env_int("PDE_DEBUG_TABLE0", 0);
+    a.tile_sets = p.tile_sets;
+    a.tmem_cols = p.tmem_cols;
     a.tables = static_cast<const char *>(tables);
     a.u = u; a.gout = gout; a.chan = chan; a.skipw = skipw; a.gin = gin;
     a.scratch = ws;
@@ -1117,14 +1288,7 @@ extern "C" int pde_adi_backward(const pde_adi_desc *d, const void *tables, const
         if (g_skip) PDE_CUDA_TRY(cudaMemsetAsync(g_skip, 0, sizeof(float), st));
         return PDE_OK;
     }
-    switch (d->N) {
-        case 8: rc = launch_bwd<8>(a, p.PB, p.grid, p.warps * 32, p.smem, st); break;
-        case 12: rc = launch_bwd<12>(a, p.PB, p.grid, p.warps * 32, p.smem, st); break;
-        case 16: rc = launch_bwd<16>(a, p.PB, p.grid, p.warps * 32, p.smem, st); break;
-        case 28: rc = launch_bwd<28>(a, p.PB, p.grid, p.warps * 32, p.smem, st); break;
-        case 32: rc = launch_bwd<32>(a, p.PB, p.grid, p.warps * 32, p.smem, st); break;
-        default: rc = PDE_ERR_UNSUPPORTED;
-    }
+    rc = launch_bwd(a, p, st);
     if (rc) return rc;
     const size_t total = 4 * (size_t)d->C * d->N * d->N;
     finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(*d, nw, a.part_maps, a.part_chan, a.part_skip,

@@ -130,6 +130,7 @@ def run_b200(args):
     from tests import cases as K
     from tests import runners
     import cnn_with_pde_b200 as P
+    from cnn_with_pde_b200.parallel import allreduce_coefficient_grads
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,8 +163,7 @@ def run_b200(args):
         y = layer(x)
         y.backward(g)
         if world > 1:
-            flat = torch.cat([t.reshape(-1) for t in grads()])
-            dist.all_reduce(flat)
+            allreduce_coefficient_grads(params)   # the path's only exchange: one flat NCCL all-reduce
         return y
 
     def sync_all():
@@ -249,9 +249,9 @@ def run_b200(args):
             yy = layer(buf)
             yy.backward(g[lo:hi])
             freed[i % 2].record(main)
-        flat = torch.cat([t.reshape(-1) for t in grads()])
         if world > 1:
-            dist.all_reduce(flat)
+            allreduce_coefficient_grads(params)
+        flat = torch.cat([t.reshape(-1) for t in grads()])
         host_g.copy_(flat, non_blocking=True)
 
     for ev in freed:
@@ -287,7 +287,8 @@ def run_b200(args):
 
     out = None
     if rank == 0:
-        cpu = cpu_baseline(args.layer, budget_s=args.cpu_seconds)
+        # the CPU leg runs on rank 0 at N = 1 only (the other ranks would idle at the barrier)
+        cpu = cpu_baseline(args.layer, budget_s=args.cpu_seconds) if world == 1 else None
         others = {}
         if args.all_layers and world == 1:
             del x, y, yn, xn, host_u, dev_bufs

@@ -989,36 +989,62 @@ __global__ void __launch_bounds__(192, RB) bwd_kernel(const Args a) {
     if (warp == 0) tmem_dealloc(tmem_slot, (uint32_t)a.tmem_cols);
 }
 
-// Sum the per-warp partials (double accumulation, fixed order => deterministic).
-__global__ void finish_kernel(pde_adi_desc d, int nwarps_total, const float *__restrict__ part_maps,
-                              const float *__restrict__ part_chan, const float *__restrict__ part_skip,
-                              const float *__restrict__ skipw, float *g_ab, float *g_atc, float *g_bb,
-                              float *g_btc, float *g_chan, float *g_skip) {
+// Sum the per-warp partials (double accumulation, fixed order => deterministic).  A block covers
+// 32 output elements; its 8 warps each sum an interleaved slice of the partials (independent loads,
+// unrolled) and the 8 slice sums are combined in a fixed order through shared memory.
+constexpr int kFinishCells = 32, kFinishSlices = 8;
+__global__ void __launch_bounds__(kFinishCells *kFinishSlices)
+    finish_kernel(pde_adi_desc d, int nwarps_total, const float *__restrict__ part_maps,
+                  const float *__restrict__ part_chan, const float *__restrict__ part_skip,
+                  const float *__restrict__ skipw, float *g_ab, float *g_atc, float *g_bb, float *g_btc,
+                  float *g_chan, float *g_skip) {
+    __shared__ double red[kFinishSlices][kFinishCells];
     const int C = d.C, N = d.N;
     const size_t plane = (size_t)N * N;
     const size_t total = 4 * (size_t)C * plane;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x % kFinishCells, slice = threadIdx.x / kFinishCells;
+    const size_t idx = (size_t)blockIdx.x * kFinishCells + lane;
+    double acc = 0.0;
+    int kind = 0, c = 0;
+    size_t cell = 0;
     if (idx < total) {
-        const int kind = (int)(idx / (C * plane));
-        const int c = (int)((idx / plane) % C);
-        const size_t cell = idx % plane;
-        double acc = 0.0;
-        for (int w = c; w < nwarps_total; w += C) acc += (double)part_maps[((size_t)w * 4 + kind) * plane + cell];
+        kind = (int)(idx / (C * plane));
+        c = (int)((idx / plane) % C);
+        cell = idx % plane;
+        const int per_c = (nwarps_total - c + C - 1) / C;   // warps that own channel c: c, c + C, ...
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int j = slice;
+        for (; j + 3 * kFinishSlices < per_c; j += 4 * kFinishSlices) {
+            a0 += (double)part_maps[((size_t)(c + (size_t)C * j) * 4 + kind) * plane + cell];
+            a1 += (double)part_maps[((size_t)(c + (size_t)C * (j + kFinishSlices)) * 4 + kind) * plane + cell];
+            a2 += (double)part_maps[((size_t)(c + (size_t)C * (j + 2 * kFinishSlices)) * 4 + kind) * plane + cell];
+            a3 += (double)part_maps[((size_t)(c + (size_t)C * (j + 3 * kFinishSlices)) * 4 + kind) * plane + cell];
+        }
+        for (; j < per_c; j += kFinishSlices)
+            a0 += (double)part_maps[((size_t)(c + (size_t)C * j) * 4 + kind) * plane + cell];
+        acc = (a0 + a1) + (a2 + a3);
+    }
+    red[slice][lane] = acc;
+    __syncthreads();
+    if (slice == 0 && idx < total) {
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < kFinishSlices; ++q) sum += red[q][lane];
         float *dst = kind == 0 ? g_ab : kind == 1 ? g_atc : kind == 2 ? g_bb : g_btc;
-        dst[(size_t)c * plane + cell] = (float)acc;
+        dst[(size_t)c * plane + cell] = (float)sum;
     }
     if (blockIdx.x == 0) {
         if (g_chan && threadIdx.x < C * C) {
-            const int c = threadIdx.x / C, dd = threadIdx.x % C;
-            double acc = 0.0;
-            for (int w = c; w < nwarps_total; w += C) acc += (double)part_chan[(size_t)w * PDE_MAX_CHANNELS + dd];
-            g_chan[c * C + dd] = (float)acc;
+            const int cc = threadIdx.x / C, dd = threadIdx.x % C;
+            double a = 0.0;
+            for (int w = cc; w < nwarps_total; w += C) a += (double)part_chan[(size_t)w * PDE_MAX_CHANNELS + dd];
+            g_chan[cc * C + dd] = (float)a;
         }
         if (g_skip && threadIdx.x == 32) {
-            double acc = 0.0;
-            for (int w = 0; w < nwarps_total; ++w) acc += (double)part_skip[w];
+            double a = 0.0;
+            for (int w = 0; w < nwarps_total; ++w) a += (double)part_skip[w];
             const double sg = 1.0 / (1.0 + exp(-(double)skipw[0]));
-            g_skip[0] = (float)(acc * sg * (1.0 - sg));
+            g_skip[0] = (float)(a * sg * (1.0 - sg));
         }
     }
 }
@@ -1291,7 +1317,7 @@ extern "C" int pde_adi_backward(const pde_adi_desc *d, const void *tables, const
     rc = launch_bwd(a, p, st);
     if (rc) return rc;
     const size_t total = 4 * (size_t)d->C * d->N * d->N;
-    finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(*d, nw, a.part_maps, a.part_chan, a.part_skip,
+    finish_kernel<<<(unsigned)((total + kFinishCells - 1) / kFinishCells), kFinishCells * kFinishSlices, 0, st>>>(*d, nw, a.part_maps, a.part_chan, a.part_skip,
                                                                   skipw, g_ab, g_atc, g_bb, g_btc, g_chan, g_skip);
     return cuda_last_error();
 }

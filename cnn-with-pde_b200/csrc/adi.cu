@@ -492,14 +492,14 @@ __device__ __forceinline__ void ck_store(float *slot, int lane, const float (&x)
 #pragma unroll
     for (int p = 0; p < PB; ++p)
 #pragma unroll
-        for (int i = 0; i < N; ++i) slot[(p * N + i) * 32 + lane] = x[p][i];
+        for (int i = 0; i < N; ++i) __stcg(&slot[(p * N + i) * 32 + lane], x[p][i]);   // L2 only: keep L1 for the tables
 }
 template <int N, int PB>
 __device__ __forceinline__ void ck_load(const float *slot, int lane, float (&x)[PB][N]) {
 #pragma unroll
     for (int p = 0; p < PB; ++p)
 #pragma unroll
-        for (int i = 0; i < N; ++i) x[p][i] = slot[(p * N + i) * 32 + lane];
+        for (int i = 0; i < N; ++i) x[p][i] = __ldcg(&slot[(p * N + i) * 32 + lane]);
 }
 template <int N, int PB, int AX>
 __device__ __forceinline__ void ck_to_tile(const float *slot, int lane, int t, bool active, float *tiles) {
@@ -508,7 +508,7 @@ __device__ __forceinline__ void ck_to_tile(const float *slot, int lane, int t, b
     for (int p = 0; p < PB; ++p) {
         float x[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = slot[(p * N + i) * 32 + lane];
+        for (int i = 0; i < N; ++i) x[i] = __ldcg(&slot[(p * N + i) * 32 + lane]);
         if (active) st_line<N, AX>(tiles + p * WORDS, t, x);
     }
 }

@@ -38,11 +38,17 @@ def main():
             continue
         if in_fn and re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", ln):
             lines_of.append(cur_line)
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    short = "bwd_kernel" if "bwd_kernel" in kname else ("fwd_kernel" if "fwd_kernel" in kname else kname)
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + short],
+                         capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     h = rows[1]
     ix = {n: i for i, n in enumerate(h)}
-    body = [r for r in rows[2:] if len(r) == len(h)]
+    body, seen = [], set()
+    for r in rows[2:]:
+        if len(r) == len(h) and r[ix["Address"]] not in seen and r[ix["Address"]] != "Address":
+            seen.add(r[ix["Address"]])
+            body.append(r)
     if len(body) != len(lines_of):
         print(f"warning: {len(body)} profiled instructions vs {len(lines_of)} disassembled", file=sys.stderr)
     agg = collections.defaultdict(lambda: collections.Counter())

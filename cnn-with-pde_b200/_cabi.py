@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpde_b200.so")
+# PDE_B200_LIB points at another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("PDE_B200_LIB") or os.path.join(_HERE, "libpde_b200.so")
 MAX_SWEEPS = 192
 MAX_CHANNELS = 4
 

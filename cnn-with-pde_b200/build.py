@@ -54,9 +54,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # the image exports CC/CXX wrappers that break host compilation; use the system g++
     ccbin = shutil.which("g++") or "/usr/bin/g++"
 
+    extra = os.environ.get("PDE_B200_NVCC_EXTRA", "").split()   # e.g. -DPDE_BWD_MINBLOCKS=1 for A/B builds
+
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, "-ccbin", ccbin] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [nvcc, "-ccbin", ccbin] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, env=env, capture_output=True, text=True)
         if r.returncode != 0:

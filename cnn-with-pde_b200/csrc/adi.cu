@@ -40,16 +40,23 @@ struct Header {
     float t[PDE_MAX_SWEEPS];
     unsigned rmax_bits[PDE_MAX_SWEEPS];
     int clamped[PDE_MAX_SWEEPS];   // 1 if any cell of sweep s sits outside the clamp interval
+    // sweeps with the same axis, time, time step and spacing have the same tables (Strang: the
+    // closing half sweep of a step and the opening one of the next): slot[s] numbers the distinct
+    // ones in order of first appearance, rep[u] is the first sweep of slot u
+    int nslots;
+    short slot[PDE_MAX_SWEEPS];
+    short rep[PDE_MAX_SWEEPS];
 };
 static_assert(sizeof(Header) <= kHeaderBytes, "header too large");
 
 template <int N>
 struct Geo {
     static_assert(N % 4 == 0 && N >= 8 && N <= 32, "plane edge must be a multiple of 4 in [8, 32]");
-    // row stride (words) == 4 (mod 8): 128-bit row accesses by 8 consecutive lanes hit 32
-    // distinct banks, and column accesses (lane == column) are conflict-free for any stride.
-    static constexpr int ST = (N % 8 == 4) ? N : N + 4;
-    static constexpr int WORDS = N * ST;
+    // A tile interleaves two samples as float2.  Row stride ST (in float2) with ST / 2 odd: the
+    // 128-bit row accesses of 8 consecutive lanes hit 8 distinct 16-byte bank groups, and the
+    // 64-bit column accesses (lane == column) of a half warp are 128 contiguous bytes.
+    static constexpr int ST = N + 2;
+    static constexpr int WORDS = 2 * N * ST;   // floats per tile
     static constexpr int Q = N / 4;
 };
 
@@ -159,111 +166,133 @@ __global__ void header_kernel(pde_adi_desc d, pde_adi_schedule sch, char *tables
     }
     hdr->amp_bound = amp;
     hdr->mode_exact = (amp > kAmpLimit || !(amp == amp)) ? 1 : 0;
+    int nslots = 0;
+    for (int s = 0; s < S; ++s) {
+        int u = -1;
+        for (int q = 0; q < s && u < 0; ++q)
+            if (sweep_axis(q % sps) == sweep_axis(s % sps) && sch.t[q] == sch.t[s] && sch.dts[q] == sch.dts[s] &&
+                sch.h2[q] == sch.h2[s])
+                u = hdr->slot[q];
+        if (u < 0) {
+            u = nslots++;
+            hdr->rep[u] = (short)s;
+        }
+        hdr->slot[s] = (short)u;
+    }
+    hdr->nslots = nslots;
 }
 
 // ------------------------------------------------------------------------------------------
-// tile helpers.  A tile is one N x N plane with row stride ST in shared memory.
+// tile helpers.  A tile holds the same plane of TWO samples, interleaved cell by cell as float2
+// (lo = sample 2k, hi = sample 2k+1), N rows of ST float2.
 // ------------------------------------------------------------------------------------------
 template <int N>
-__device__ __forceinline__ void plane_to_tile(const float *__restrict__ g, float *tile, int lane, bool valid) {
+__device__ __forceinline__ void planes_to_tile(const float *__restrict__ ga, const float *__restrict__ gb,
+                                               float *tile, int lane, bool va, bool vb) {
     constexpr int ST = Geo<N>::ST;
-    const float4 *g4 = reinterpret_cast<const float4 *>(g);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int q0 = 0; q0 < N * N / 4; q0 += 32) {
         const int q = q0 + lane;
         if (q < N * N / 4) {
-            const float4 v = valid ? ld_stream(g4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a = va ? ld_stream(reinterpret_cast<const float4 *>(ga) + q) : zero;
+            const float4 b = vb ? ld_stream(reinterpret_cast<const float4 *>(gb) + q) : zero;
             const int idx = 4 * q, r = idx / N, cc = idx % N;
-            *reinterpret_cast<float4 *>(&tile[r * ST + cc]) = v;
+            float4 *dst = reinterpret_cast<float4 *>(&tile[(r * ST + cc) * 2]);
+            dst[0] = make_float4(a.x, b.x, a.y, b.y);
+            dst[1] = make_float4(a.z, b.z, a.w, b.w);
         }
     }
 }
 
-// out = tile                      (u0 == nullptr)
+// out = tile                      (ua == nullptr)
 // out = sig * u0 + om * tile      (skip epilogue, or gin = g + sig * gout with om == 1)
 template <int N>
-__device__ __forceinline__ void tile_to_plane(const float *tile, float *__restrict__ g, int lane,
-                                              const float *__restrict__ u0, float sig, float om) {
+__device__ __forceinline__ void tile_to_planes(const float *tile, float *__restrict__ ga, float *__restrict__ gb,
+                                               int lane, bool va, bool vb, const float *__restrict__ ua,
+                                               const float *__restrict__ ub, float sig, float om) {
     constexpr int ST = Geo<N>::ST;
-    float4 *g4 = reinterpret_cast<float4 *>(g);
 #pragma unroll
     for (int q0 = 0; q0 < N * N / 4; q0 += 32) {
         const int q = q0 + lane;
         if (q < N * N / 4) {
             const int idx = 4 * q, r = idx / N, cc = idx % N;
-            float4 v = *reinterpret_cast<const float4 *>(&tile[r * ST + cc]);
-            if (u0) {
-                const float4 w = ld_stream(reinterpret_cast<const float4 *>(u0) + q);
-                v.x = fmaf(om, v.x, sig * w.x);
-                v.y = fmaf(om, v.y, sig * w.y);
-                v.z = fmaf(om, v.z, sig * w.z);
-                v.w = fmaf(om, v.w, sig * w.w);
+            const float4 *src = reinterpret_cast<const float4 *>(&tile[(r * ST + cc) * 2]);
+            const float4 v0 = src[0], v1 = src[1];
+            float4 a = make_float4(v0.x, v0.z, v1.x, v1.z), b = make_float4(v0.y, v0.w, v1.y, v1.w);
+            if (va) {
+                if (ua) {
+                    const float4 w = ld_stream(reinterpret_cast<const float4 *>(ua) + q);
+                    a.x = fmaf(om, a.x, sig * w.x); a.y = fmaf(om, a.y, sig * w.y);
+                    a.z = fmaf(om, a.z, sig * w.z); a.w = fmaf(om, a.w, sig * w.w);
+                }
+                st_stream(reinterpret_cast<float4 *>(ga) + q, a);
             }
-            st_stream(g4 + q, v);
+            if (vb) {
+                if (ub) {
+                    const float4 w = ld_stream(reinterpret_cast<const float4 *>(ub) + q);
+                    b.x = fmaf(om, b.x, sig * w.x); b.y = fmaf(om, b.y, sig * w.y);
+                    b.z = fmaf(om, b.z, sig * w.z); b.w = fmaf(om, b.w, sig * w.w);
+                }
+                st_stream(reinterpret_cast<float4 *>(gb) + q, b);
+            }
         }
     }
 }
 
-// 4 consecutive elements of the line owned by lane t: AX == 0 -> row t, AX == 1 -> column t.
+// The line owned by lane t: AX == 0 -> row t (128-bit accesses, two cells of both samples each),
+// AX == 1 -> column t (64-bit accesses).
 template <int N, int AX>
-__device__ __forceinline__ float4 ld4(const float *tile, int t, int q) {
-    constexpr int ST = Geo<N>::ST;
-    if (AX == 0) return *reinterpret_cast<const float4 *>(&tile[t * ST + 4 * q]);
-    return make_float4(tile[(4 * q) * ST + t], tile[(4 * q + 1) * ST + t], tile[(4 * q + 2) * ST + t],
-                       tile[(4 * q + 3) * ST + t]);
-}
-template <int N, int AX>
-__device__ __forceinline__ void st4(float *tile, int t, int q, float4 v) {
+__device__ __forceinline__ void ld_line(const float *tile, int t, f2 (&x)[N]) {
     constexpr int ST = Geo<N>::ST;
     if (AX == 0) {
-        *reinterpret_cast<float4 *>(&tile[t * ST + 4 * q]) = v;
+#pragma unroll
+        for (int j = 0; j < N / 2; ++j) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&tile[(t * ST + 2 * j) * 2]);
+            x[2 * j].v = v.x;
+            x[2 * j + 1].v = v.y;
+        }
     } else {
-        tile[(4 * q) * ST + t] = v.x;
-        tile[(4 * q + 1) * ST + t] = v.y;
-        tile[(4 * q + 2) * ST + t] = v.z;
-        tile[(4 * q + 3) * ST + t] = v.w;
-    }
-}
-
-template <int N, int AX>
-__device__ __forceinline__ void ld_line(const float *tile, int t, float (&x)[N]) {
 #pragma unroll
-    for (int q = 0; q < N / 4; ++q) {
-        const float4 v = ld4<N, AX>(tile, t, q);
-        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        for (int i = 0; i < N; ++i) x[i].v = *reinterpret_cast<const unsigned long long *>(&tile[(i * ST + t) * 2]);
     }
 }
 template <int N, int AX>
-__device__ __forceinline__ void st_line(float *tile, int t, const float (&x)[N]) {
+__device__ __forceinline__ void st_line(float *tile, int t, const f2 (&x)[N]) {
+    constexpr int ST = Geo<N>::ST;
+    if (AX == 0) {
 #pragma unroll
-    for (int q = 0; q < N / 4; ++q)
-        st4<N, AX>(tile, t, q, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
+        for (int j = 0; j < N / 2; ++j) {
+            ulonglong2 v;
+            v.x = x[2 * j].v;
+            v.y = x[2 * j + 1].v;
+            *reinterpret_cast<ulonglong2 *>(&tile[(t * ST + 2 * j) * 2]) = v;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) *reinterpret_cast<unsigned long long *>(&tile[(i * ST + t) * 2]) = x[i].v;
+    }
 }
 
 // x[p][i] = sum_d mat[d * mstride] * tile_d[p][row t][i]   over the C channel tiles of a group.
 // mstride == 1 walks a row of the matrix (forward mix), mstride == C a column (adjoint).
-template <int N, int PB>
-__device__ __forceinline__ void mix_rows(const float *group_tiles, int tiles_per_chan, int C,
-                                         const float *__restrict__ mat, int mstride, int t,
-                                         float (&x)[PB][N]) {
+template <int N, int NP>
+__device__ __forceinline__ void mix_rows(const float *group_tiles, int C, const float *__restrict__ mat, int mstride,
+                                         int t, f2 (&x)[NP][N]) {
     constexpr int WORDS = Geo<N>::WORDS;
+    const f2 zero = f2_bc(0.0f);
 #pragma unroll
-    for (int p = 0; p < PB; ++p)
+    for (int p = 0; p < NP; ++p)
 #pragma unroll
-        for (int i = 0; i < N; ++i) x[p][i] = 0.0f;
+        for (int i = 0; i < N; ++i) x[p][i] = zero;
     for (int dd = 0; dd < C; ++dd) {
         const float m = __ldg(mat + dd * mstride);
 #pragma unroll
-        for (int p = 0; p < PB; ++p) {
-            const float *tile = group_tiles + ((size_t)dd * tiles_per_chan + p) * WORDS;
+        for (int p = 0; p < NP; ++p) {
+            f2 row[N];
+            ld_line<N, 0>(group_tiles + ((size_t)dd * NP + p) * WORDS, t, row);
 #pragma unroll
-            for (int q = 0; q < N / 4; ++q) {
-                const float4 v = ld4<N, 0>(tile, t, q);
-                x[p][4 * q] = fmaf(m, v.x, x[p][4 * q]);
-                x[p][4 * q + 1] = fmaf(m, v.y, x[p][4 * q + 1]);
-                x[p][4 * q + 2] = fmaf(m, v.z, x[p][4 * q + 2]);
-                x[p][4 * q + 3] = fmaf(m, v.w, x[p][4 * q + 3]);
-            }
+            for (int i = 0; i < N; ++i) x[p][i] = f2_fmas(m, row[i], x[p][i]);
         }
     }
 }
@@ -290,12 +319,12 @@ __device__ __forceinline__ void prefetch_plane_l2(const float *g, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Thomas solve of (A + eps I) x = d for the PB lines a lane holds (same coefficients for all
-// PB: the factorisation is batch independent).  With inv = 1/pivot and e = r/pivot = -c*:
+// Thomas solve of (A + eps I) x = d for the NP sample pairs a lane holds (same coefficients for
+// all of them: the factorisation is batch independent).  With inv = 1/pivot and e = r/pivot = -c*:
 //   d*_i = inv_i d_i + e_i d*_{i-1}         x_i = d*_i + e_i x_{i+1}
 // ------------------------------------------------------------------------------------------
-template <int N, int PB>
-__device__ __forceinline__ void thomas_solve(float (&x)[PB][N], const float4 *__restrict__ tinv,
+template <int N, int NP>
+__device__ __forceinline__ void thomas_solve(f2 (&x)[NP][N], const float4 *__restrict__ tinv,
                                              const float4 *__restrict__ te) {
     float e[N];
     float4 iv_n = __ldg(tinv), ev_n = __ldg(te);
@@ -312,54 +341,14 @@ __device__ __forceinline__ void thomas_solve(float (&x)[PB][N], const float4 *__
             const int i = 4 * q + k;
             e[i] = evs[k];
 #pragma unroll
-            for (int p = 0; p < PB; ++p)
-                x[p][i] = (i == 0) ? x[p][0] * ivs[k] : fmaf(evs[k], x[p][i - 1], x[p][i] * ivs[k]);
+            for (int p = 0; p < NP; ++p)
+                x[p][i] = (i == 0) ? f2_muls(ivs[k], x[p][0]) : f2_fmas(evs[k], x[p][i - 1], f2_muls(ivs[k], x[p][i]));
         }
     }
 #pragma unroll
     for (int i = N - 2; i >= 0; --i)
 #pragma unroll
-        for (int p = 0; p < PB; ++p) x[p][i] = fmaf(e[i], x[p][i + 1], x[p][i]);
-}
-
-// Adjoint solve (A + eps I)^T lambda = g through the same factorisation A = L U:
-//   U^T w = g:        w_i = g_i + e_{i-1} w_{i-1}
-//   L^T lambda = w:   lambda_i = inv_i (w_i + r_{i+1} lambda_{i+1})
-template <int N, int PB>
-__device__ __forceinline__ void thomas_solve_adjoint(float (&g)[PB][N], float (&rr)[N],
-                                                     const float4 *__restrict__ tr,
-                                                     const float4 *__restrict__ tinv,
-                                                     const float4 *__restrict__ te) {
-    float eprev = 0.0f;
-#pragma unroll
-    for (int q = 0; q < N / 4; ++q) {
-        const float4 ev = __ldg(te + q * N);
-        const float evs[4] = {ev.x, ev.y, ev.z, ev.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = 4 * q + k;
-            if (i > 0) {
-#pragma unroll
-                for (int p = 0; p < PB; ++p) g[p][i] = fmaf(eprev, g[p][i - 1], g[p][i]);
-            }
-            eprev = evs[k];
-        }
-    }
-    float rnext = 0.0f;
-#pragma unroll
-    for (int q = N / 4 - 1; q >= 0; --q) {
-        const float4 iv = __ldg(tinv + q * N), rv = __ldg(tr + q * N);
-        const float ivs[4] = {iv.x, iv.y, iv.z, iv.w}, rvs[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-        for (int k = 3; k >= 0; --k) {
-            const int i = 4 * q + k;
-#pragma unroll
-            for (int p = 0; p < PB; ++p)
-                g[p][i] = (i == N - 1) ? g[p][i] * ivs[k] : fmaf(rnext * ivs[k], g[p][i + 1], g[p][i] * ivs[k]);
-            rnext = rvs[k];
-            rr[i] = rvs[k];
-        }
-    }
+        for (int p = 0; p < NP; ++p) x[p][i] = f2_fmas(e[i], x[p][i + 1], x[p][i]);
 }
 
 struct Args {
@@ -380,9 +369,9 @@ __device__ __forceinline__ void group_sync(int C, int group) {
 }
 
 // ------------------------------------------------------------------------------------------
-// forward
+// forward: one warp owns channel c of 2 * NP samples
 // ------------------------------------------------------------------------------------------
-template <int N, int PB>
+template <int N, int NP>
 __global__ void fwd_kernel(const Args a) {
     constexpr int WORDS = Geo<N>::WORDS;
     extern __shared__ __align__(16) float smem[];
@@ -391,8 +380,8 @@ __global__ void fwd_kernel(const Args a) {
     const int C = d.C, group = warp / C, c = warp % C;
     const bool active = lane < N;
     const int t = active ? lane : N - 1;
-    float *gtiles = smem + (size_t)group * C * PB * WORDS;  // [C][PB][WORDS]
-    float *my = gtiles + (size_t)c * PB * WORDS;
+    float *gtiles = smem + (size_t)group * C * NP * WORDS;  // [C][NP][WORDS]
+    float *my = gtiles + (size_t)c * NP * WORDS;
     const Tables T = split_tables(a.tables, d);
     const size_t plane = (size_t)N * N;
     float sig = 0.0f;
@@ -400,117 +389,107 @@ __global__ void fwd_kernel(const Args a) {
     const float om = 1.0f - sig;
 
     for (int item = blockIdx.x * a.G + group; item < a.nitems; item += gridDim.x * a.G) {
-        const int b0 = item * PB;
+        const int b0 = item * 2 * NP;
 #pragma unroll
-        for (int p = 0; p < PB; ++p) {
-            const bool valid = b0 + p < d.B;
-            plane_to_tile<N>(a.u + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, my + p * WORDS, lane, valid);
+        for (int p = 0; p < NP; ++p) {
+            const int ba = b0 + 2 * p, bb = ba + 1;
+            const bool va = ba < d.B, vb = bb < d.B;
+            planes_to_tile<N>(a.u + ((size_t)(va ? ba : 0) * C + c) * plane, a.u + ((size_t)(vb ? bb : 0) * C + c) * plane,
+                              my + p * WORDS, lane, va, vb);
         }
         __syncwarp();
-        float x[PB][N];
+        f2 x[NP][N];
         bool in_regs = false;  // x holds the state as rows
         for (int step = 0; step < d.steps; ++step) {
             const int s0 = step * a.sps;
             if (d.chan_op == 1) {
                 if (in_regs && active) {
 #pragma unroll
-                    for (int p = 0; p < PB; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
+                    for (int p = 0; p < NP; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
                 }
                 group_sync(C, group);
-                mix_rows<N, PB>(gtiles, PB, C, a.chan + c * C, 1, t, x);
+                mix_rows<N, NP>(gtiles, C, a.chan + c * C, 1, t, x);
                 group_sync(C, group);
             } else if (!in_regs) {
 #pragma unroll
-                for (int p = 0; p < PB; ++p) ld_line<N, 0>(my + p * WORDS, t, x[p]);
+                for (int p = 0; p < NP; ++p) ld_line<N, 0>(my + p * WORDS, t, x[p]);
             }
             {   // x sweep
                 const size_t o = ((size_t)s0 * C + c) * (N / 4) * N + t;
-                thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
+                thomas_solve<N, NP>(x, reinterpret_cast<const float4 *>(T.inv) + o,
                                     reinterpret_cast<const float4 *>(T.e) + o);
             }
             if (active) {
 #pragma unroll
-                for (int p = 0; p < PB; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
+                for (int p = 0; p < NP; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
             }
             __syncwarp();
 #pragma unroll
-            for (int p = 0; p < PB; ++p) ld_line<N, 1>(my + p * WORDS, t, x[p]);
+            for (int p = 0; p < NP; ++p) ld_line<N, 1>(my + p * WORDS, t, x[p]);
             {   // y sweep
                 const size_t o = ((size_t)(s0 + 1) * C + c) * (N / 4) * N + t;
-                thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
+                thomas_solve<N, NP>(x, reinterpret_cast<const float4 *>(T.inv) + o,
                                     reinterpret_cast<const float4 *>(T.e) + o);
             }
             if (active) {
 #pragma unroll
-                for (int p = 0; p < PB; ++p) st_line<N, 1>(my + p * WORDS, t, x[p]);
+                for (int p = 0; p < NP; ++p) st_line<N, 1>(my + p * WORDS, t, x[p]);
             }
             __syncwarp();
             in_regs = false;
             if (a.sps == 3) {
 #pragma unroll
-                for (int p = 0; p < PB; ++p) ld_line<N, 0>(my + p * WORDS, t, x[p]);
+                for (int p = 0; p < NP; ++p) ld_line<N, 0>(my + p * WORDS, t, x[p]);
                 const size_t o = ((size_t)(s0 + 2) * C + c) * (N / 4) * N + t;
-                thomas_solve<N, PB>(x, reinterpret_cast<const float4 *>(T.inv) + o,
+                thomas_solve<N, NP>(x, reinterpret_cast<const float4 *>(T.inv) + o,
                                     reinterpret_cast<const float4 *>(T.e) + o);
                 in_regs = true;
             }
             if (d.chan_op == 2) {
                 if (in_regs && active) {
 #pragma unroll
-                    for (int p = 0; p < PB; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
+                    for (int p = 0; p < NP; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
                 }
                 group_sync(C, group);
-                mix_rows<N, PB>(gtiles, PB, C, a.chan + c * C, 1, t, x);
+                mix_rows<N, NP>(gtiles, C, a.chan + c * C, 1, t, x);
                 group_sync(C, group);
                 in_regs = true;
             }
         }
         if (in_regs && active) {
 #pragma unroll
-            for (int p = 0; p < PB; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
+            for (int p = 0; p < NP; ++p) st_line<N, 0>(my + p * WORDS, t, x[p]);
         }
         __syncwarp();
 #pragma unroll
-        for (int p = 0; p < PB; ++p) {
-            if (b0 + p < d.B) {
-                const size_t off = ((size_t)(b0 + p) * C + c) * plane;
-                tile_to_plane<N>(my + p * WORDS, a.out + off, lane, d.skip ? a.u + off : nullptr, sig, om);
-            }
+        for (int p = 0; p < NP; ++p) {
+            const int ba = b0 + 2 * p, bb = ba + 1;
+            const bool va = ba < d.B, vb = bb < d.B;
+            const size_t oa = ((size_t)(va ? ba : 0) * C + c) * plane, ob = ((size_t)(vb ? bb : 0) * C + c) * plane;
+            tile_to_planes<N>(my + p * WORDS, a.out + oa, a.out + ob, lane, va, vb, d.skip ? a.u + oa : nullptr,
+                              d.skip ? a.u + ob : nullptr, sig, om);
         }
         __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// backward
+// backward: one warp owns channel c of one sample pair
 // ------------------------------------------------------------------------------------------
 
-// checkpoint a lane's lines: scratch[(p*N + i)*32 + lane] (coalesced 128 B per element index);
+// checkpoint a lane's line: scratch pair [i * 32 + lane] (coalesced 256 B per element index);
 // a slot is read back in the orientation it was written in
-template <int N, int PB>
-__device__ __forceinline__ void ck_store(float *slot, int lane, const float (&x)[PB][N]) {
+template <int N>
+__device__ __forceinline__ void ck_store(float *slot, int lane, const f2 (&x)[N]) {
+    unsigned long long *s = reinterpret_cast<unsigned long long *>(slot);
 #pragma unroll
-    for (int p = 0; p < PB; ++p)
-#pragma unroll
-        for (int i = 0; i < N; ++i) __stcg(&slot[(p * N + i) * 32 + lane], x[p][i]);   // L2 only: keep L1 for the tables
+    for (int i = 0; i < N; ++i) __stcg(&s[i * 32 + lane], x[i].v);   // L2 only: keep L1 for the tables
 }
-template <int N, int PB>
-__device__ __forceinline__ void ck_load(const float *slot, int lane, float (&x)[PB][N]) {
+template <int N>
+__device__ __forceinline__ void ck_load(const float *slot, int lane, f2 (&x)[N]) {
+    const unsigned long long *s = reinterpret_cast<const unsigned long long *>(slot);
 #pragma unroll
-    for (int p = 0; p < PB; ++p)
-#pragma unroll
-        for (int i = 0; i < N; ++i) x[p][i] = __ldcg(&slot[(p * N + i) * 32 + lane]);
-}
-template <int N, int PB, int AX>
-__device__ __forceinline__ void ck_to_tile(const float *slot, int lane, int t, bool active, float *tiles) {
-    constexpr int WORDS = Geo<N>::WORDS;
-#pragma unroll
-    for (int p = 0; p < PB; ++p) {
-        float x[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = __ldcg(&slot[(p * N + i) * 32 + lane]);
-        if (active) st_line<N, AX>(tiles + p * WORDS, t, x);
-    }
+    for (int i = 0; i < N; ++i) x[i].v = __ldcg(&s[i * 32 + lane]);
 }
 
 // Per-pixel gradient accumulators live in TMEM: 128 columns per warp = {A0, A1, B0, B1} x 32,
@@ -535,76 +514,107 @@ __device__ __forceinline__ void tmem_accumulate(uint32_t tacc, const float (&z)[
     tmem_st16(tacc + 48, a + 16);
 }
 
-// One reversed sweep on the lines this lane holds in registers (either orientation).
-//   g: adjoint; solved in place through the factorisation A = L U:
+// Four consecutive cells (4q .. 4q+3) of the line owned by lane t, straight from / to the tile.
+template <int N, int AX>
+__device__ __forceinline__ void ld_quad(const float *tile, int t, int q, f2 (&c)[4]) {
+    constexpr int ST = Geo<N>::ST;
+    if (AX == 0) {
+        const ulonglong2 v0 = *reinterpret_cast<const ulonglong2 *>(&tile[(t * ST + 4 * q) * 2]);
+        const ulonglong2 v1 = *reinterpret_cast<const ulonglong2 *>(&tile[(t * ST + 4 * q + 2) * 2]);
+        c[0].v = v0.x; c[1].v = v0.y; c[2].v = v1.x; c[3].v = v1.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            c[k].v = *reinterpret_cast<const unsigned long long *>(&tile[((4 * q + k) * ST + t) * 2]);
+    }
+}
+template <int N, int AX>
+__device__ __forceinline__ void st_quad(float *tile, int t, int q, const f2 (&c)[4]) {
+    constexpr int ST = Geo<N>::ST;
+    if (AX == 0) {
+        ulonglong2 v0, v1;
+        v0.x = c[0].v; v0.y = c[1].v; v1.x = c[2].v; v1.y = c[3].v;
+        *reinterpret_cast<ulonglong2 *>(&tile[(t * ST + 4 * q) * 2]) = v0;
+        *reinterpret_cast<ulonglong2 *>(&tile[(t * ST + 4 * q + 2) * 2]) = v1;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<unsigned long long *>(&tile[((4 * q + k) * ST + t) * 2]) = c[k].v;
+    }
+}
+
+// One reversed sweep.  AX: orientation of the sweep (0: lane = row, 1: lane = column).
+//   g: adjoint of the sweep output, in registers in orientation AX; solved in place through the
+//      factorisation A = L U:
 //        U^T w = g:        w_i = g_i + e_{i-1} w_{i-1}
 //        L^T lambda = w:   lambda_i = inv_i (w_i + r_{i+1} lambda_{i+1})
-//   x: the sweep OUTPUT; inside the back-substitution loop, while lambda_i is fresh,
-//        (L x)_i, v_i += lambda_i (L x)_i, and (if `rebuild`) the sweep INPUT
-//        x_in,i = (1 + eps) x_i - r_i (L x)_i   written in place.
+//   xt: tile holding the sweep OUTPUT (the state is never parked in registers during the reverse
+//      pass: a lane streams its line through a window of two quads).  Inside the back-substitution
+//      loop, while lambda_i is fresh: (L x)_i, v_i = lambda_i (L x)_i summed over the two samples,
+//      and (if `rebuild`) the sweep INPUT x_in,i = (1 + eps) x_i - r_i (L x)_i written back in place,
+//      so that the tile holds the output of the previous sweep when this one returns.
 //   v -> smoothing^T -> clamp mask -> TMEM accumulators of this sweep's kind.
-template <int N, int PB>
-__device__ __forceinline__ void reverse_sweep(float (&g)[PB][N], float (&x)[PB][N], uint32_t tacc,
-                                              const Tables &T, size_t o, float scale, float tt, float onepe,
-                                              bool smooth, bool rebuild, bool clamped) {
-    const float4 *tr = reinterpret_cast<const float4 *>(T.r) + o;
-    const float4 *tinv = reinterpret_cast<const float4 *>(T.inv) + o;
-    const float4 *te = reinterpret_cast<const float4 *>(T.e) + o;
+template <int N, int AX>
+__device__ __forceinline__ void reverse_sweep(f2 (&g)[N], float *xt, int t, bool active, uint32_t tacc,
+                                              const float4 *tr, const float4 *tinv, const float4 *te,
+                                              const float4 *tm, float scale, float tt, float onepe, bool smooth,
+                                              bool rebuild, bool clamped) {
+    constexpr int Q = N / 4;
     float eprev = 0.0f;
     float4 ev_n = __ldg(te);
-    // the back-substitution's first coefficients are requested before the forward pass starts
-    float4 iv_n = __ldg(tinv + (N / 4 - 1) * N), rv_n = __ldg(tr + (N / 4 - 1) * N);
+    // the back-substitution's first coefficients and state quads are requested before the
+    // forward pass starts
+    float4 iv_n = __ldg(tinv + (Q - 1) * N), rv_n = __ldg(tr + (Q - 1) * N);
+    f2 xc[4], xn[4];
+    ld_quad<N, AX>(xt, t, Q - 1, xc);
+    ld_quad<N, AX>(xt, t, Q - 2, xn);
 #pragma unroll
-    for (int q = 0; q < N / 4; ++q) {
+    for (int q = 0; q < Q; ++q) {
         const float4 ev = ev_n;
-        if (q + 1 < N / 4) ev_n = __ldg(te + (q + 1) * N);
+        if (q + 1 < Q) ev_n = __ldg(te + (q + 1) * N);
         const float evs[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int i = 4 * q + k;
-            if (i > 0) {
-#pragma unroll
-                for (int p = 0; p < PB; ++p) g[p][i] = fmaf(eprev, g[p][i - 1], g[p][i]);
-            }
+            if (i > 0) g[i] = f2_fmas(eprev, g[i - 1], g[i]);
             eprev = evs[k];
         }
     }
     float v[N];
-    float xnext[PB];   // value of x_{i+1} before it was rebuilt
-#pragma unroll
-    for (int p = 0; p < PB; ++p) xnext[p] = 0.0f;
+    f2 xnext = f2_bc(0.0f);   // value of x_{i+1} before it was rebuilt
     float rnext = 0.0f;
 #pragma unroll
-    for (int q = N / 4 - 1; q >= 0; --q) {
+    for (int q = Q - 1; q >= 0; --q) {
         const float4 iv = iv_n, rv = rv_n;
         if (q > 0) {
             iv_n = __ldg(tinv + (q - 1) * N);
             rv_n = __ldg(tr + (q - 1) * N);
         }
         const float ivs[4] = {iv.x, iv.y, iv.z, iv.w}, rvs[4] = {rv.x, rv.y, rv.z, rv.w};
+        f2 xo[4];
 #pragma unroll
         for (int k = 3; k >= 0; --k) {
             const int i = 4 * q + k;
-            float vi = 0.0f;
-#pragma unroll
-            for (int p = 0; p < PB; ++p) {
-                const float lam = (i == N - 1) ? g[p][i] * ivs[k] : fmaf(rnext * ivs[k], g[p][i + 1], g[p][i] * ivs[k]);
-                g[p][i] = lam;
-                const float cur = x[p][i];
-                float lx;
-                if (i == N - 1)
-                    lx = x[p][N - 2] - cur;
-                else if (i == 0)
-                    lx = xnext[p] - cur;
-                else
-                    lx = (x[p][i - 1] - cur) + (xnext[p] - cur);
-                vi = fmaf(lam, lx, vi);
-                if (rebuild) x[p][i] = fmaf(-rvs[k], lx, onepe * cur);
-                xnext[p] = cur;
-            }
-            v[i] = vi;
+            const f2 gi = f2_muls(ivs[k], g[i]);
+            const f2 lam = (i == N - 1) ? gi : f2_fmas(rnext * ivs[k], g[i + 1], gi);
+            g[i] = lam;
+            const f2 cur = xc[k];
+            f2 lx;
+            if (i == N - 1)
+                lx = f2_sub(xc[k - 1], cur);
+            else if (i == 0)
+                lx = f2_sub(xnext, cur);
+            else
+                lx = f2_fmas(-2.0f, cur, f2_add(k > 0 ? xc[k - 1] : xn[3], xnext));
+            v[i] = f2_hsum(f2_mul(lam, lx));
+            xo[k] = f2_fmas(-rvs[k], lx, f2_muls(onepe, cur));
+            xnext = cur;
             rnext = rvs[k];
         }
+        if (rebuild && active) st_quad<N, AX>(xt, t, q, xo);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xc[k] = xn[k];
+        if (q >= 2) ld_quad<N, AX>(xt, t, q - 2, xn);
     }
     // smoothing^T along the line (replicate padding puts the end taps back on the end cells)
     if (smooth) {
@@ -622,9 +632,8 @@ __device__ __forceinline__ void reverse_sweep(float (&g)[PB][N], float (&x)[PB][
         for (int i = 0; i < N; ++i) v[i] *= scale;
     }
     if (clamped) {
-        const float4 *tm = reinterpret_cast<const float4 *>(T.msk) + o;
 #pragma unroll
-        for (int q = 0; q < N / 4; ++q) {
+        for (int q = 0; q < Q; ++q) {
             const float4 m = __ldg(tm + q * N);
             v[4 * q] *= m.x; v[4 * q + 1] *= m.y; v[4 * q + 2] *= m.z; v[4 * q + 3] *= m.w;
         }
@@ -634,43 +643,35 @@ __device__ __forceinline__ void reverse_sweep(float (&g)[PB][N], float (&x)[PB][
 
 // Adjoint of a channel op on the group's g tiles (rows), using the op's INPUT state in the x
 // tiles:  gm[dd] += sum g_c * x_dd ;  g_c <- sum_c' mat[c'][c] g_c'.
-template <int N, int PB>
+template <int N>
 __device__ __forceinline__ void chan_adjoint(float *ggt, float *gxt, int C, int c, int group,
                                              const float *__restrict__ mat, int t, bool active,
                                              float (&gm)[PDE_MAX_CHANNELS]) {
     constexpr int WORDS = Geo<N>::WORDS;
     group_sync(C, group);
     if (active) {
+        f2 g[N];
+        ld_line<N, 0>(ggt + (size_t)c * WORDS, t, g);
+        for (int dd = 0; dd < C; ++dd) {
+            f2 x[N];
+            ld_line<N, 0>(gxt + (size_t)dd * WORDS, t, x);
+            f2 acc = f2_bc(0.0f);
 #pragma unroll
-        for (int p = 0; p < PB; ++p) {
-            float g[N];
-            ld_line<N, 0>(ggt + ((size_t)c * PB + p) * WORDS, t, g);
-            for (int dd = 0; dd < C; ++dd) {
-                float x[N];
-                ld_line<N, 0>(gxt + ((size_t)dd * PB + p) * WORDS, t, x);
-                float acc = 0.0f;
-#pragma unroll
-                for (int i = 0; i < N; ++i) acc = fmaf(g[i], x[i], acc);
-                gm[dd] += acc;
-            }
+            for (int i = 0; i < N; ++i) acc = f2_fma(g[i], x[i], acc);
+            gm[dd] += f2_hsum(acc);
         }
     }
-    float gn[PB][N];
-    mix_rows<N, PB>(ggt, PB, C, mat + c, C, t, gn);
+    f2 gn[1][N];
+    mix_rows<N, 1>(ggt, C, mat + c, C, t, gn);
     group_sync(C, group);
-    if (active) {
-#pragma unroll
-        for (int p = 0; p < PB; ++p) st_line<N, 0>(ggt + ((size_t)c * PB + p) * WORDS, t, gn[p]);
-    }
+    if (active) st_line<N, 0>(ggt + (size_t)c * WORDS, t, gn[0]);
     __syncwarp();
 }
 
-// RB = resident blocks the register allocation must allow for a 192-thread block:
-// 1 -> 255 registers, 2 -> 168, 3 -> 96-112.
-template <int N, int PB, int RB>
-__global__ void __launch_bounds__(192, RB) bwd_kernel(const Args a) {
+template <int N, bool CHAN>
+__global__ void __launch_bounds__(192, 1) bwd_kernel(const Args a) {
     constexpr int WORDS = Geo<N>::WORDS;
-    constexpr int SLOT = PB * N * 32;
+    constexpr int SLOT = 2 * N * 32;   // floats per checkpoint slot
     extern __shared__ __align__(16) float smem[];
     __shared__ uint32_t tmem_slot;
     const pde_adi_desc &d = a.d;
@@ -679,12 +680,11 @@ __global__ void __launch_bounds__(192, RB) bwd_kernel(const Args a) {
     const int C = d.C, group = warp / C, c = warp % C;
     const bool active = lane < N;
     const int t = active ? lane : N - 1;
-    // Shared memory is only a transposition medium: one set of PB tiles per warp, two sets when a
-    // cross-channel op (or the skip epilogue) needs the state and the adjoint side by side.
-    const bool shared_set = a.tile_sets == 1;
-    float *gxt = smem + (size_t)group * C * PB * WORDS;
-    float *ggt = (shared_set ? smem : smem + (size_t)nwarps * PB * WORDS) + (size_t)group * C * PB * WORDS;
-    float *xt = gxt + (size_t)c * PB * WORDS, *gt = ggt + (size_t)c * PB * WORDS;
+    // Two tiles per warp: the state (streamed in place by the reverse sweeps) and the adjoint
+    // (transposed through its tile between sweeps of different orientation).
+    float *gxt = smem + (size_t)group * C * WORDS;
+    float *ggt = smem + (size_t)nwarps * WORDS + (size_t)group * C * WORDS;
+    float *xt = gxt + (size_t)c * WORDS, *gt = ggt + (size_t)c * WORDS;
 
     // TMEM: 128 columns per warp, lane quadrant = warp % 4
     if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)a.tmem_cols);
@@ -711,7 +711,22 @@ __global__ void __launch_bounds__(192, RB) bwd_kernel(const Args a) {
         h_t[i] = T.hdr->t[i];
         h_clamped[i] = T.hdr->clamped[i];
     }
+    constexpr int PLANE4 = N * N / 4;
     __syncthreads();
+    // tables of sweep s for this lane's line
+    auto sweep_tables = [&](int s, const float4 *&pr, const float4 *&pinv, const float4 *&pe) {
+        const size_t o = ((size_t)s * C + c) * PLANE4 + t;
+        pr = reinterpret_cast<const float4 *>(T.r) + o;
+        pinv = reinterpret_cast<const float4 *>(T.inv) + o;
+        pe = reinterpret_cast<const float4 *>(T.e) + o;
+    };
+    // pull the table rows of a sweep into L1 one sweep ahead
+    auto prefetch_sweep = [&](int s, bool with_r) {
+        if (s < 0 || s >= a.S) return;
+        const size_t o = ((size_t)s * C + c) * PLANE4 + t;
+        prefetch_tables<N>(reinterpret_cast<const float4 *>(T.inv) + o, reinterpret_cast<const float4 *>(T.e) + o,
+                           with_r ? reinterpret_cast<const float4 *>(T.r) + o : nullptr);
+    };
     const size_t plane = (size_t)N * N;
     const int wg = blockIdx.x * nwarps + warp;
     float *scratch = a.scratch + (size_t)wg * a.S * SLOT;
@@ -726,238 +741,208 @@ __global__ void __launch_bounds__(192, RB) bwd_kernel(const Args a) {
     const int last_ax = (sps == 3) ? 0 : 1;  // orientation of the state after the last sweep of a step
 
     for (int item = blockIdx.x * a.G + group; item < a.nitems; item += gridDim.x * a.G) {
-        const int b0 = item * PB;
-        float x[PB][N];
+        const int ba = item * 2, bb = ba + 1;
+        const bool va = ba < d.B, vb = bb < d.B;
+        const size_t oa = ((size_t)(va ? ba : 0) * C + c) * plane, ob = ((size_t)(vb ? bb : 0) * C + c) * plane;
+        f2 x[1][N];
         int x_ax = -1;   // orientation of x in registers (0 rows, 1 columns), -1: the tile holds it
         auto x_store = [&](int ax) {
             if (active) {
-#pragma unroll
-                for (int p = 0; p < PB; ++p) {
-                    if (ax == 0) st_line<N, 0>(xt + p * WORDS, t, x[p]);
-                    else st_line<N, 1>(xt + p * WORDS, t, x[p]);
-                }
+                if (ax == 0) st_line<N, 0>(xt, t, x[0]);
+                else st_line<N, 1>(xt, t, x[0]);
             }
         };
         auto x_load = [&](int ax) {
-#pragma unroll
-            for (int p = 0; p < PB; ++p) {
-                if (ax == 0) ld_line<N, 0>(xt + p * WORDS, t, x[p]);
-                else ld_line<N, 1>(xt + p * WORDS, t, x[p]);
-            }
+            if (ax == 0) ld_line<N, 0>(xt, t, x[0]);
+            else ld_line<N, 1>(xt, t, x[0]);
         };
         // ------------------------------ phase 1: forward trajectory with checkpoints
-#pragma unroll
-        for (int p = 0; p < PB; ++p) {
-            const bool valid = b0 + p < d.B;
-            plane_to_tile<N>(a.u + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, xt + p * WORDS, lane, valid);
-        }
+        planes_to_tile<N>(a.u + oa, a.u + ob, xt, lane, va, vb);
         __syncwarp();
         for (int step = 0; step < d.steps; ++step) {
-            if (d.chan_op == 1) {
-                if (x_ax >= 0) x_store(x_ax);
+            if (CHAN && d.chan_op == 1) {
+                if (x_ax >= 0) {
+                    __syncwarp();
+                    x_store(x_ax);
+                }
                 group_sync(C, group);
-                mix_rows<N, PB>(gxt, PB, C, a.chan + c * C, 1, t, x);
+                mix_rows<N, 1>(gxt, C, a.chan + c * C, 1, t, x);
                 group_sync(C, group);
                 x_ax = 0;
             }
             // straight-line x, y, (x) sweeps: a loop over the sweeps of a step keeps ptxas from
             // scheduling the next sweep's coefficient loads across the transposition
             const int s0 = step * sps;
-            const size_t o0 = ((size_t)s0 * C + c) * (N / 4) * N + t, ostride = (size_t)C * (N / 4) * N;
-            auto tab = [&](const float *base, size_t o) { return reinterpret_cast<const float4 *>(base) + o; };
+            const float4 *pr, *pinv, *pe;
             if (x_ax != 0) {
                 if (x_ax >= 0) {
+                    __syncwarp();
                     x_store(x_ax);
                     __syncwarp();
                 }
                 x_load(0);
             }
-            prefetch_tables<N>(tab(T.inv, o0 + ostride), tab(T.e, o0 + ostride), nullptr);
-            thomas_solve<N, PB>(x, tab(T.inv, o0), tab(T.e, o0));
-            if (exact) ck_store<N, PB>(scratch + (size_t)s0 * SLOT, lane, x);
+            prefetch_sweep(s0 + 1, false);
+            sweep_tables(s0, pr, pinv, pe);
+            thomas_solve<N, 1>(x, pinv, pe);
+            if (exact) ck_store<N>(scratch + (size_t)s0 * SLOT, lane, x[0]);
             x_store(0);
             __syncwarp();
             x_load(1);
-            if (s0 + 2 < a.S)
-                prefetch_tables<N>(tab(T.inv, o0 + 2 * ostride), tab(T.e, o0 + 2 * ostride), nullptr);
-            else
-                prefetch_tables<N>(tab(T.r, o0 + ostride), tab(T.r, o0 + ostride), nullptr);
-            thomas_solve<N, PB>(x, tab(T.inv, o0 + ostride), tab(T.e, o0 + ostride));
+            prefetch_sweep(s0 + 2, false);
+            sweep_tables(s0 + 1, pr, pinv, pe);
+            thomas_solve<N, 1>(x, pinv, pe);
             x_ax = 1;
-            if (exact || sps == 2) ck_store<N, PB>(scratch + (size_t)(s0 + 1) * SLOT, lane, x);
+            if (exact || sps == 2) ck_store<N>(scratch + (size_t)(s0 + 1) * SLOT, lane, x[0]);
             if (sps == 3) {
                 x_store(1);
                 __syncwarp();
                 x_load(0);
-                if (s0 + 3 < a.S)
-                    prefetch_tables<N>(tab(T.inv, o0 + 3 * ostride), tab(T.e, o0 + 3 * ostride), nullptr);
-                else
-                    prefetch_tables<N>(tab(T.r, o0 + 2 * ostride), tab(T.r, o0 + 2 * ostride), nullptr);
-                thomas_solve<N, PB>(x, tab(T.inv, o0 + 2 * ostride), tab(T.e, o0 + 2 * ostride));
+                prefetch_sweep(s0 + 3, false);
+                sweep_tables(s0 + 2, pr, pinv, pe);
+                thomas_solve<N, 1>(x, pinv, pe);
                 x_ax = 0;
-                ck_store<N, PB>(scratch + (size_t)(s0 + 2) * SLOT, lane, x);
+                ck_store<N>(scratch + (size_t)(s0 + 2) * SLOT, lane, x[0]);
             }
-            if (d.chan_op == 2) {
+            if (CHAN && d.chan_op == 2) {
+                __syncwarp();
                 x_store(x_ax);
                 group_sync(C, group);
-                mix_rows<N, PB>(gxt, PB, C, a.chan + c * C, 1, t, x);
+                mix_rows<N, 1>(gxt, C, a.chan + c * C, 1, t, x);
                 group_sync(C, group);
                 x_ax = 0;
             }
         }
         // the skip epilogue needs the FINAL state (after the last coupling): park it in the x tile
         if (d.skip && x_ax >= 0) {
-            if (x_ax == 1) __syncwarp();
+            __syncwarp();
             x_store(x_ax);
         }
         __syncwarp();
         // ------------------------------ phase 2: reverse
         {   // the next item's input planes start their trip from HBM to L2 now
-            const int nb0 = (item + gridDim.x * a.G) * PB;
+            const int nb = (item + gridDim.x * a.G) * 2;
 #pragma unroll
-            for (int p = 0; p < PB; ++p)
-                if (nb0 + p < d.B) {
-                    prefetch_plane_l2<N>(a.u + ((size_t)(nb0 + p) * C + c) * plane, lane);
-                    prefetch_plane_l2<N>(a.gout + ((size_t)(nb0 + p) * C + c) * plane, lane);
+            for (int p = 0; p < 2; ++p)
+                if (nb + p < d.B) {
+                    prefetch_plane_l2<N>(a.u + ((size_t)(nb + p) * C + c) * plane, lane);
+                    prefetch_plane_l2<N>(a.gout + ((size_t)(nb + p) * C + c) * plane, lane);
                 }
         }
-        float g[PB][N];
-        int g_ax = -1;
-        auto g_store = [&](int ax) {
-            if (active) {
-#pragma unroll
-                for (int p = 0; p < PB; ++p) {
-                    if (ax == 0) st_line<N, 0>(gt + p * WORDS, t, g[p]);
-                    else st_line<N, 1>(gt + p * WORDS, t, g[p]);
-                }
-            }
-        };
-        auto g_load = [&](int ax) {
-#pragma unroll
-            for (int p = 0; p < PB; ++p) {
-                if (ax == 0) ld_line<N, 0>(gt + p * WORDS, t, g[p]);
-                else ld_line<N, 1>(gt + p * WORDS, t, g[p]);
-            }
-        };
-#pragma unroll
-        for (int p = 0; p < PB; ++p) {
-            const bool valid = b0 + p < d.B;
-            plane_to_tile<N>(a.gout + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, gt + p * WORDS, lane, valid);
-        }
+        planes_to_tile<N>(a.gout + oa, a.gout + ob, gt, lane, va, vb);
         __syncwarp();
         if (d.skip) {
             // out = sig u0 + om uF:  dL/dw += sig' * sum gout (u0 - uF),  g <- om * gout
-            float accw = 0.0f;
+            if (active) {
+                f2 accw = f2_bc(0.0f);
+                f2 gl[N], uf[N];
+                ld_line<N, 0>(gt, t, gl);
+                ld_line<N, 0>(xt, t, uf);
+                const float2 zero2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int p = 0; p < PB; ++p) {
-                if (b0 + p < d.B && active) {
-                    const float4 *u4 = reinterpret_cast<const float4 *>(a.u + ((size_t)(b0 + p) * C + c) * plane + (size_t)t * N);
-#pragma unroll
-                    for (int q = 0; q < N / 4; ++q) {
-                        float4 g4 = ld4<N, 0>(gt + p * WORDS, t, q);
-                        const float4 uf = ld4<N, 0>(xt + p * WORDS, t, q);
-                        const float4 u0 = __ldg(u4 + q);
-                        accw = fmaf(g4.x, u0.x - uf.x, accw);
-                        accw = fmaf(g4.y, u0.y - uf.y, accw);
-                        accw = fmaf(g4.z, u0.z - uf.z, accw);
-                        accw = fmaf(g4.w, u0.w - uf.w, accw);
-                        g4.x *= om; g4.y *= om; g4.z *= om; g4.w *= om;
-                        st4<N, 0>(gt + p * WORDS, t, q, g4);
-                    }
+                for (int j = 0; j < N / 2; ++j) {
+                    const float2 wa = va ? __ldg(reinterpret_cast<const float2 *>(a.u + oa + (size_t)t * N) + j) : zero2;
+                    const float2 wb = vb ? __ldg(reinterpret_cast<const float2 *>(a.u + ob + (size_t)t * N) + j) : zero2;
+                    accw = f2_fma(gl[2 * j], f2_sub(f2_make(wa.x, wb.x), uf[2 * j]), accw);
+                    accw = f2_fma(gl[2 * j + 1], f2_sub(f2_make(wa.y, wb.y), uf[2 * j + 1]), accw);
+                    gl[2 * j] = f2_muls(om, gl[2 * j]);
+                    gl[2 * j + 1] = f2_muls(om, gl[2 * j + 1]);
                 }
+                st_line<N, 0>(gt, t, gl);
+                gw += f2_hsum(accw);
             }
-            gw += accw;
             __syncwarp();
         }
-        for (int step = d.steps - 1; step >= 0; --step) {
-            const int sl = step * sps + sps - 1;
-            // state after the last sweep of this step: straight from the checkpoint into registers
-            ck_load<N, PB>(scratch + (size_t)sl * SLOT, lane, x);
-            x_ax = last_ax;
-            if (d.chan_op == 2) {
-                // adjoint of the post-step coupling works on the group's tiles (rows)
-                if (g_ax >= 0) {
-                    g_store(g_ax);
-                    g_ax = -1;
-                }
-                x_store(x_ax);
-                __syncwarp();
-                chan_adjoint<N, PB>(ggt, gxt, C, c, group, a.chan, t, active, gm);
+        auto g_store = [&](const f2 (&g)[N], int ax) {
+            if (active) {
+                if (ax == 0) st_line<N, 0>(gt, t, g);
+                else st_line<N, 1>(gt, t, g);
             }
+        };
+        // checkpoint slot -> x tile (a slot is read back in the orientation it was written in)
+        auto ck_to_xt = [&](int slot, int ax) {
+            f2 xs[N];
+            ck_load<N>(scratch + (size_t)slot * SLOT, lane, xs);
+            __syncwarp();   // every lane is done with the previous content of the tile
+            if (active) {
+                if (ax == 0) st_line<N, 0>(xt, t, xs);
+                else st_line<N, 1>(xt, t, xs);
+            }
+        };
+        // the reversed sweeps of one step; g sits in registers in orientation g_ax (-1: in its tile)
+        auto reverse_step = [&](f2 (&g)[N], int &g_ax, int step) {
             for (int k = sps - 1; k >= 0; --k) {
                 const int s = step * sps + k, ax = sweep_axis(k);
-                if (exact && k != sps - 1) {
-                    ck_load<N, PB>(scratch + (size_t)s * SLOT, lane, x);
-                    x_ax = ax;
-                }
+                if (exact && k != sps - 1) ck_to_xt(s, ax);
                 if (g_ax != ax) {
-                    if (g_ax >= 0) {
-                        if (shared_set) __syncwarp();
-                        g_store(g_ax);
-                    }
+                    if (g_ax >= 0) g_store(g, g_ax);
                     __syncwarp();
-                    g_load(ax);
+                    if (ax == 0) ld_line<N, 0>(gt, t, g);
+                    else ld_line<N, 1>(gt, t, g);
                     g_ax = ax;
-                }
-                if (x_ax != ax) {
-                    if (shared_set) __syncwarp();
-                    x_store(x_ax);
+                } else {
                     __syncwarp();
-                    x_load(ax);
-                    x_ax = ax;
                 }
-                const size_t o = ((size_t)s * C + c) * (N / 4) * N + t;
-                if (s > 0) {
-                    const size_t op = o - (size_t)C * (N / 4) * N;   // tables of the sweep reversed next -> L1
-                    prefetch_tables<N>(reinterpret_cast<const float4 *>(T.inv) + op,
-                                       reinterpret_cast<const float4 *>(T.e) + op,
-                                       reinterpret_cast<const float4 *>(T.r) + op);
-                }
+                const float4 *pr, *pinv, *pe;
+                sweep_tables(s, pr, pinv, pe);
+                prefetch_sweep(s - 1, true);
+                const float4 *pm = reinterpret_cast<const float4 *>(T.msk) + ((size_t)s * C + c) * PLANE4 + t;
                 const float scale = h_scale[s], tt = h_t[s];
                 const bool clamped = h_clamped[s] != 0;
                 const bool rebuild = !exact && k > 0;
-                reverse_sweep<N, PB>(g, x, tbase + (uint32_t)(ax * 64), T, o, scale, tt, onepe, smooth, rebuild, clamped);
+                if (ax == 0)
+                    reverse_sweep<N, 0>(g, xt, t, active, tbase, pr, pinv, pe, pm, scale, tt, onepe, smooth, rebuild, clamped);
+                else
+                    reverse_sweep<N, 1>(g, xt, t, active, tbase + 64u, pr, pinv, pe, pm, scale, tt, onepe, smooth, rebuild, clamped);
             }
-            if (d.chan_op == 1) {
-                // adjoint of the pre-step mix: needs g (rows) and the mix INPUT = state before this
-                // step = checkpoint of the previous step (or u) in the group's tiles
-                g_store(g_ax);
-                g_ax = -1;
-                if (step > 0) {
-                    if (last_ax == 0)
-                        ck_to_tile<N, PB, 0>(scratch + (size_t)(step * sps - 1) * SLOT, lane, t, active, xt);
-                    else
-                        ck_to_tile<N, PB, 1>(scratch + (size_t)(step * sps - 1) * SLOT, lane, t, active, xt);
-                } else {
-#pragma unroll
-                    for (int p = 0; p < PB; ++p) {
-                        const bool valid = b0 + p < d.B;
-                        plane_to_tile<N>(a.u + ((size_t)(valid ? b0 + p : 0) * C + c) * plane, xt + p * WORDS, lane, valid);
-                    }
+        };
+        if (CHAN) {
+            // a channel op sits at one end of every step and works on the group's tiles: the adjoint
+            // lives in registers only inside a step
+            for (int step = d.steps - 1; step >= 0; --step) {
+                // state after the last sweep of this step = input of the post-step coupling
+                ck_to_xt(step * sps + sps - 1, last_ax);
+                if (d.chan_op == 2) {
+                    __syncwarp();
+                    chan_adjoint<N>(ggt, gxt, C, c, group, a.chan, t, active, gm);
                 }
-                __syncwarp();
-                chan_adjoint<N, PB>(ggt, gxt, C, c, group, a.chan, t, active, gm);
+                {
+                    f2 g[N];
+                    int g_ax = -1;
+                    reverse_step(g, g_ax, step);
+                    g_store(g, g_ax);
+                }
+                if (d.chan_op == 1) {
+                    // adjoint of the pre-step mix: needs g (rows) and the mix INPUT = state before
+                    // this step = checkpoint of the previous step (or u) in the group's tiles
+                    if (step > 0) {
+                        ck_to_xt(step * sps - 1, last_ax);
+                    } else {
+                        __syncwarp();
+                        planes_to_tile<N>(a.u + oa, a.u + ob, xt, lane, va, vb);
+                    }
+                    __syncwarp();
+                    chan_adjoint<N>(ggt, gxt, C, c, group, a.chan, t, active, gm);
+                }
             }
-        }
-        if (g_ax >= 0) {
-            if (shared_set) __syncwarp();
-            g_store(g_ax);
+        } else {
+            f2 g[N];
+            int g_ax = -1;
+            for (int step = d.steps - 1; step >= 0; --step) {
+                ck_to_xt(step * sps + sps - 1, last_ax);
+                reverse_step(g, g_ax, step);
+            }
+            if (g_ax >= 0) g_store(g, g_ax);
         }
         __syncwarp();
-        if (a.need_gin) {
-#pragma unroll
-            for (int p = 0; p < PB; ++p) {
-                if (b0 + p < d.B) {
-                    const size_t off = ((size_t)(b0 + p) * C + c) * plane;
-                    tile_to_plane<N>(gt + p * WORDS, a.gin + off, lane, d.skip ? a.gout + off : nullptr, sig, 1.0f);
-                }
-            }
-        }
+        if (a.need_gin)
+            tile_to_planes<N>(gt, a.gin + oa, a.gin + ob, lane, va, vb, d.skip ? a.gout + oa : nullptr,
+                              d.skip ? a.gout + ob : nullptr, sig, 1.0f);
         __syncwarp();
         // the next item's phase 1 mixes through the group's x tiles: nobody may still read them
-        if (d.chan_op != 0) group_sync(C, group);
+        if (CHAN) group_sync(C, group);
     }
-    // ------------------------------ per-warp partials: TMEM -> tile (line orientation) -> global
+    // ------------------------------ per-warp partials: TMEM -> global (cell order [row][col])
     tmem_wait_st();
     float *pm = a.part_maps + (size_t)wg * 4 * plane;
 #pragma unroll
@@ -966,16 +951,17 @@ __global__ void __launch_bounds__(192, RB) bwd_kernel(const Args a) {
         tmem_ld16(tbase + kk * 32, av);
         tmem_ld16(tbase + kk * 32 + 16, av + 16);
         tmem_wait_ld();
-        float ln[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) ln[i] = av[i];
-        __syncwarp();
         if (active) {
-            if (kk < 2) st_line<N, 0>(xt, t, ln);
-            else st_line<N, 1>(xt, t, ln);
+            if (kk < 2) {   // lane = row
+#pragma unroll
+                for (int q = 0; q < N / 4; ++q)
+                    *reinterpret_cast<float4 *>(pm + kk * plane + (size_t)t * N + 4 * q) =
+                        make_float4(av[4 * q], av[4 * q + 1], av[4 * q + 2], av[4 * q + 3]);
+            } else {        // lane = column
+#pragma unroll
+                for (int i = 0; i < N; ++i) pm[kk * plane + (size_t)i * N + t] = av[i];
+            }
         }
-        __syncwarp();
-        tile_to_plane<N>(xt, pm + kk * plane, lane, nullptr, 0.f, 1.f);
     }
 #pragma unroll
     for (int dd = 0; dd < PDE_MAX_CHANNELS; ++dd) {
@@ -1073,36 +1059,27 @@ static int env_int(const char *name, int dflt) {
     return atoi(v);
 }
 
-static int tile_words(int N) { return N * ((N % 8 == 4) ? N : N + 4); }
+static int tile_words(int N) { return 2 * N * (N + 2); }   // one tile = one sample pair
 
 struct BwdPlan {
-    int PB, RB, G, warps, blocks_per_sm, grid, nitems, tile_sets, tmem_cols;
+    int G, warps, blocks_per_sm, grid, nitems, tile_sets, tmem_cols;
     size_t smem, scratch_floats, maps_floats, chan_floats, skip_floats;
 };
-
-static int bwd_pb() {
-    int pb = env_int("PDE_B200_BWD_PB", 2);
-    return pb == 1 ? 1 : 2;
-}
-// Two builds of the backward kernel: {PB = 2, 255 registers, 8 warps / SM} (default: fastest on
-// every layer measured) and {PB = 1, 168 registers, 12 warps / SM} (PDE_B200_BWD_PB=1).
-static int bwd_rb(int PB) { return PB == 2 ? 1 : 2; }
 
 static int bwd_groups(int C) { return C == 1 ? 4 : (C == 2 ? 2 : (C == 3 ? 2 : 1)); }
 
 template <int N>
-static const void *bwd_kernel_ptr(int PB, int RB) {
-    (void)RB;
-    return PB == 2 ? reinterpret_cast<const void *>(bwd_kernel<N, 2, 1>) : reinterpret_cast<const void *>(bwd_kernel<N, 1, 2>);
+static const void *bwd_kernel_ptr(bool chan) {
+    return chan ? reinterpret_cast<const void *>(bwd_kernel<N, true>) : reinterpret_cast<const void *>(bwd_kernel<N, false>);
 }
 
-static const void *bwd_kernel_for(int N, int PB, int RB) {
+static const void *bwd_kernel_for(int N, bool chan) {
     switch (N) {
-        case 8: return bwd_kernel_ptr<8>(PB, RB);
-        case 12: return bwd_kernel_ptr<12>(PB, RB);
-        case 16: return bwd_kernel_ptr<16>(PB, RB);
-        case 28: return bwd_kernel_ptr<28>(PB, RB);
-        case 32: return bwd_kernel_ptr<32>(PB, RB);
+        case 8: return bwd_kernel_ptr<8>(chan);
+        case 12: return bwd_kernel_ptr<12>(chan);
+        case 16: return bwd_kernel_ptr<16>(chan);
+        case 28: return bwd_kernel_ptr<28>(chan);
+        case 32: return bwd_kernel_ptr<32>(chan);
         default: return nullptr;
     }
 }
@@ -1111,15 +1088,13 @@ static int plan_bwd(const pde_adi_desc *d, BwdPlan *p) {
     DeviceProps props;
     int rc = query_props(&props);
     if (rc) return rc;
-    p->PB = bwd_pb();
     p->G = bwd_groups(d->C);
     p->warps = p->G * d->C;
-    p->tile_sets = (d->chan_op != 0 || d->skip) ? 2 : 1;
+    p->tile_sets = 2;
     p->tmem_cols = p->warps <= 4 ? 128 : (p->warps <= 8 ? 256 : 512);
-    p->smem = (size_t)p->tile_sets * p->warps * p->PB * tile_words(d->N) * sizeof(float);
+    p->smem = (size_t)p->tile_sets * p->warps * tile_words(d->N) * sizeof(float);
     if (p->smem > (size_t)props.max_smem_optin || p->warps > 16) return PDE_ERR_UNSUPPORTED;
-    p->RB = bwd_rb(p->PB);
-    const void *kern = bwd_kernel_for(d->N, p->PB, p->RB);
+    const void *kern = bwd_kernel_for(d->N, d->chan_op != 0);
     if (!kern) return PDE_ERR_UNSUPPORTED;
     PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     // Residency from first principles: the occupancy calculator answers 1 block / SM for kernels
@@ -1138,17 +1113,17 @@ static int plan_bwd(const pde_adi_desc *d, BwdPlan *p) {
     if (by_tmem < occ) occ = by_tmem;
     p->blocks_per_sm = occ;
     if (env_int("PDE_B200_DEBUG", 0))
-        fprintf(stderr, "[pde_b200] bwd plan: N=%d C=%d PB=%d RB=%d warps=%d smem=%zu regs=%d by_regs=%d by_smem=%d by_tmem=%d\n",
-                d->N, d->C, p->PB, p->RB, p->warps, p->smem, fa.numRegs, by_regs, by_smem, by_tmem);
+        fprintf(stderr, "[pde_b200] bwd plan: N=%d C=%d warps=%d smem=%zu regs=%d by_regs=%d by_smem=%d by_tmem=%d\n",
+                d->N, d->C, p->warps, p->smem, fa.numRegs, by_regs, by_smem, by_tmem);
     if (p->blocks_per_sm < 1) p->blocks_per_sm = 1;
-    p->nitems = (d->B + p->PB - 1) / p->PB;
+    p->nitems = (d->B + 1) / 2;
     int want = (p->nitems + p->G - 1) / p->G;
     int cap = props.sm_count * p->blocks_per_sm;
     p->grid = want < cap ? want : cap;
     if (p->grid < 1) p->grid = 1;
     const size_t S = (size_t)d->steps * sweeps_per_step(*d);
     const size_t nw = (size_t)p->grid * p->warps;
-    p->scratch_floats = nw * (S > 0 ? S : 1) * p->PB * d->N * 32;
+    p->scratch_floats = nw * (S > 0 ? S : 1) * 2 * d->N * 32;
     p->maps_floats = nw * 4 * d->N * d->N;
     p->chan_floats = nw * PDE_MAX_CHANNELS;
     p->skip_floats = nw;
@@ -1156,21 +1131,22 @@ static int plan_bwd(const pde_adi_desc *d, BwdPlan *p) {
 }
 
 template <int N>
-static int launch_fwd(const Args &a, int PB, int grid, int threads, size_t smem, cudaStream_t st) {
+static int launch_fwd(const Args &a, int NP, int sm_count, int threads, size_t smem, cudaStream_t st) {
     auto go = [&](auto kern) -> int {
         PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, st>>>(a);
+        // persistent grid: exactly the blocks that are resident at once (registers included)
+        int per_sm = 1;
+        PDE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+        if (per_sm < 1) per_sm = 1;
+        const int want = (a.nitems + a.G - 1) / a.G, cap = sm_count * per_sm;
+        kern<<<want < cap ? want : cap, threads, smem, st>>>(a);
         return cuda_last_error();
     };
-    switch (PB) {
-        case 1: return go(fwd_kernel<N, 1>);
-        case 2: return go(fwd_kernel<N, 2>);
-        default: return go(fwd_kernel<N, 4>);
-    }
+    return NP == 1 ? go(fwd_kernel<N, 1>) : go(fwd_kernel<N, 2>);
 }
 
 static int launch_bwd(const Args &a, const BwdPlan &p, cudaStream_t st) {
-    const void *kern = bwd_kernel_for(a.d.N, p.PB, p.RB);
+    const void *kern = bwd_kernel_for(a.d.N, a.d.chan_op != 0);
     if (!kern) return PDE_ERR_UNSUPPORTED;
     void *params[] = {const_cast<Args *>(&a)};
     PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(p.grid), dim3(p.warps * 32), params, p.smem, st));
@@ -1243,28 +1219,20 @@ extern "C" int pde_adi_forward(const pde_adi_desc *d, const void *tables, const 
     a.sps = sweeps_per_step(*d);
     a.S = d->steps * a.sps;
     a.G = groups_per_block(d->C);
-    int PB = env_int("PDE_B200_FWD_PB", 2);
-    if (PB != 1 && PB != 2) PB = 4;
-    // small batches: spread samples over more warps instead of stacking them in one
-    while (PB > 1 && (d->B + PB - 1) / PB < props.sm_count * 4 * a.G) PB >>= 1;
-    a.nitems = (d->B + PB - 1) / PB;
+    // a warp advances NP sample pairs; small batches spread over more warps instead
+    int NP = env_int("PDE_B200_FWD_NP", 2) == 1 ? 1 : 2;
+    if (NP == 2 && (d->B + 3) / 4 < props.sm_count * 4 * a.G) NP = 1;
+    a.nitems = (d->B + 2 * NP - 1) / (2 * NP);
     a.tables = static_cast<const char *>(tables);
     a.u = u; a.chan = chan; a.skipw = skipw; a.out = out;
     const int warps = a.G * d->C;
-    const size_t smem = (size_t)warps * PB * tile_words(d->N) * sizeof(float);
-    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
-    const int by_warps = 32 / warps;
-    if (per_sm > by_warps) per_sm = by_warps;
-    if (per_sm < 1) per_sm = 1;
-    const int want = (a.nitems + a.G - 1) / a.G, cap = props.sm_count * per_sm;
-    const int grid = want < cap ? want : cap;
-#define FWD_CALL launch_fwd
+    const size_t smem = (size_t)warps * NP * tile_words(d->N) * sizeof(float);
     switch (d->N) {
-        case 8: rc = launch_fwd<8>(a, PB, grid, warps * 32, smem, st); break;
-        case 12: rc = launch_fwd<12>(a, PB, grid, warps * 32, smem, st); break;
-        case 16: rc = launch_fwd<16>(a, PB, grid, warps * 32, smem, st); break;
-        case 28: rc = launch_fwd<28>(a, PB, grid, warps * 32, smem, st); break;
-        case 32: rc = launch_fwd<32>(a, PB, grid, warps * 32, smem, st); break;
+        case 8: rc = launch_fwd<8>(a, NP, props.sm_count, warps * 32, smem, st); break;
+        case 12: rc = launch_fwd<12>(a, NP, props.sm_count, warps * 32, smem, st); break;
+        case 16: rc = launch_fwd<16>(a, NP, props.sm_count, warps * 32, smem, st); break;
+        case 28: rc = launch_fwd<28>(a, NP, props.sm_count, warps * 32, smem, st); break;
+        case 32: rc = launch_fwd<32>(a, NP, props.sm_count, warps * 32, smem, st); break;
         default: rc = PDE_ERR_UNSUPPORTED;
     }
     return rc;

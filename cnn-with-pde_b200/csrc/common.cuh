@@ -153,3 +153,59 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float *v) {
 }
 
 }  // namespace pde
+
+// ------------------------------------------------------------------------------------------
+// Packed fp32 pairs (PTX .f32x2, SASS FFMA2 / FMUL2 / FADD2): one instruction advances the same
+// cell of two samples.  The FMA pipe spends two cycles on a packed op, so peak flops are those
+// of scalar FFMA, but the issue slot, the shared-memory instruction and the coefficient operand
+// (a scalar register, broadcast by the instruction) are spent once per pair.
+// Probe: tools/probes/ffma2_probe.cu.
+// ------------------------------------------------------------------------------------------
+namespace pde {
+
+struct f2 {
+    unsigned long long v;
+};
+
+__device__ __forceinline__ f2 f2_make(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 f2_bc(float s) { return f2_make(s, s); }
+__device__ __forceinline__ float f2_lo(f2 a) {
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+    return x;
+}
+__device__ __forceinline__ float f2_hi(f2 a) {
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+    return y;
+}
+__device__ __forceinline__ float f2_hsum(f2 a) { return f2_lo(a) + f2_hi(a); }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) {
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+// scalar coefficient times / fused with a pair
+__device__ __forceinline__ f2 f2_muls(float s, f2 b) { return f2_mul(f2_bc(s), b); }
+__device__ __forceinline__ f2 f2_fmas(float s, f2 b, f2 c) { return f2_fma(f2_bc(s), b, c); }
+
+}  // namespace pde

@@ -285,13 +285,35 @@ def run_b200(args):
 
     small_ms = time_phase(small, 50)
 
+    # ------------------------------------------- whole-model training step (BASELINE metric, part ii)
+    # cifar10.CIFAR10PDENoConv (BASELINE configs[2]: 3x32x32, batch 512 per GPU), three PDE layers +
+    # the reference's dense head, AdamW recipe of cifar10.py:400-527, synthetic device-resident data,
+    # one flat NCCL all-reduce of the gradients per step, step captured in CUDA graphs.
+    train = None
+    if args.train:
+        from cnn_with_pde_b200 import train as T
+        del x, y, yn, xn
+        torch.cuda.empty_cache()
+        try:
+            train = T.run(args.train_model, args.train_batch, steps=max(args.steps, 20), warmup=max(args.warmup, 5),
+                          graph=True, quiet=True)
+        except Exception as ex:   # the headline line survives a failure of the side measurement
+            train = {"error": f"{type(ex).__name__}: {ex}"}
+        x = u.clone().requires_grad_(True)
+        y = yn = xn = None
+
     out = None
     if rank == 0:
         # the CPU leg runs on rank 0 at N = 1 only (the other ranks would idle at the barrier)
         cpu = cpu_baseline(args.layer, budget_s=args.cpu_seconds) if world == 1 else None
+        if train is not None and "error" not in train and world == 1:
+            try:
+                train["cpu_baseline"] = cpu_train_baseline(args.train_model)
+            except Exception as ex:
+                train["cpu_baseline"] = {"error": f"{type(ex).__name__}: {ex}"}
         others = {}
         if args.all_layers and world == 1:
-            del x, y, yn, xn, host_u, dev_bufs
+            x = y = yn = xn = host_u = dev_bufs = None
             torch.cuda.empty_cache()
             for name in LAYERS:
                 if name != args.layer:
@@ -332,6 +354,8 @@ def run_b200(args):
             "clocks": clocks,
             "device": info,
         }
+        if train is not None:
+            out["train"] = train
         if others:
             out["other_layers"] = others
         print(json.dumps(out), flush=True)
@@ -426,6 +450,73 @@ def cpu_baseline(layer, budget_s=12.0, fixed_batch=None, reps=1):
                       f"{dt2:.2f} s", "batch": b2, "seconds": round(dt2, 3)}
 
 
+def cpu_train_baseline(model_name="cifar10", batch=64, steps=2):
+    """Whole-model training step on the host CPU: the classifier of cnn_with_pde_b200.classifiers in
+    stock CPU torch (all cores) with every PDE layer's forward/backward routed to the C oracle
+    (OpenMP, all cores) -- a port: the reference's own Python layer is ~1000x slower than the C
+    restatement and does not exist on this box.  Checker-side only."""
+    import numpy as np
+    import torch
+    import oracle
+    from cnn_with_pde_b200 import train as T
+    from cnn_with_pde_b200.cifar10 import EnhancedDiffusionLayer
+    if model_name != "cifar10":
+        raise NotImplementedError("CPU training baseline is wired for cifar10 only")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    r = T._recipes()[model_name]
+    torch.manual_seed(1234)
+    model = r.build()
+    model.train()
+
+    class OracleAdi(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, u, ab, bb, atc, btc, chan, spec):
+            ctx.spec = spec
+            ctx.save_for_backward(u, ab, bb, atc, btc, chan)
+            out = oracle.adi_forward(spec, u.numpy(), ab.detach().numpy(), bb.detach().numpy(), atc.detach().numpy(),
+                                     btc.detach().numpy(), chan=chan.detach().numpy(), nthreads=cores)
+            return torch.from_numpy(out)
+
+        @staticmethod
+        def backward(ctx, gout):
+            u, ab, bb, atc, btc, chan = ctx.saved_tensors
+            g = oracle.adi_backward(ctx.spec, u.numpy(), gout.contiguous().numpy(), ab.detach().numpy(),
+                                    bb.detach().numpy(), atc.detach().numpy(), btc.detach().numpy(),
+                                    chan=chan.detach().numpy(), need_gin=False, nthreads=cores)
+            f = lambda k: torch.from_numpy(np.asarray(g[k], np.float32))
+            return (None, f("alpha_base"), f("beta_base"), f("alpha_time_coeff"), f("beta_time_coeff"), f("chan"), None)
+
+    for m in model.modules():
+        if isinstance(m, EnhancedDiffusionLayer):
+            spec = oracle.spec_cifar10(m.size, m.channels, m.dt, m.dx, m.dy, m.num_steps)
+            m.forward = (lambda u, m=m, spec=spec: OracleAdi.apply(u, m.alpha_base, m.beta_base, m.alpha_time_coeff,
+                                                                   m.beta_time_coeff, m.channel_mixing, spec))
+    opt = T.make_optimizer(model, r, capturable=False)
+    crit = torch.nn.CrossEntropyLoss(label_smoothing=r.label_smoothing)
+    gen = torch.Generator().manual_seed(7)
+    xb = torch.randn(batch, *r.shape, generator=gen)
+    yb = torch.randint(0, r.classes, (batch,), generator=gen)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(xb), yb)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        return float(loss.detach())
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(batch / dt, 1), "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{model_name} classifier in CPU torch + oracle/pde_oracle.c PDE layers (fp32, OpenMP x{cores}), "
+                      f"batch {batch}, {steps} optimiser steps, {dt * 1e3:.1f} ms/step",
+            "reference_python_img_per_s_build_container": 48.4}
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the host cores, same metric."""
     rank = int(os.environ.get("RANK", "0"))
@@ -473,6 +564,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: roofline-size batch of the layer)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--all-layers", type=int, default=1, help="also time the other layers (N=1 only)")
+    ap.add_argument("--train", type=int, default=1, help="also time a whole-model training step (img/s)")
+    ap.add_argument("--train-model", default="cifar10")
+    ap.add_argument("--train-batch", type=int, default=512, help="per-GPU batch of the training step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -46,3 +46,6 @@ class DiffusionLayer(nn.Module):
 
     def smooth_coefficients(self, coeffs, dim=1, kernel_size=3):
         return _smooth(coeffs, dim, kernel_size)
+
+
+from .classifiers import SvhnPDEClassifier as PDEClassifier  # noqa: E402,F401  (SVHN.py:234)

@@ -47,3 +47,6 @@ class EnhancedDiffusionLayer(nn.Module):
         check_input(u, self.channels, self.size, self.size, type(self).__name__)
         return adi_layer(u, self.alpha_base, self.beta_base, self.alpha_time_coeff, self.beta_time_coeff,
                          self.channel_mixing, None, self._config())
+
+
+from .classifiers import CIFAR10PDENoConv, EnhancedFC, MultiScaleExtractor, SpatialAttention  # noqa: E402,F401  (cifar10.py:215-361)

@@ -1,0 +1,180 @@
+"""The classifiers the reference scripts wrap around their PDE layer, rebuilt on the B200 layers.
+
+Only the PDE block is native code; everything after it is stock torch (dense layers, batch
+norm, pooling: cuBLAS / ATen), exactly as in the reference.  The classes keep the reference's
+attribute names so that a ``state_dict`` saved by a reference model loads here and vice versa
+(tests/test_classifiers.py):
+
+    mnist_test.PDEClassifier              mnist_test.py:223-237
+    fashion_mnist.FashionPDEClassifier    fashion_mnist.py:200-224
+    SVHN.PDEClassifier                    SVHN.py:234-270
+    emotion_recognition.DiffusionClassifier   emotion_recognition.py:170-195
+    cifar10.SpatialAttention / MultiScaleExtractor / EnhancedFC / CIFAR10PDENoConv   cifar10.py:215-361
+
+They are used by the data-parallel launcher (train.py); each is re-exported from the module
+named after its script.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _dense_stack(owner: nn.Module, widths, batch_norm: bool):
+    """Register fc1..fcK (and bn1..bn{K-1}) on `owner` for the layer widths w0 -> w1 -> ... -> wK."""
+    for k in range(1, len(widths)):
+        setattr(owner, f"fc{k}", nn.Linear(widths[k - 1], widths[k]))
+    if batch_norm:   # registered after the linears, as the reference does (parameter order matters to optimizers)
+        for k in range(1, len(widths) - 1):
+            setattr(owner, f"bn{k}", nn.BatchNorm1d(widths[k]))
+
+
+class MnistPDEClassifier(nn.Module):
+    """diff -> flatten -> dropout -> fc1 -> relu -> dropout -> fc2 (mnist_test.py:223-237)."""
+
+    def __init__(self, dropout_rate=0.1, dx=1.0, dy=1.0):
+        super().__init__()
+        from .mnist_test import DiffusionLayer
+        self.diff = DiffusionLayer(dx=dx, dy=dy)
+        self.dropout = nn.Dropout(dropout_rate)
+        _dense_stack(self, (28 * 28, 256, 10), batch_norm=False)
+
+    def forward(self, x):
+        h = self.diff(x).flatten(1)
+        h = self.dropout(F.relu(self.fc1(self.dropout(h))))
+        return self.fc2(h)
+
+
+class FashionPDEClassifier(nn.Module):
+    """diff -> 784-512-256-10 with batch norm (fashion_mnist.py:200-224)."""
+
+    def __init__(self, dropout_rate=0.15):
+        super().__init__()
+        from .fashion_mnist import DiffusionLayer
+        self.diff = DiffusionLayer()
+        self.dropout = nn.Dropout(dropout_rate)
+        _dense_stack(self, (28 * 28, 512, 256, 10), batch_norm=True)
+
+    def forward(self, x):
+        h = self.diff(x).flatten(1)
+        h = self.dropout(F.relu(self.bn1(self.fc1(h))))
+        h = self.dropout(F.relu(self.bn2(self.fc2(h))))
+        return self.fc3(h)
+
+
+class SvhnPDEClassifier(nn.Module):
+    """diff(32, 3) -> 3072-2048-1024-512-256-10 with batch norm (SVHN.py:234-270).  The reference
+    registers fc_k and bn_k interleaved; so does this class."""
+
+    def __init__(self, dropout_rate=0.5):
+        super().__init__()
+        from .SVHN import DiffusionLayer
+        self.diff = DiffusionLayer(size=32, channels=3)
+        self.dropout = nn.Dropout(dropout_rate)
+        widths = (32 * 32 * 3, 2048, 1024, 512, 256, 10)
+        for k in range(1, len(widths)):
+            setattr(self, f"fc{k}", nn.Linear(widths[k - 1], widths[k]))
+            if k < len(widths) - 1:
+                setattr(self, f"bn{k}", nn.BatchNorm1d(widths[k]))
+
+    def forward(self, x):
+        h = self.diff(x).flatten(1)
+        for k in range(1, 5):
+            h = self.dropout(F.relu(getattr(self, f"bn{k}")(getattr(self, f"fc{k}")(h))))
+        return self.fc5(h)
+
+
+class DiffusionClassifier(nn.Module):
+    """pde -> Sequential(flatten, [linear, bn, relu, dropout] x 3, linear) (emotion_recognition.py:170-195)."""
+
+    def __init__(self, img_size=48, num_classes=7, dropout_rate=0.3):
+        super().__init__()
+        from .emotion_recognition import PDELayer
+        self.pde = PDELayer(Nx=img_size, Ny=img_size)
+        mods = [nn.Flatten()]
+        widths = (img_size * img_size, 512, 256, 128)
+        for k in range(1, len(widths)):
+            mods += [nn.Linear(widths[k - 1], widths[k]), nn.BatchNorm1d(widths[k]), nn.ReLU(), nn.Dropout(dropout_rate)]
+        mods.append(nn.Linear(widths[-1], num_classes))
+        self.classifier = nn.Sequential(*mods)
+
+    def forward(self, x):
+        return self.classifier(self.pde(x))
+
+
+class SpatialAttention(nn.Module):
+    """Channel gate from the spatial mean of (x + learned position embedding) (cifar10.py:215-244)."""
+
+    def __init__(self, channels, size):
+        super().__init__()
+        self.channels = channels
+        self.size = size
+        self.pos_embed = nn.Parameter(torch.randn(1, channels, size, size) * 0.1)
+        self.attention_fc = nn.Sequential(nn.Linear(channels, channels * 2), nn.ReLU(),
+                                          nn.Linear(channels * 2, channels), nn.Sigmoid())
+
+    def forward(self, x):
+        gate = self.attention_fc((x + self.pos_embed).mean(dim=(2, 3)))
+        return x * gate[:, :, None, None]
+
+
+class MultiScaleExtractor(nn.Module):
+    """Three PDE layers on the same input, each gated, softmax-combined (cifar10.py:248-282)."""
+
+    def __init__(self, input_size=32, channels=3):
+        super().__init__()
+        from .cifar10 import EnhancedDiffusionLayer
+        self.pde1 = EnhancedDiffusionLayer(input_size, channels, dt=0.001, num_steps=5, dx=1.0, dy=1.0)
+        self.pde2 = EnhancedDiffusionLayer(input_size, channels, dt=0.002, num_steps=8, dx=2.0, dy=2.0)
+        self.pde3 = EnhancedDiffusionLayer(input_size, channels, dt=0.005, num_steps=4, dx=1.5, dy=1.5)
+        self.attention1 = SpatialAttention(channels, input_size)
+        self.attention2 = SpatialAttention(channels, input_size)
+        self.attention3 = SpatialAttention(channels, input_size)
+        self.combine_weights = nn.Parameter(torch.ones(3) / 3)
+
+    def forward(self, x):
+        feats = [att(pde(x)) for pde, att in ((self.pde1, self.attention1), (self.pde2, self.attention2),
+                                              (self.pde3, self.attention3))]
+        w = F.softmax(self.combine_weights, dim=0)
+        combined = w[0] * feats[0] + w[1] * feats[1] + w[2] * feats[2]
+        return (combined, *feats)
+
+
+class EnhancedFC(nn.Module):
+    """[linear, bn, relu, dropout] per hidden width, then a linear; Kaiming-normal weights (cifar10.py:286-314)."""
+
+    def __init__(self, input_size, hidden_sizes, num_classes, dropout_rate=0.3):
+        super().__init__()
+        mods, prev = [], input_size
+        for width in hidden_sizes:
+            mods += [nn.Linear(prev, width), nn.BatchNorm1d(width), nn.ReLU(inplace=True), nn.Dropout(dropout_rate)]
+            prev = width
+        mods.append(nn.Linear(prev, num_classes))
+        self.network = nn.Sequential(*mods)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.kaiming_normal_(m.weight)
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        return self.network(x)
+
+
+class CIFAR10PDENoConv(nn.Module):
+    """Multi-scale PDE features -> BatchNorm2d -> 4x4 avg + max pooling -> EnhancedFC (cifar10.py:318-361)."""
+
+    def __init__(self, dropout_rate=0.3):
+        super().__init__()
+        self.feature_extractor = MultiScaleExtractor(input_size=32, channels=3)
+        self.adaptive_pool = nn.AdaptiveAvgPool2d((4, 4))
+        self.max_pool = nn.AdaptiveMaxPool2d((4, 4))
+        self.classifier = EnhancedFC(input_size=96, hidden_sizes=[512, 256, 128, 64], num_classes=10,
+                                     dropout_rate=dropout_rate)
+        self.feature_bn = nn.BatchNorm2d(3)
+
+    def forward(self, x):
+        combined = self.feature_extractor(x)[0]
+        f = self.feature_bn(combined)
+        pooled = torch.cat([self.adaptive_pool(f), self.max_pool(f)], dim=1)
+        return self.classifier(pooled.flatten(1))

@@ -42,3 +42,6 @@ class PDELayer(nn.Module):
         w6 = torch.stack([self.alpha_w1, self.alpha_w2, self.alpha_w3, self.beta_w1, self.beta_w2, self.beta_w3])
         cfg = EmoConfig(N=self.Nx, Nt=self.Nt, dt=self.dt, dx=self.dx, dy=self.dy)
         return emotion_layer(u0, w6, self.x, self.y, cfg)
+
+
+from .classifiers import DiffusionClassifier  # noqa: E402,F401  (emotion_recognition.py:170)

@@ -38,3 +38,6 @@ class DiffusionLayer(nn.Module):
 
     def smooth_coefficients(self, coeffs, dim=1, kernel_size=3):
         return _smooth(coeffs, dim, kernel_size)
+
+
+from .classifiers import FashionPDEClassifier  # noqa: E402,F401  (fashion_mnist.py:200)

@@ -48,3 +48,6 @@ class DiffusionLayer(nn.Module):
             cfl_y = beta_max * self.dt / (self.dy ** 2)
             return {"cfl_x": cfl_x.item(), "cfl_y": cfl_y.item(), "dx": self.dx, "dy": self.dy, "dt": self.dt,
                     "stable_x": cfl_x.item() < 0.5, "stable_y": cfl_y.item() < 0.5}
+
+
+from .classifiers import MnistPDEClassifier as PDEClassifier  # noqa: E402,F401  (mnist_test.py:223)

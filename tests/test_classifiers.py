@@ -1,0 +1,106 @@
+"""The classifiers around the PDE layers (cnn_with_pde_b200.classifiers) against the reference's.
+
+CPU: same state_dict keys / shapes / registration order as the reference classes, state_dicts
+load across in both directions, the launcher's optimiser groups follow cifar10.py:423-434.
+GPU: logits, loss and every PDE-parameter gradient of a whole model against fixtures generated
+from the unmodified reference (tests/golden/make_golden_models.py), tolerance 1e-5 (north_star).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from . import refload
+from .golden.make_golden_models import MODELS, is_pde_param
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+OURS = {
+    "mnist": ("mnist_test", "PDEClassifier"),
+    "fashion": ("fashion_mnist", "FashionPDEClassifier"),
+    "cifar10": ("cifar10", "CIFAR10PDENoConv"),
+    "svhn": ("SVHN", "PDEClassifier"),
+    "emotion": ("emotion_recognition", "DiffusionClassifier"),
+}
+REF = dict(MODELS, svhn=("SVHN", "PDEClassifier", (3, 32, 32), 10, 2),
+           emotion=("emotion_recognition", "DiffusionClassifier", (1, 48, 48), 7, 3))
+
+
+def ours(name):
+    import importlib
+    import cnn_with_pde_b200  # noqa: F401
+    mod, cls = OURS[name]
+    return getattr(importlib.import_module("cnn_with_pde_b200." + mod), cls)()
+
+
+@pytest.mark.skipif(not refload.available(), reason="needs /root/reference (build container)")
+@pytest.mark.parametrize("name", sorted(OURS))
+def test_state_dict_layout_matches_reference(name):
+    script, cls = REF[name][:2]
+    ref = refload.quiet(getattr(refload.load(script), cls))
+    mine = ours(name)
+    rsd, msd = ref.state_dict(), mine.state_dict()
+    assert list(rsd.keys()) == list(msd.keys())
+    assert [tuple(v.shape) for v in rsd.values()] == [tuple(v.shape) for v in msd.values()]
+    assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
+    mine.load_state_dict(rsd)
+    ref.load_state_dict(mine.state_dict())
+    for k in rsd:
+        assert torch.equal(ref.state_dict()[k], mine.state_dict()[k]), k
+
+
+def test_cifar10_optimizer_groups_follow_the_script():
+    from cnn_with_pde_b200 import train
+    r = train._recipes()["cifar10"]
+    model = r.build()
+    opt = train.make_optimizer(model, r, capturable=False)
+    coef, rest = opt.param_groups
+    n_coef = sum(p.numel() for n, p in model.named_parameters() if "alpha" in n or "beta" in n)
+    assert sum(p.numel() for p in coef["params"]) == n_coef == 3 * 4 * 3 * 32 * 32
+    assert coef["lr"] == 1e-3 and coef["weight_decay"] == 1e-6
+    assert rest["lr"] == 5e-4 and rest["weight_decay"] == 1e-4
+    assert sum(p.numel() for g in opt.param_groups for p in g["params"]) == sum(p.numel() for p in model.parameters())
+
+
+def test_launcher_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from cnn_with_pde_b200 import train
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        train.run("mnist", 4, 1, 0, quiet=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_whole_model_matches_reference_fixture(name):
+    z = np.load(os.path.join(GOLDEN_DIR, f"model_{name}.npz"))
+    model = ours(name)
+    model.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd_")})
+    model = model.cuda().eval()
+    x, y = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["y"]).cuda()
+    logits = model(x)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    tol = 1e-5
+
+    def rel(a, b):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+    assert rel(logits.detach().cpu().numpy(), z["logits"]) <= tol
+    assert abs(loss.item() - float(z["loss"])) <= tol * abs(float(z["loss"]))
+    checked = 0
+    for n, p in model.named_parameters():
+        if is_pde_param(n) and ("g_" + n) in z.files:
+            assert p.grad is not None, n
+            assert rel(p.grad.cpu().numpy(), z["g_" + n]) <= tol, n
+            checked += 1
+    assert checked >= 4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_launcher_trains_one_gpu(graph):
+    from cnn_with_pde_b200 import train
+    out = train.run("fashion", 32, 4, 2, graph=graph, quiet=True)
+    assert out["img_per_s"] > 0 and np.isfinite(out["loss"]) and out["cuda_graph"] == graph

@@ -1220,7 +1220,9 @@ extern "C" int pde_adi_forward(const pde_adi_desc *d, const void *tables, const 
     a.S = d->steps * a.sps;
     a.G = groups_per_block(d->C);
     // a warp advances NP sample pairs; small batches spread over more warps instead
-    int NP = env_int("PDE_B200_FWD_NP", 2) == 1 ? 1 : 2;
+    // measured: two pairs per warp win for the single-channel 28 x 28 layers (coefficient rows shared
+    // by four samples), one pair for the three-channel 32 x 32 ones (254 registers cost residency)
+    int NP = env_int("PDE_B200_FWD_NP", d->C == 1 ? 2 : 1) == 1 ? 1 : 2;
     if (NP == 2 && (d->B + 3) / 4 < props.sm_count * 4 * a.G) NP = 1;
     a.nitems = (d->B + 2 * NP - 1) / (2 * NP);
     a.tables = static_cast<const char *>(tables);

@@ -14,6 +14,8 @@
 // Backward kernels recompute the forward states on-chip (nothing but the layer input is
 // saved), run the hand-derived adjoint, and reduce the coefficient gradients per thread ->
 // per block -> tiny finishing kernel (double accumulation, fixed order: deterministic).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pde {
@@ -563,8 +565,15 @@ static int emo_bwd_grid(const pde_emo_desc *d, const DeviceProps &props, size_t 
     return (int)(grid < 1 ? 1 : grid);
 }
 
+static int env_flag(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 }  // namespace expl
 }  // namespace pde
+
+#include "emotion_tiled.cuh"
 
 using namespace pde;
 using namespace pde::expl;
@@ -641,7 +650,12 @@ extern "C" size_t pde_emotion_backward_workspace_bytes(const pde_emo_desc *d) {
     if (emo_validate(d) != PDE_OK) return 0;
     DeviceProps props;
     if (query_props(&props) != PDE_OK) return 0;
-    return (size_t)props.sm_count * 4 * 2 * kEmoMaxN * sizeof(float) + 256;
+    const size_t generic = (size_t)props.sm_count * 4 * 2 * kEmoMaxN * sizeof(float) + 256;
+    if (emo_tiled_ok(d) && env_flag("PDE_B200_EMO_TILED", 1)) {
+        const size_t tiled = emo_tiled_workspace_bytes(d, props.sm_count);
+        return tiled > generic ? tiled : generic;
+    }
+    return generic;
 }
 
 extern "C" int pde_emotion_forward(const pde_emo_desc *d, const float *u0, const float *w6, const float *xs,
@@ -655,6 +669,8 @@ extern "C" int pde_emotion_forward(const pde_emo_desc *d, const float *u0, const
     if (rc) return rc;
     EmoArgs a{};
     a.d = *d; a.u0 = u0; a.w6 = w6; a.xs = xs; a.ys = ys; a.out = out;
+    if (emo_tiled_ok(d) && env_flag("PDE_B200_EMO_TILED", 1))
+        return emo_tiled_forward(a, props.sm_count, static_cast<cudaStream_t>(stream));
     const size_t smem = emo_fwd_smem(d);
     const int threads = emo_threads(d->N);
     long grid = (long)props.sm_count * 6;
@@ -678,6 +694,13 @@ extern "C" int pde_emotion_backward(const pde_emo_desc *d, const float *u0, cons
     DeviceProps props;
     rc = query_props(&props);
     if (rc) return rc;
+    if (emo_tiled_ok(d) && env_flag("PDE_B200_EMO_TILED", 1)) {
+        if (!workspace || workspace_bytes < emo_tiled_workspace_bytes(d, props.sm_count)) return PDE_ERR_WORKSPACE;
+        EmoArgs t{};
+        t.d = *d; t.u0 = u0; t.gout = gout; t.w6 = w6; t.xs = xs; t.ys = ys; t.gin = gin;
+        t.need_gin = gin != nullptr;
+        return emo_tiled_backward(t, props.sm_count, workspace, xs, g_w6, st);
+    }
     const size_t smem = emo_bwd_smem(d);
     if (smem > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
     const int grid = emo_bwd_grid(d, props, smem);

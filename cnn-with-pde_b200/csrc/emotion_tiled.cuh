@@ -17,7 +17,7 @@
 // u^k back row by row a few rows ahead of its use, and accumulates
 //   dA_i += lam * d2_row u^k, weighted on the fly by {1, sin 2 pi y_i, sin 4 pi y_i}  (3 registers),
 //   dB_j += lam * d2_col u^k per owned column                                        (CW registers),
-// in fp32 per plane and in double across planes.  What flows into the frozen ghost ring is summed
+// in fp32 within a step and in double across steps and planes.  What flows into the frozen ghost ring is summed
 // over the steps (top / bottom rows in registers, left / right columns in shared memory by the edge
 // lanes) and folded back through the reflection at the end.
 #pragma once
@@ -215,13 +215,18 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_bwd_tiled(const EmoArgs a
         }
 #pragma unroll
         for (int r = 0; r < RH; ++r) eslot[r * 32] = 0.0f;
-        float eedge[CW], fA0 = 0.f, fA1 = 0.f, fA2 = 0.f, fB[CW];
+        float eedge[CW];
 #pragma unroll
-        for (int c = 0; c < CW; ++c) eedge[c] = fB[c] = 0.f;
+        for (int c = 0; c < CW; ++c) eedge[c] = 0.f;
         __syncwarp();
         constexpr int AHEAD = 4;    // history rows requested ahead of their use
         for (int k = Nt - 1; k >= 0; --k) {
             const float *hk = hist + (size_t)k * RH * HROW;
+            // fp32 partial sums live for one step only (72 terms per lane); across steps and planes
+            // the sums are carried in double: the six gradients are sums with heavy cancellation
+            float fA0 = 0.f, fA1 = 0.f, fA2 = 0.f, fB[CW];
+#pragma unroll
+            for (int c = 0; c < CW; ++c) fB[c] = 0.f;
             float uh[RH][CW];
 #pragma unroll
             for (int r = 0; r < AHEAD; ++r)
@@ -307,10 +312,10 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_bwd_tiled(const EmoArgs a
                     lam[r][c] = nv[c];
                 }
             }
-        }
-        dA0 += (double)fA0; dA1 += (double)fA1; dA2 += (double)fA2;
+            dA0 += (double)fA0; dA1 += (double)fA1; dA2 += (double)fA2;
 #pragma unroll
-        for (int c = 0; c < CW; ++c) dBd[c] += (double)fB[c];
+            for (int c = 0; c < CW; ++c) dBd[c] += (double)fB[c];
+        }
         __syncwarp();
         if (a.need_gin) {
             float *gi = a.gin + off;

@@ -72,6 +72,24 @@ def test_cuda_edge_cases():
     np.testing.assert_array_equal(got["gin"], g)
 
 
+@pytest.mark.parametrize("ctor", [dict(Nx=16, Ny=16), dict(Nx=32, Ny=32, T=0.004), dict(Nx=48, Ny=48, T=0.003),
+                                  dict(Nx=24, Ny=24), dict(Nx=64, Ny=64, T=0.002)],
+                         ids=lambda d: f"N{d['Nx']}")
+def test_cuda_emotion_plane_sizes(ctor):
+    """Plane edges 16 / 32 / 48 take the register-tiled kernels (a warp per plane), the others the
+    generic shared-memory kernels; odd batch, stable coefficients and the unstable default ones."""
+    for perturb, B in ((False, 5), (True, 7)):
+        c = K.case(f"emo_{ctor['Nx']}_{int(perturb)}", "emotion", B=B, perturb=perturb, **ctor)
+        params, io = K.make_params(c), K.make_io(c)
+        got = runners.run_cuda(c, params=params, io=io)
+        want = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+        _assert_close(got, want, TOL, c.name)
+        got = runners.run_cuda(c, params=params, io=io, need_gin=False)
+        assert got["gin"] is None
+        _assert_close({k: v for k, v in got.items() if k != "gin"},
+                      {k: v for k, v in want.items() if k != "gin"}, TOL, c.name + " (no grad_input)")
+
+
 def test_cuda_exact_mode_for_large_coefficients():
     """dt large enough that rebuilding sweep inputs would amplify rounding noise: the kernel must
     switch to per-sweep checkpoints on its own (DESIGN.md 'reverse reconstruction')."""

@@ -56,3 +56,39 @@ def test_sharded_backward_plus_allreduce_equals_full_batch(tmp_path):
     full = runners.run_oracle(c, dtype=np.float64)
     for n in K.grad_names(c):
         np.testing.assert_allclose(got[n], full["g_" + n], rtol=1e-11, atol=1e-13, err_msg=n)
+
+
+def _flat_worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cnn_with_pde_b200.train import FlatGradSync
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+        sync = FlatGradSync(net, world)
+        x = torch.arange(24, dtype=torch.float32).reshape(4, 6) / 10.0
+        for _ in range(2):                      # second pass: the views must survive zero() + backward
+            sync.zero()
+            net(x[2 * rank:2 * rank + 2]).square().mean().backward()
+            assert all(p.grad.untyped_storage().data_ptr() == sync.flat.untyped_storage().data_ptr()
+                       for p in net.parameters())
+            sync.all_reduce()
+        if rank == 0:
+            torch.save([p.grad.clone() for p in net.parameters()], os.path.join(tmpdir, "flat.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_flat_gradient_sync_matches_full_batch_mean(tmp_path):
+    """The launcher's gradient sync (every .grad a view of one flat buffer, one all-reduce, mean
+    over ranks as DDP) on 2 CPU ranks equals the single-process gradient of the mean loss."""
+    world = 2
+    mp.spawn(_flat_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = torch.load(tmp_path / "flat.pt")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    x = torch.arange(24, dtype=torch.float32).reshape(4, 6) / 10.0
+    (0.5 * (net(x[:2]).square().mean() + net(x[2:]).square().mean())).backward()
+    for g, p in zip(got, net.parameters()):
+        torch.testing.assert_close(g, p.grad, rtol=1e-6, atol=1e-7)

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_fwd_tiled(const EmoArgs a
         const size_t off = (size_t)plane * N * N;
         float u[RH][CW], gedge[CW];
         tile_load<N>(a.u0 + off, half, sub, r0, j0, u, gedge, gl, gr);
+#pragma unroll 1
         for (int k = 0; k < a.d.Nt; ++k) tile_step<N>(u, gedge, b, sh.a + 1 + r0, gl + r0, gr + r0, half, sub);
         float *o = a.out + off;
 #pragma unroll
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_bwd_tiled(const EmoArgs a
         {   // ------------------------------ phase 1: u^0 .. u^{Nt-1} into the history
             float u[RH][CW];
             tile_load<N>(a.u0 + off, half, sub, r0, j0, u, gedge, gl, gr);
+#pragma unroll 1
             for (int k = 0; k < Nt; ++k) {
                 float *hk = hist + (size_t)k * RH * HROW;
 #pragma unroll
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_bwd_tiled(const EmoArgs a
         for (int c = 0; c < CW; ++c) eedge[c] = 0.f;
         __syncwarp();
         constexpr int AHEAD = 4;    // history rows requested ahead of their use
+#pragma unroll 1   // the body is 24 unrolled rows; more copies only thrash the instruction cache
         for (int k = Nt - 1; k >= 0; --k) {
             const float *hk = hist + (size_t)k * RH * HROW;
             // fp32 partial sums live for one step only (72 terms per lane); across steps and planes

@@ -20,6 +20,8 @@ EXPORTS = (
     "pde_b200_abi_version", "pde_b200_error_string", "pde_b200_device_info",
     "pde_adi_tables_bytes", "pde_adi_backward_workspace_bytes", "pde_adi_prepare",
     "pde_adi_forward", "pde_adi_backward",
+    "pde_adi_checkpoint_bytes", "pde_adi_backward_saved_workspace_bytes", "pde_adi_forward_train",
+    "pde_adi_backward_saved",
     "pde_emotion_backward_workspace_bytes", "pde_emotion_forward", "pde_emotion_backward",
     "pde_tiny_backward_workspace_bytes", "pde_tiny_forward", "pde_tiny_backward",
 )
@@ -76,6 +78,15 @@ def lib():
     L.pde_adi_forward.argtypes = [POINTER(AdiDesc), vp, fp, fp, fp, fp, vp]
     L.pde_adi_backward.restype = c_int
     L.pde_adi_backward.argtypes = [POINTER(AdiDesc), vp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, vp, c_size_t, vp]
+    L.pde_adi_checkpoint_bytes.restype = c_size_t
+    L.pde_adi_checkpoint_bytes.argtypes = [POINTER(AdiDesc)]
+    L.pde_adi_backward_saved_workspace_bytes.restype = c_size_t
+    L.pde_adi_backward_saved_workspace_bytes.argtypes = [POINTER(AdiDesc)]
+    L.pde_adi_forward_train.restype = c_int
+    L.pde_adi_forward_train.argtypes = [POINTER(AdiDesc), vp, fp, fp, fp, fp, vp, vp]
+    L.pde_adi_backward_saved.restype = c_int
+    L.pde_adi_backward_saved.argtypes = [POINTER(AdiDesc), vp, fp, fp, fp, fp, vp, fp, fp, fp, fp, fp, fp, fp, vp,
+                                         c_size_t, vp]
     L.pde_emotion_backward_workspace_bytes.restype = c_size_t
     L.pde_emotion_backward_workspace_bytes.argtypes = [POINTER(EmoDesc)]
     L.pde_emotion_forward.restype = c_int
@@ -88,7 +99,7 @@ def lib():
     L.pde_tiny_forward.argtypes = [POINTER(TinyDesc), fp, fp, fp, fp, vp]
     L.pde_tiny_backward.restype = c_int
     L.pde_tiny_backward.argtypes = [POINTER(TinyDesc), fp, fp, fp, fp, fp, fp, fp, vp, c_size_t, vp]
-    if L.pde_b200_abi_version() != 1:
+    if L.pde_b200_abi_version() != 2:
         raise PdeB200Error("libpde_b200.so ABI version mismatch; rebuild it")
     _lib = L
     return L

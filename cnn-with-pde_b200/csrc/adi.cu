@@ -21,33 +21,10 @@
 //                       would amplify rounding noise (device-computed bound), the kernel
 //                       switches to exact per-sweep checkpoints instead.
 //   * adi_finish_kernel sums the per-warp gradient partials in double (deterministic).
-#include <cstdio>
-#include <cstdlib>
-
-#include "common.cuh"
+#include "adi_common.cuh"
 
 namespace pde {
 namespace adi {
-
-constexpr int kHeaderBytes = 4096;
-constexpr float kAmpLimit = 256.0f;  // see DESIGN.md "reverse reconstruction"
-
-struct Header {
-    int mode_exact;
-    float amp_bound;
-    int pad[2];
-    float scale[PDE_MAX_SWEEPS];
-    float t[PDE_MAX_SWEEPS];
-    unsigned rmax_bits[PDE_MAX_SWEEPS];
-    int clamped[PDE_MAX_SWEEPS];   // 1 if any cell of sweep s sits outside the clamp interval
-    // sweeps with the same axis, time, time step and spacing have the same tables (Strang: the
-    // closing half sweep of a step and the opening one of the next): slot[s] numbers the distinct
-    // ones in order of first appearance, rep[u] is the first sweep of slot u
-    int nslots;
-    short slot[PDE_MAX_SWEEPS];
-    short rep[PDE_MAX_SWEEPS];
-};
-static_assert(sizeof(Header) <= kHeaderBytes, "header too large");
 
 template <int N>
 struct Geo {
@@ -59,32 +36,6 @@ struct Geo {
     static constexpr int WORDS = 2 * N * ST;   // floats per tile
     static constexpr int Q = N / 4;
 };
-
-__host__ __device__ inline int sweeps_per_step(const pde_adi_desc &d) { return d.lie ? 2 : 3; }
-// axis 0: lines along W (alpha); axis 1: lines along H (beta)
-__host__ __device__ inline int sweep_axis(int k_in_step) { return k_in_step == 1 ? 1 : 0; }
-
-__host__ __device__ inline size_t table_elems(const pde_adi_desc &d) {
-    return (size_t)d.steps * sweeps_per_step(d) * d.C * d.N * d.N;
-}
-
-struct Tables {
-    const Header *hdr;
-    const float *r, *inv, *e, *msk;
-};
-
-__host__ __device__ inline Tables split_tables(const void *tables, const pde_adi_desc &d) {
-    Tables t;
-    const char *b = static_cast<const char *>(tables);
-    t.hdr = reinterpret_cast<const Header *>(b);
-    const float *f = reinterpret_cast<const float *>(b + kHeaderBytes);
-    const size_t T = table_elems(d);
-    t.r = f;
-    t.inv = f + T;
-    t.e = f + 2 * T;
-    t.msk = f + 3 * T;
-    return t;
-}
 
 // ------------------------------------------------------------------------------------------
 // prepare: coefficient map -> clamp -> smoothing -> r -> pivots.  One thread per (sweep,
@@ -297,11 +248,6 @@ __device__ __forceinline__ void mix_rows(const float *group_tiles, int C, const 
     }
 }
 
-// Software prefetch (no register destination): pull the next sweep's table rows into L1 / the next
-// item's planes into L2 while the current sweep computes.
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 template <int N>
 __device__ __forceinline__ void prefetch_tables(const float4 *ta, const float4 *tb, const float4 *tc) {
 #pragma unroll
@@ -350,16 +296,6 @@ __device__ __forceinline__ void thomas_solve(f2 (&x)[NP][N], const float4 *__res
 #pragma unroll
         for (int p = 0; p < NP; ++p) x[p][i] = f2_fmas(e[i], x[p][i + 1], x[p][i]);
 }
-
-struct Args {
-    pde_adi_desc d;
-    int S, sps, G, nitems, need_gin;
-    int tile_sets, tmem_cols;
-    const char *tables;
-    const float *u, *gout, *chan, *skipw;
-    float *out, *gin;
-    float *scratch, *part_maps, *part_chan, *part_skip;
-};
 
 __device__ __forceinline__ void group_sync(int C, int group) {
     if (C == 1)
@@ -980,7 +916,7 @@ __global__ void __launch_bounds__(192, 1) bwd_kernel(const Args a) {
 // unrolled) and the 8 slice sums are combined in a fixed order through shared memory.
 constexpr int kFinishCells = 32, kFinishSlices = 8;
 __global__ void __launch_bounds__(kFinishCells *kFinishSlices)
-    finish_kernel(pde_adi_desc d, int nwarps_total, const float *__restrict__ part_maps,
+    finish_kernel(pde_adi_desc d, int nwarps_total, int nsets_small, const float *__restrict__ part_maps,
                   const float *__restrict__ part_chan, const float *__restrict__ part_skip,
                   const float *__restrict__ skipw, float *g_ab, float *g_atc, float *g_bb, float *g_btc,
                   float *g_chan, float *g_skip) {
@@ -1023,12 +959,12 @@ __global__ void __launch_bounds__(kFinishCells *kFinishSlices)
         if (g_chan && threadIdx.x < C * C) {
             const int cc = threadIdx.x / C, dd = threadIdx.x % C;
             double a = 0.0;
-            for (int w = cc; w < nwarps_total; w += C) a += (double)part_chan[(size_t)w * PDE_MAX_CHANNELS + dd];
+            for (int w = cc; w < nsets_small; w += C) a += (double)part_chan[(size_t)w * PDE_MAX_CHANNELS + dd];
             g_chan[cc * C + dd] = (float)a;
         }
         if (g_skip && threadIdx.x == 32) {
             double a = 0.0;
-            for (int w = 0; w < nwarps_total; ++w) a += (double)part_skip[w];
+            for (int w = 0; w < nsets_small; ++w) a += (double)part_skip[w];
             const double sg = 1.0 / (1.0 + exp(-(double)skipw[0]));
             g_skip[0] = (float)(a * sg * (1.0 - sg));
         }
@@ -1052,12 +988,6 @@ static int validate(const pde_adi_desc *d) {
 }
 
 static int groups_per_block(int C) { return C >= 3 ? 1 : (C == 2 ? 2 : 4); }
-
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    if (!v || !*v) return dflt;
-    return atoi(v);
-}
 
 static int tile_words(int N) { return 2 * N * (N + 2); }   // one tile = one sample pair
 
@@ -1163,6 +1093,14 @@ static int launch_bwd(const Args &a, const BwdPlan &p, cudaStream_t st) {
         default: rc = PDE_ERR_UNSUPPORTED;           \
     }
 
+void launch_finish(const pde_adi_desc &d, int nsets_maps, int nsets_small, const float *part_maps,
+                   const float *part_chan, const float *part_skip, const float *skipw, float *g_ab, float *g_atc,
+                   float *g_bb, float *g_btc, float *g_chan, float *g_skip, cudaStream_t st) {
+    const size_t total = 4 * (size_t)d.C * d.N * d.N;
+    finish_kernel<<<(unsigned)((total + kFinishCells - 1) / kFinishCells), kFinishCells * kFinishSlices, 0, st>>>(
+        d, nsets_maps, nsets_small, part_maps, part_chan, part_skip, skipw, g_ab, g_atc, g_bb, g_btc, g_chan, g_skip);
+}
+
 }  // namespace adi
 }  // namespace pde
 
@@ -1171,14 +1109,32 @@ using namespace pde::adi;
 
 extern "C" size_t pde_adi_tables_bytes(const pde_adi_desc *d) {
     if (validate(d) != PDE_OK) return 0;
-    return (size_t)kHeaderBytes + 4 * table_elems(*d) * sizeof(float);
+    // header | tables of adi.cu | tables of adi_split.cu (always reserved: the size does not depend
+    // on which implementation a call ends up using)
+    return (size_t)kHeaderBytes + (4 * table_elems(*d) + split::table_floats(*d)) * sizeof(float);
+}
+
+static size_t legacy_workspace_bytes(const pde_adi_desc *d) {
+    BwdPlan p;
+    if (plan_bwd(d, &p) != PDE_OK) return 0;
+    return (p.scratch_floats + p.maps_floats + p.chan_floats + p.skip_floats) * sizeof(float) + 256;
+}
+
+extern "C" size_t pde_adi_checkpoint_bytes(const pde_adi_desc *d) {
+    if (validate(d) != PDE_OK) return 0;
+    return split::supported(*d) ? split::checkpoint_bytes(*d) : 0;
+}
+
+extern "C" size_t pde_adi_backward_saved_workspace_bytes(const pde_adi_desc *d) {
+    if (validate(d) != PDE_OK) return 0;
+    if (split::supported(*d)) return split::workspace_bytes(*d);
+    return legacy_workspace_bytes(d);
 }
 
 extern "C" size_t pde_adi_backward_workspace_bytes(const pde_adi_desc *d) {
     if (validate(d) != PDE_OK) return 0;
-    BwdPlan p;
-    if (plan_bwd(d, &p) != PDE_OK) return 0;
-    return (p.scratch_floats + p.maps_floats + p.chan_floats + p.skip_floats) * sizeof(float) + 256;
+    if (split::supported(*d)) return split::workspace_bytes(*d) + split::checkpoint_bytes(*d) + 256;
+    return legacy_workspace_bytes(d);
 }
 
 extern "C" int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sched, const float *ab,
@@ -1198,11 +1154,14 @@ extern "C" int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sc
         if (rc) return rc;
     }
     header_kernel<<<1, 1, 0, st>>>(*d, *sched, static_cast<char *>(tables));
-    return cuda_last_error();
+    rc = cuda_last_error();
+    if (rc) return rc;
+    if (split::supported(*d)) rc = split::prepare(*d, *sched, ab, bb, atc, btc, static_cast<char *>(tables), st);
+    return rc;
 }
 
-extern "C" int pde_adi_forward(const pde_adi_desc *d, const void *tables, const float *u, const float *chan,
-                               const float *skipw, float *out, void *stream) {
+extern "C" int pde_adi_forward_train(const pde_adi_desc *d, const void *tables, const float *u, const float *chan,
+                                     const float *skipw, float *out, void *ckpt, void *stream) {
     int rc = validate(d);
     if (rc) return rc;
     if (!tables || !u || !out) return PDE_ERR_INVALID;
@@ -1210,6 +1169,9 @@ extern "C" int pde_adi_forward(const pde_adi_desc *d, const void *tables, const 
     if (d->skip && !skipw) return PDE_ERR_INVALID;
     if (!aligned16(u) || !aligned16(out)) return PDE_ERR_INVALID;
     if (d->B == 0) return PDE_OK;
+    if (split::supported(*d))
+        return split::forward(*d, static_cast<const char *>(tables), u, chan, skipw, out, static_cast<float *>(ckpt),
+                              static_cast<cudaStream_t>(stream));
     DeviceProps props;
     rc = query_props(&props);
     if (rc) return rc;
@@ -1240,10 +1202,23 @@ extern "C" int pde_adi_forward(const pde_adi_desc *d, const void *tables, const 
     return rc;
 }
 
+extern "C" int pde_adi_forward(const pde_adi_desc *d, const void *tables, const float *u, const float *chan,
+                               const float *skipw, float *out, void *stream) {
+    return pde_adi_forward_train(d, tables, u, chan, skipw, out, nullptr, stream);
+}
+
 extern "C" int pde_adi_backward(const pde_adi_desc *d, const void *tables, const float *u, const float *gout,
                                 const float *chan, const float *skipw, float *gin, float *g_ab, float *g_bb,
                                 float *g_atc, float *g_btc, float *g_chan, float *g_skip, void *workspace,
                                 size_t workspace_bytes, void *stream) {
+    return pde_adi_backward_saved(d, tables, u, gout, chan, skipw, nullptr, gin, g_ab, g_bb, g_atc, g_btc, g_chan,
+                                  g_skip, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pde_adi_backward_saved(const pde_adi_desc *d, const void *tables, const float *u, const float *gout,
+                                      const float *chan, const float *skipw, const void *ckpt, float *gin,
+                                      float *g_ab, float *g_bb, float *g_atc, float *g_btc, float *g_chan,
+                                      float *g_skip, void *workspace, size_t workspace_bytes, void *stream) {
     int rc = validate(d);
     if (rc) return rc;
     if (!tables || !u || !gout || !g_ab || !g_bb || !g_atc || !g_btc) return PDE_ERR_INVALID;
@@ -1251,6 +1226,19 @@ extern "C" int pde_adi_backward(const pde_adi_desc *d, const void *tables, const
     if (d->skip && (!skipw || !g_skip)) return PDE_ERR_INVALID;
     if (!aligned16(u) || !aligned16(gout) || (gin && !aligned16(gin))) return PDE_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->B > 0 && split::supported(*d)) {
+        const char *tb = static_cast<const char *>(tables);
+        if (ckpt)
+            return split::backward(*d, tb, u, gout, chan, skipw, static_cast<const float *>(ckpt), gin, g_ab, g_bb, g_atc,
+                                   g_btc, g_chan, g_skip, workspace, workspace_bytes, st);
+        // no checkpoints from the forward call: make them first, at the head of the workspace
+        const size_t ckb = split::checkpoint_bytes(*d) + 256;
+        if (!workspace || workspace_bytes < ckb + split::workspace_bytes(*d)) return PDE_ERR_WORKSPACE;
+        rc = split::forward(*d, tb, u, chan, skipw, nullptr, static_cast<float *>(workspace), st);
+        if (rc) return rc;
+        return split::backward(*d, tb, u, gout, chan, skipw, static_cast<const float *>(workspace), gin, g_ab, g_bb,
+                               g_atc, g_btc, g_chan, g_skip, static_cast<char *>(workspace) + ckb, workspace_bytes - ckb, st);
+    }
     BwdPlan p;
     rc = plan_bwd(d, &p);
     if (rc) return rc;
@@ -1286,8 +1274,6 @@ extern "C" int pde_adi_backward(const pde_adi_desc *d, const void *tables, const
     }
     rc = launch_bwd(a, p, st);
     if (rc) return rc;
-    const size_t total = 4 * (size_t)d->C * d->N * d->N;
-    finish_kernel<<<(unsigned)((total + kFinishCells - 1) / kFinishCells), kFinishCells * kFinishSlices, 0, st>>>(*d, nw, a.part_maps, a.part_chan, a.part_skip,
-                                                                  skipw, g_ab, g_atc, g_bb, g_btc, g_chan, g_skip);
+    launch_finish(*d, nw, nw, a.part_maps, a.part_chan, a.part_skip, skipw, g_ab, g_atc, g_bb, g_btc, g_chan, g_skip, st);
     return cuda_last_error();
 }

@@ -1,0 +1,1096 @@
+// Implicit ADI layers, second implementation: HALF a line per thread, twisted factorisation.
+//
+// Same mathematics as adi.cu (reference: mnist_test.py:33-198, fashion_mnist.py:40-196,
+// SVHN.py:38-230, cifar10.py:53-211, cifar_2version.py:52-187); different mapping onto the SM:
+//
+//   * A tridiagonal system can be eliminated from BOTH ends towards the middle ("twisted"
+//     factorisation): two independent recurrences of half the length and one exchange where they
+//     meet.  Here the two halves of a line belong to two threads of a warp (lanes l and l ^ P), so
+//     a thread keeps N/2 cells of one sample pair in registers, the dependent chains are half as
+//     long and an SM holds twice the warps of adi.cu for the same number of samples in flight.
+//   * Everything is addressed in MIRRORED coordinates: a half line is indexed from the plane edge
+//     (k = 0) to the junction (k = H-1) in both halves, so both threads of a line run the same
+//     instruction stream; rows and columns of the tile are stored in that order too.
+//   * A block advances P sample pairs of every channel: the P threads that own the same half line
+//     read the same coefficient address (one L1 wavefront serves P pairs and 32/P half lines), and
+//     every lane of a warp is busy for any plane edge that is a multiple of 32 / (2 P).
+//   * The transposition between x and y sweeps goes through a shared-memory tile as in adi.cu, but
+//     across the warps of the block: one __syncthreads() per change of orientation.
+//   * The forward kernel optionally writes the state at the end of every step (the "checkpoints",
+//     HBM is idle in these kernels); the backward kernel starts from them instead of recomputing
+//     the forward trajectory.
+#include "adi_common.cuh"
+
+namespace pde {
+namespace adi {
+namespace split {
+
+template <int N, int P>
+struct SG {
+    static_assert(N % 4 == 0 && N >= 8 && N <= 32, "plane edge must be a multiple of 4 in [8, 32]");
+    static_assert(P == 1 || P == 2 || P == 4 || P == 8, "pairs per block");
+    static constexpr int H = N / 2;                 // cells per half line
+    static constexpr int HQ = (H + 3) / 4;          // float4 chunks of a half line in the tables
+    static constexpr int HCH = H / 2;               // 16-byte tile chunks (2 cells x 2 samples) per half row
+    static constexpr int PADC = (HCH % 2 == 0) ? 1 : 0;   // keeps the two halves of a row in different bank halves
+    static constexpr int HS = HCH + PADC;           // chunk stride between the halves of a row
+    static constexpr int NC = 2 * HS;               // chunks per tile row
+    static constexpr int LPW = 16 / P;              // lines per warp
+    static constexpr int WPC = (N + LPW - 1) / LPW; // warps per channel
+    static constexpr int RS = NC * P * 4;           // floats per tile row
+    static constexpr int HPAD = 16;                 // 64 bytes between the two halves of the rows: a half warp
+                                                    // reading a column touches rows of both halves
+    static constexpr int TILE = N * RS + HPAD;      // floats per tile: P sample pairs of one channel
+    static constexpr int QS = N * 2;                // float4 stride between the chunks of a table row
+};
+
+// float offset of (mirrored) row R of a tile
+template <int N, int P>
+__device__ __forceinline__ int row_off(int R) {
+    return R * SG<N, P>::RS + (R >= SG<N, P>::H ? SG<N, P>::HPAD : 0);
+}
+
+// mirrored index of a row / column / line: 0 .. H-1 from the near edge, H .. N-1 from the far edge
+// inwards (an involution)
+__host__ __device__ __forceinline__ int mirror(int i, int N) {
+    const int H = N / 2;
+    return i < H ? i : H + (N - 1 - i);
+}
+
+__host__ __device__ inline size_t stab_floats_per_table(const pde_adi_desc &d) {
+    const int H = d.N / 2, HQ = (H + 3) / 4;
+    return (size_t)d.steps * sweeps_per_step(d) * d.C * HQ * d.N * 2 * 4;
+}
+
+// ------------------------------------------------------------------------------------------
+// tables.  One thread per (sweep, channel, line): clamp -> smoothing -> r, then the twisted
+// pivots: top-down for cells 0 .. H-1 (op for op the reference's elimination), bottom-up for cells
+// N-1 .. H+1, and cell H closes both.  Layout [s][c][k/4][line][half][k%4] (k = mirrored cell).
+// ------------------------------------------------------------------------------------------
+__global__ void stables_kernel(pde_adi_desc d, pde_adi_schedule sch, const float *__restrict__ ab,
+                               const float *__restrict__ bb, const float *__restrict__ atc,
+                               const float *__restrict__ btc, float *stab) {
+    const int sps = sweeps_per_step(d), S = d.steps * sps, N = d.N, C = d.C, H = N / 2, HQ = (H + 3) / 4;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * C * N) return;
+    const int line = idx % N, c = (idx / N) % C, s = idx / (N * C);
+    const int axis = sweep_axis(s % sps);
+    const float *base = axis ? bb : ab, *tc = axis ? btc : atc;
+    const float tt = sch.t[s], dts = sch.dts[s], h2 = sch.h2[s];
+    const float third = __fdiv_rn(1.0f, 3.0f);
+    const size_t T = stab_floats_per_table(d);
+    float *tr = stab, *tinv = stab + T, *te = stab + 2 * T, *tm = stab + 3 * T;
+
+    float kap[32], msk[32], r[32], den[32];
+    for (int i = 0; i < N; ++i) {
+        const size_t q = axis == 0 ? ((size_t)c * N + line) * N + i : ((size_t)c * N + i) * N + line;
+        const float raw = __fadd_rn(base[q], __fmul_rn(tc[q], tt));
+        bool m = raw >= d.cmin;
+        float k = raw < d.cmin ? d.cmin : raw;
+        if (d.has_max) {
+            m = m && raw <= d.cmax;
+            k = k > d.cmax ? d.cmax : k;
+        }
+        kap[i] = k;
+        msk[i] = m ? 1.0f : 0.0f;
+    }
+    for (int i = 0; i < N; ++i) {
+        float ks = kap[i];
+        if (d.smooth) {
+            const float a0 = __fmul_rn(kap[i > 0 ? i - 1 : 0], third);
+            const float a1 = __fmul_rn(kap[i], third);
+            const float a2 = __fmul_rn(kap[i < N - 1 ? i + 1 : N - 1], third);
+            ks = __fadd_rn(__fadd_rn(a0, a1), a2);
+        }
+        r[i] = __fdiv_rn(__fmul_rn(ks, dts), h2);
+    }
+    auto diag = [&](int i) {
+        return (i == 0 || i == N - 1) ? __fadd_rn(1.0f, r[i]) : __fadd_rn(1.0f, __fmul_rn(2.0f, r[i]));
+    };
+    float cst = 0.0f;   // c*_{i-1} = -r_{i-1} / den_{i-1}
+    for (int i = 0; i < H; ++i) {
+        den[i] = i == 0 ? __fadd_rn(diag(i), d.eps) : __fadd_rn(__fsub_rn(diag(i), __fmul_rn(-r[i], cst)), d.eps);
+        cst = __fdiv_rn(-r[i], den[i]);
+    }
+    float ast = 0.0f;   // mirror image from the far end
+    for (int i = N - 1; i > H; --i) {
+        den[i] = i == N - 1 ? __fadd_rn(diag(i), d.eps) : __fadd_rn(__fsub_rn(diag(i), __fmul_rn(-r[i], ast)), d.eps);
+        ast = __fdiv_rn(-r[i], den[i]);
+    }
+    den[H] = __fadd_rn(__fsub_rn(__fsub_rn(diag(H), __fmul_rn(-r[H], cst)), __fmul_rn(-r[H], ast)), d.eps);
+
+    const int R = mirror(line, N);
+    for (int h = 0; h < 2; ++h)
+        for (int k = 0; k < 4 * HQ; ++k) {
+            const size_t o = ((((size_t)s * C + c) * HQ + k / 4) * N + R) * 8 + h * 4 + (k & 3);
+            if (k < H) {
+                const int i = h ? N - 1 - k : k;
+                tr[o] = r[i];
+                tinv[o] = __fdiv_rn(1.0f, den[i]);
+                te[o] = __fdiv_rn(r[i], den[i]);
+                tm[o] = msk[i];
+            } else {
+                tr[o] = 0.0f; tinv[o] = 0.0f; te[o] = 0.0f; tm[o] = 0.0f;
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// tile: N rows (mirrored order) x NC chunks x P pairs x {cell 2m, cell 2m+1} x {sample a, b}
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ f2 shfl_xor_f2(f2 a, int m) {
+    const float lo = __shfl_xor_sync(kFullMask, f2_lo(a), m);
+    const float hi = __shfl_xor_sync(kFullMask, f2_hi(a), m);
+    return f2_make(lo, hi);
+}
+
+struct Lane {
+    int c, wi, pp, h, R, tid_c;
+    bool active;
+};
+
+// AX == 0: the thread's half row (row R, half h); AX == 1: its half column (column R, rows of half h)
+template <int N, int P, int AX>
+__device__ __forceinline__ int half_base(const Lane &t) {
+    using G = SG<N, P>;
+    if (AX == 0) return row_off<N, P>(t.R) + (t.h * G::HS * P + t.pp) * 4;
+    const int hc = t.R >= G::H ? 1 : 0, kc = t.R - hc * G::H;
+    return t.h * (G::H * G::RS + G::HPAD) + ((hc * G::HS + (kc >> 1)) * P + t.pp) * 4 + (kc & 1) * 2;
+}
+
+template <int N, int P, int AX>
+__device__ __forceinline__ void ld_half(const float *tile, const Lane &t, f2 (&x)[N / 2]) {
+    using G = SG<N, P>;
+    const float *b = tile + half_base<N, P, AX>(t);
+    if (AX == 0) {
+#pragma unroll
+        for (int m = 0; m < G::HCH; ++m) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(b + m * P * 4);
+            x[2 * m].v = v.x;
+            x[2 * m + 1].v = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < G::H; ++k) x[k].v = *reinterpret_cast<const unsigned long long *>(b + k * G::RS);
+    }
+}
+template <int N, int P, int AX>
+__device__ __forceinline__ void st_half(float *tile, const Lane &t, const f2 (&x)[N / 2]) {
+    using G = SG<N, P>;
+    float *b = tile + half_base<N, P, AX>(t);
+    if (AX == 0) {
+#pragma unroll
+        for (int m = 0; m < G::HCH; ++m) {
+            ulonglong2 v;
+            v.x = x[2 * m].v;
+            v.y = x[2 * m + 1].v;
+            *reinterpret_cast<ulonglong2 *>(b + m * P * 4) = v;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < G::H; ++k) *reinterpret_cast<unsigned long long *>(b + k * G::RS) = x[k].v;
+    }
+}
+
+// planes of the block's P sample pairs (channel c) <-> tile.  A thread moves two adjacent cells of
+// both samples of a pair per step; consecutive lanes take consecutive pairs, then consecutive
+// cells.  All global loads of a thread are issued before the first one is used.
+template <int N, int P>
+struct PlaneIO {
+    using G = SG<N, P>;
+    static constexpr int F2 = N * N / 2;
+    static constexpr int NTHR = G::WPC * 32;
+    static constexpr int IT = (P * F2 + NTHR - 1) / NTHR;
+
+    __device__ static __forceinline__ int tile_off(int f, int pp, bool &hc) {
+        const int i = f / (N / 2), j0 = 2 * (f % (N / 2));
+        hc = j0 >= G::H;
+        const int m = hc ? (N - 2 - j0) / 2 : j0 / 2;
+        return row_off<N, P>(mirror(i, N)) + (((hc ? G::HS : 0) + m) * P + pp) * 4;
+    }
+
+    __device__ static __forceinline__ void to_tile(const float *__restrict__ g, float *tile, int item, int c, int C, int B,
+                                                   int tid_c) {
+        const float2 zero = make_float2(0.f, 0.f);
+        float2 a[IT], b[IT];
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int idx = tid_c + it * NTHR;
+            const int pp = idx % P, f = idx / P;
+            const int ba = (item * P + pp) * 2, bb = ba + 1;
+            const bool in = idx < P * F2;
+            a[it] = (in && ba < B) ? __ldcs(reinterpret_cast<const float2 *>(g + ((size_t)ba * C + c) * (N * N)) + f) : zero;
+            b[it] = (in && bb < B) ? __ldcs(reinterpret_cast<const float2 *>(g + ((size_t)bb * C + c) * (N * N)) + f) : zero;
+        }
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int idx = tid_c + it * NTHR;
+            if (idx < P * F2) {
+                bool hc;
+                const int o = tile_off(idx / P, idx % P, hc);
+                *reinterpret_cast<float4 *>(tile + o) = hc ? make_float4(a[it].y, b[it].y, a[it].x, b[it].x)
+                                                           : make_float4(a[it].x, b[it].x, a[it].y, b[it].y);
+            }
+        }
+    }
+
+    // out = tile                    (w == nullptr)
+    // out = sig * w + om * tile     (skip epilogue: w = u0;  grad_input: w = gout, om = 1)
+    __device__ static __forceinline__ void from_tile(const float *tile, float *__restrict__ g, int item, int c, int C,
+                                                     int B, int tid_c, const float *__restrict__ w, float sig, float om) {
+        const float2 zero = make_float2(0.f, 0.f);
+        float2 wa[IT], wb[IT];
+        if (w) {
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int idx = tid_c + it * NTHR;
+                const int pp = idx % P, f = idx / P;
+                const int ba = (item * P + pp) * 2, bb = ba + 1;
+                const bool in = idx < P * F2;
+                wa[it] = (in && ba < B) ? __ldcs(reinterpret_cast<const float2 *>(w + ((size_t)ba * C + c) * (N * N)) + f) : zero;
+                wb[it] = (in && bb < B) ? __ldcs(reinterpret_cast<const float2 *>(w + ((size_t)bb * C + c) * (N * N)) + f) : zero;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int idx = tid_c + it * NTHR;
+            if (idx < P * F2) {
+                const int pp = idx % P, f = idx / P;
+                const int ba = (item * P + pp) * 2, bb = ba + 1;
+                bool hc;
+                const float4 v = *reinterpret_cast<const float4 *>(tile + tile_off(f, pp, hc));
+                float2 a = hc ? make_float2(v.z, v.x) : make_float2(v.x, v.z);
+                float2 b = hc ? make_float2(v.w, v.y) : make_float2(v.y, v.w);
+                if (w) {
+                    a.x = fmaf(om, a.x, sig * wa[it].x);
+                    a.y = fmaf(om, a.y, sig * wa[it].y);
+                    b.x = fmaf(om, b.x, sig * wb[it].x);
+                    b.y = fmaf(om, b.y, sig * wb[it].y);
+                }
+                if (ba < B) __stcs(reinterpret_cast<float2 *>(g + ((size_t)ba * C + c) * (N * N)) + f, a);
+                if (bb < B) __stcs(reinterpret_cast<float2 *>(g + ((size_t)bb * C + c) * (N * N)) + f, b);
+            }
+        }
+    }
+};
+
+template <int N, int P>
+__device__ __forceinline__ void planes_to_tile(const float *__restrict__ g, float *tile, int item, int c, int C, int B,
+                                               int tid_c, int) {
+    PlaneIO<N, P>::to_tile(g, tile, item, c, C, B, tid_c);
+}
+template <int N, int P>
+__device__ __forceinline__ void tile_to_planes(const float *tile, float *__restrict__ g, int item, int c, int C, int B,
+                                               int tid_c, int, const float *__restrict__ w, float sig, float om) {
+    PlaneIO<N, P>::from_tile(tile, g, item, c, C, B, tid_c, w, sig, om);
+}
+
+// the thread's coefficients of one table for one sweep: HQ float4, the same address for the P
+// threads that own this half line in different sample pairs
+template <int N, int P>
+__device__ __forceinline__ void ld_coef(const float4 *__restrict__ p, float (&v)[4 * SG<N, P>::HQ]) {
+    using G = SG<N, P>;
+#pragma unroll
+    for (int q = 0; q < G::HQ; ++q) {
+        const float4 a = __ldg(p + q * G::QS);
+        v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+    }
+}
+
+// x[k] = sum_d mat[d * mstride] * (half row of channel d)
+template <int N, int P>
+__device__ __forceinline__ void mix_rows(const float *tiles, int C, const float *__restrict__ mat, int mstride,
+                                         const Lane &t, f2 (&x)[N / 2]) {
+    using G = SG<N, P>;
+    const f2 zero = f2_bc(0.0f);
+#pragma unroll
+    for (int k = 0; k < G::H; ++k) x[k] = zero;
+    for (int dd = 0; dd < C; ++dd) {
+        const float m = __ldg(mat + dd * mstride);
+        f2 row[G::H];
+        ld_half<N, P, 0>(tiles + (size_t)dd * G::TILE, t, row);
+#pragma unroll
+        for (int k = 0; k < G::H; ++k) x[k] = f2_fmas(m, row[k], x[k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// (A + eps I) x = d by twisted elimination.  Each half, cells numbered from its edge:
+//   d*_k = inv_k d_k + e_k d*_{k-1}                         k = 0 .. H-1
+//   the far half owns the closing cell: x = d*_{H-1} + e_{H-1} (near half's d*_{H-1})
+//   the near half's last cell:          x = d*_{H-1} + e_{H-1} (that x)
+//   x_k = d*_k + e_k x_{k+1}                               k = H-2 .. 0
+// ------------------------------------------------------------------------------------------
+template <int N, int P>
+__device__ __forceinline__ void solve(f2 (&x)[N / 2], const float4 *__restrict__ tinv, const float4 *__restrict__ te,
+                                      bool far) {
+    using G = SG<N, P>;
+    constexpr int H = G::H;
+    float iv[4 * G::HQ], e[4 * G::HQ];
+    ld_coef<N, P>(tinv, iv);
+    ld_coef<N, P>(te, e);
+    x[0] = f2_muls(iv[0], x[0]);
+#pragma unroll
+    for (int k = 1; k < H; ++k) x[k] = f2_fmas(e[k], x[k - 1], f2_muls(iv[k], x[k]));
+    f2 o = shfl_xor_f2(x[H - 1], P);
+    x[H - 1] = f2_fmas(far ? e[H - 1] : 0.0f, o, x[H - 1]);
+    o = shfl_xor_f2(x[H - 1], P);
+    x[H - 1] = f2_fmas(far ? 0.0f : e[H - 1], o, x[H - 1]);
+#pragma unroll
+    for (int k = H - 2; k >= 0; --k) x[k] = f2_fmas(e[k], x[k + 1], x[k]);
+}
+
+// L2 prefetch of a contiguous region by one thread (TMA bulk prefetch: no registers, no smem)
+__device__ __forceinline__ void prefetch_region_l2(const void *p, size_t bytes) {
+    const char *b = static_cast<const char *>(p);
+    constexpr size_t kChunk = 16384;
+    for (size_t off = 0; off < bytes; off += kChunk) {
+        const unsigned n = (unsigned)((bytes - off < kChunk ? bytes - off : kChunk) & ~(size_t)15);
+        if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b + off), "r"(n) : "memory");
+    }
+}
+
+template <int N, int P>
+__device__ __forceinline__ Lane make_lane() {
+    using G = SG<N, P>;
+    Lane t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    t.c = warp / G::WPC;
+    t.wi = warp % G::WPC;
+    t.pp = lane % P;
+    t.h = (lane / P) & 1;
+    const int line = t.wi * G::LPW + lane / (2 * P);
+    t.active = line < N;
+    t.R = t.active ? line : N - 1;
+    t.tid_c = threadIdx.x - t.c * G::WPC * 32;
+    return t;
+}
+
+// per-thread pointer (float4 units) into a split table for sweep s
+template <int N, int P>
+__device__ __forceinline__ size_t tab_off(int s, int C, const Lane &t) {
+    using G = SG<N, P>;
+    return ((((size_t)s * C + t.c) * G::HQ) * N + t.R) * 2 + t.h;
+}
+
+template <int N, int P>
+constexpr int fwd_max_threads() { return P >= 4 ? SG<N, P>::WPC * 32 : SG<N, P>::WPC * 32 * PDE_MAX_CHANNELS; }
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <int N, int P>
+__global__ void __launch_bounds__(fwd_max_threads<N, P>(), P >= 4 ? 3 : 1) sfwd_kernel(const Args a) {
+    using G = SG<N, P>;
+    constexpr int H = G::H, TILE = G::TILE;
+    extern __shared__ __align__(16) float smem[];
+    const pde_adi_desc &d = a.d;
+    const Lane t = make_lane<N, P>();
+    const int C = d.C, nthr = blockDim.x, nthr_c = G::WPC * 32;
+    const bool far = t.h == 1;
+    float *my = smem + (size_t)t.c * TILE;
+    const size_t T = stab_floats_per_table(d);
+    const float4 *tinv = reinterpret_cast<const float4 *>(a.stab + T);
+    const float4 *te = reinterpret_cast<const float4 *>(a.stab + 2 * T);
+    float sig = 0.0f;
+    if (d.skip) sig = 1.0f / (1.0f + expf(-__ldg(a.skipw)));
+    const float om = 1.0f - sig;
+    const size_t plane = (size_t)N * N;
+    const size_t ck_slot = (size_t)H * nthr;   // f2 per (item, step)
+    const int last_ax = a.sps == 3 ? 0 : 1;
+
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        if (threadIdx.x == 0) {   // the next item's planes start their trip from HBM to L2 now
+            const long long nb = (long long)(item + gridDim.x) * 2 * P;
+            if (nb < d.B) {
+                const long long ns = (d.B - nb) < 2 * P ? (d.B - nb) : 2 * P;
+                prefetch_region_l2(a.u + (size_t)nb * C * plane, (size_t)ns * C * plane * sizeof(float));
+            }
+        }
+        planes_to_tile<N, P>(a.u, my, item, t.c, C, d.B, t.tid_c, nthr_c);
+        __syncthreads();
+        f2 x[H];
+        bool in_regs = false;   // x holds the state as rows
+        for (int step = 0; step < d.steps; ++step) {
+            const int s0 = step * a.sps;
+            if (d.chan_op == 1) {
+                if (in_regs) {
+                    if (t.active) st_half<N, P, 0>(my, t, x);
+                    __syncthreads();
+                }
+                mix_rows<N, P>(smem, C, a.chan + t.c * C, 1, t, x);
+                __syncthreads();
+            } else if (!in_regs) {
+                ld_half<N, P, 0>(my, t, x);
+            }
+            solve<N, P>(x, tinv + tab_off<N, P>(s0, C, t), te + tab_off<N, P>(s0, C, t), far);
+            if (t.active) st_half<N, P, 0>(my, t, x);
+            __syncthreads();
+            ld_half<N, P, 1>(my, t, x);
+            solve<N, P>(x, tinv + tab_off<N, P>(s0 + 1, C, t), te + tab_off<N, P>(s0 + 1, C, t), far);
+            if (a.sps == 3) {
+                if (t.active) st_half<N, P, 1>(my, t, x);
+                __syncthreads();
+                ld_half<N, P, 0>(my, t, x);
+                solve<N, P>(x, tinv + tab_off<N, P>(s0 + 2, C, t), te + tab_off<N, P>(s0 + 2, C, t), far);
+                in_regs = true;
+            }
+            if (a.ckpt) {   // state after the last sweep of the step, in the orientation it is in
+                unsigned long long *ck = reinterpret_cast<unsigned long long *>(a.ckpt) +
+                                         ((size_t)item * d.steps + step) * ck_slot + threadIdx.x;
+#pragma unroll
+                for (int k = 0; k < H; ++k) __stcs(ck + (size_t)k * nthr, x[k].v);
+            }
+            if (a.sps != 3) {   // Lie: the state sits in registers as columns
+                if (t.active) st_half<N, P, 1>(my, t, x);
+                __syncthreads();
+                in_regs = false;
+            }
+            if (d.chan_op == 2) {
+                if (in_regs) {
+                    if (t.active) st_half<N, P, 0>(my, t, x);
+                    __syncthreads();
+                }
+                mix_rows<N, P>(smem, C, a.chan + t.c * C, 1, t, x);
+                __syncthreads();
+                in_regs = true;
+            }
+        }
+        if (in_regs) {
+            if (t.active) st_half<N, P, 0>(my, t, x);
+            __syncthreads();
+        }
+        (void)last_ax;
+        if (a.out) tile_to_planes<N, P>(my, a.out, item, t.c, C, d.B, t.tid_c, nthr_c, d.skip ? a.u : nullptr, sig, om);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+
+// Per-pixel gradient accumulators in TMEM: 64 columns per warp = {A0, A1, B0, B1} x 16, one TMEM
+// lane per thread.  acc0 += z, acc1 += t * z for the kind (alpha / beta) of the sweep.
+__device__ __forceinline__ void tmem_accumulate16(uint32_t tacc, const float (&z)[16], float tt) {
+    float a0[16], a1[16];
+    tmem_wait_st();
+    tmem_ld16(tacc, a0);
+    tmem_ld16(tacc + 16, a1);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        a0[i] += z[i];
+        a1[i] = fmaf(tt, z[i], a1[i]);
+    }
+    tmem_st16(tacc, a0);
+    tmem_st16(tacc + 16, a1);
+}
+
+// One reversed sweep for the thread's half line (orientation AX).
+//   g : adjoint of the sweep output -> adjoint of the sweep input, in registers
+//       w_k = g_k + e_{k-1} w_{k-1};  the far half's closing cell also takes e w of the near half's last cell
+//       lambda_{H-1} = inv w (far) | inv (w + r lambda of the closing cell) (near)
+//       lambda_k = inv_k (w_k + r_{k+1} lambda_{k+1})
+//   xt: tile holding the sweep OUTPUT; (L x)_k, v_k = lambda_k (L x)_k summed over the two samples,
+//       and (if `rebuild`) the sweep INPUT x_in = (1 + eps) x - r (L x) written back in place.
+//   v -> smoothing^T -> clamp mask -> TMEM accumulators of this sweep's kind.
+template <int N, int P, int AX>
+__device__ __forceinline__ void reverse_sweep(f2 (&g)[N / 2], float *xt, const Lane &t, uint32_t tacc,
+                                              const float4 *tr, const float4 *tinv, const float4 *te, const float4 *tm,
+                                              float scale, float tt, float onepe, bool smooth, bool rebuild,
+                                              bool clamped) {
+    using G = SG<N, P>;
+    constexpr int H = G::H;
+    const bool far = t.h == 1;
+    float r[4 * G::HQ], iv[4 * G::HQ], e[4 * G::HQ];
+    ld_coef<N, P>(te, e);
+    ld_coef<N, P>(tinv, iv);
+    ld_coef<N, P>(tr, r);
+    f2 x[H];
+    ld_half<N, P, AX>(xt, t, x);
+#pragma unroll
+    for (int k = 1; k < H; ++k) g[k] = f2_fmas(e[k - 1], g[k - 1], g[k]);
+    {
+        const f2 z = shfl_xor_f2(f2_muls(e[H - 1], g[H - 1]), P);
+        g[H - 1] = f2_fmas(far ? 1.0f : 0.0f, z, g[H - 1]);
+    }
+    f2 lam = f2_muls(iv[H - 1], g[H - 1]);
+    {
+        const f2 z = shfl_xor_f2(f2_muls(r[H - 1], lam), P);
+        lam = f2_fmas(far ? 0.0f : iv[H - 1], z, lam);
+    }
+    f2 xnext = shfl_xor_f2(x[H - 1], P);   // the cell across the junction (sweep output)
+    float v[16];
+#pragma unroll
+    for (int k = H; k < 16; ++k) v[k] = 0.0f;
+#pragma unroll
+    for (int k = H - 1; k >= 0; --k) {
+        if (k < H - 1) lam = f2_fmas(r[k + 1] * iv[k], g[k + 1], f2_muls(iv[k], g[k]));
+        g[k] = lam;
+        const f2 cur = x[k];
+        const f2 lx = (k == 0) ? f2_sub(xnext, cur) : f2_fmas(-2.0f, cur, f2_add(x[k - 1], xnext));
+        v[k] = f2_hsum(f2_mul(lam, lx));
+        x[k] = f2_fmas(-r[k], lx, f2_muls(onepe, cur));
+        xnext = cur;
+    }
+    if (rebuild && t.active) st_half<N, P, AX>(xt, t, x);
+    if (smooth) {
+        const float k3 = scale * (1.0f / 3.0f);
+        const float vj = __shfl_xor_sync(kFullMask, v[H - 1], P);
+        float lo = v[0];
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const float cur = v[k];
+            const float hi = (k == H - 1) ? vj : v[k + 1];
+            v[k] = ((lo + cur) + hi) * k3;
+            lo = cur;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < H; ++k) v[k] *= scale;
+    }
+    if (clamped) {
+        float m[4 * G::HQ];
+        ld_coef<N, P>(tm, m);
+#pragma unroll
+        for (int k = 0; k < H; ++k) v[k] *= m[k];
+    }
+    tmem_accumulate16(tacc, v, tt);
+}
+
+// Adjoint of a channel op.  On entry (after a barrier) the g tiles hold the adjoint of the op's
+// output as rows, the x tiles the op's INPUT:  gm[dd] += sum g_c x_dd ;  g_c <- sum_c' mat[c'][c] g_c'.
+template <int N, int P>
+__device__ __forceinline__ void chan_adjoint(float *ggt, const float *gxt, int C, const float *__restrict__ mat,
+                                             const Lane &t, float (&gm)[PDE_MAX_CHANNELS]) {
+    using G = SG<N, P>;
+    constexpr int H = G::H;
+    {
+        f2 g[H];
+        ld_half<N, P, 0>(ggt + (size_t)t.c * G::TILE, t, g);
+        for (int dd = 0; dd < C; ++dd) {
+            f2 x[H];
+            ld_half<N, P, 0>(gxt + (size_t)dd * G::TILE, t, x);
+            f2 acc = f2_bc(0.0f);
+#pragma unroll
+            for (int k = 0; k < H; ++k) acc = f2_fma(g[k], x[k], acc);
+            if (t.active) gm[dd] += f2_hsum(acc);
+        }
+    }
+    f2 gn[H];
+    mix_rows<N, P>(ggt, C, mat + t.c, C, t, gn);
+    __syncthreads();
+    if (t.active) st_half<N, P, 0>(ggt + (size_t)t.c * G::TILE, t, gn);
+}
+
+template <int N, int P>
+constexpr int bwd_max_threads() { return P >= 4 ? SG<N, P>::WPC * 32 : SG<N, P>::WPC * 32 * PDE_MAX_CHANNELS; }
+
+template <int N, int P, bool CHAN>
+__global__ void __launch_bounds__(bwd_max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kernel(const Args a) {
+    using G = SG<N, P>;
+    constexpr int H = G::H, TILE = G::TILE;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float h_scale[PDE_MAX_SWEEPS], h_t[PDE_MAX_SWEEPS];
+    __shared__ int h_clamped[PDE_MAX_SWEEPS];
+    const pde_adi_desc &d = a.d;
+    const Lane t = make_lane<N, P>();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C = d.C, nthr = blockDim.x, nthr_c = G::WPC * 32;
+    float *gxt = smem, *ggt = smem + (size_t)C * TILE;
+    float *xt = gxt + (size_t)t.c * TILE, *gt = ggt + (size_t)t.c * TILE;
+
+    if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)a.tmem_cols);
+    const Header *hdr = reinterpret_cast<const Header *>(a.tables);
+    for (int i = threadIdx.x; i < a.S; i += nthr) {
+        h_scale[i] = hdr->scale[i];
+        h_t[i] = hdr->t[i];
+        h_clamped[i] = hdr->clamped[i];
+    }
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t tbase = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+    {
+        float z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0.0f;
+#pragma unroll
+        for (int col = 0; col < 64; col += 16) tmem_st16(tbase + col, z);
+        tmem_wait_st();
+    }
+    const bool exact = hdr->mode_exact != 0;
+    const size_t T = stab_floats_per_table(d);
+    const float4 *tab_r = reinterpret_cast<const float4 *>(a.stab);
+    const float4 *tab_inv = reinterpret_cast<const float4 *>(a.stab + T);
+    const float4 *tab_e = reinterpret_cast<const float4 *>(a.stab + 2 * T);
+    const float4 *tab_m = reinterpret_cast<const float4 *>(a.stab + 3 * T);
+    const size_t plane = (size_t)N * N;
+    const size_t ck_slot = (size_t)H * nthr;
+    float sig = 0.0f;
+    if (d.skip) sig = 1.0f / (1.0f + expf(-__ldg(a.skipw)));
+    const float om = 1.0f - sig;
+    const float onepe = 1.0f + d.eps;
+    const bool smooth = d.smooth != 0;
+    float gm[PDE_MAX_CHANNELS] = {0.f, 0.f, 0.f, 0.f};
+    float gw = 0.0f;
+    const int sps = a.sps;
+    const int last_ax = (sps == 3) ? 0 : 1;
+    // exact mode: outputs of the first sps-1 sweeps of the step being reversed, per block
+    unsigned long long *sweep_scr =
+        reinterpret_cast<unsigned long long *>(a.scratch) + (size_t)blockIdx.x * 2 * ck_slot + threadIdx.x;
+
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const unsigned long long *ck_item =
+            reinterpret_cast<const unsigned long long *>(a.ckpt) + (size_t)item * d.steps * ck_slot + threadIdx.x;
+        if (threadIdx.x == 0) {   // next item: checkpoints and planes on their way to L2
+            const long long ni = (long long)item + gridDim.x;
+            const long long nb = ni * 2 * P;
+            if (nb < d.B) {
+                const long long ns = (d.B - nb) < 2 * P ? (d.B - nb) : 2 * P;
+                prefetch_region_l2(a.gout + (size_t)nb * C * plane, (size_t)ns * C * plane * sizeof(float));
+                prefetch_region_l2(reinterpret_cast<const unsigned long long *>(a.ckpt) + (size_t)ni * d.steps * ck_slot,
+                                   (size_t)d.steps * ck_slot * 8);
+                if (d.skip || d.chan_op == 1 || exact)
+                    prefetch_region_l2(a.u + (size_t)nb * C * plane, (size_t)ns * C * plane * sizeof(float));
+            }
+        }
+        // Which orientation last touched a tile, and whether a barrier has passed since: a thread only
+        // reads and writes its own half line within one orientation, so a barrier is needed exactly
+        // when the orientation changes (2 = block-wide access pattern).
+        int x_last = 2, g_last = 2;
+        bool x_sync = true, g_sync = true;
+        auto bar = [&]() {
+            __syncthreads();
+            x_sync = true;
+            g_sync = true;
+        };
+        auto touch_x = [&](int o) {
+            if ((x_last != o || o == 2) && !x_sync) bar();
+            x_last = o;
+            x_sync = false;
+        };
+        auto touch_g = [&](int o) {
+            if ((g_last != o || o == 2) && !g_sync) bar();
+            g_last = o;
+            g_sync = false;
+        };
+        auto ck_load = [&](int step, f2 (&x)[H]) {
+#pragma unroll
+            for (int k = 0; k < H; ++k) x[k].v = __ldcs(ck_item + ((size_t)step * H + k) * nthr);
+        };
+        // x tile <- state after the last sweep of `step` (step == -1: the layer input)
+        auto state_to_xt = [&](int step) {
+            if (step < 0) {
+                touch_x(2);
+                planes_to_tile<N, P>(a.u, xt, item, t.c, C, d.B, t.tid_c, nthr_c);
+            } else {
+                f2 xs[H];
+                ck_load(step, xs);
+                touch_x(last_ax);
+                if (t.active) {
+                    if (last_ax == 0) st_half<N, P, 0>(xt, t, xs);
+                    else st_half<N, P, 1>(xt, t, xs);
+                }
+            }
+        };
+
+        touch_g(2);
+        planes_to_tile<N, P>(a.gout, gt, item, t.c, C, d.B, t.tid_c, nthr_c);
+        if (d.skip) {
+            // out = sig u0 + om uF:  dL/dw += sig' * sum gout (u0 - uF),  g <- om * gout
+            f2 uf[H];
+            state_to_xt(d.steps - 1);
+            if (d.chan_op == 2) {
+                touch_x(2);
+                bar();
+                mix_rows<N, P>(gxt, C, a.chan + t.c * C, 1, t, uf);
+                x_sync = false;
+            } else {
+                touch_x(0);
+                ld_half<N, P, 0>(xt, t, uf);
+            }
+            touch_g(0);
+            f2 gl[H];
+            ld_half<N, P, 0>(gt, t, gl);
+            if (t.active) {
+                f2 accw = f2_bc(0.0f);
+                const int i = mirror(t.R, N);
+                const float2 zero2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int m = 0; m < G::HCH; ++m) {
+                    // cells k = 2m, 2m+1 of the half row: columns 2m, 2m+1 (near) or N-1-2m, N-2-2m (far)
+                    const int j0 = t.h ? N - 2 - 2 * m : 2 * m;
+                    const int ba = (item * P + t.pp) * 2, bb = ba + 1;
+                    const float2 wa = ba < d.B ? __ldg(reinterpret_cast<const float2 *>(a.u + ((size_t)ba * C + t.c) * plane + (size_t)i * N + j0)) : zero2;
+                    const float2 wb = bb < d.B ? __ldg(reinterpret_cast<const float2 *>(a.u + ((size_t)bb * C + t.c) * plane + (size_t)i * N + j0)) : zero2;
+                    const f2 u0 = t.h ? f2_make(wa.y, wb.y) : f2_make(wa.x, wb.x);
+                    const f2 u1 = t.h ? f2_make(wa.x, wb.x) : f2_make(wa.y, wb.y);
+                    accw = f2_fma(gl[2 * m], f2_sub(u0, uf[2 * m]), accw);
+                    accw = f2_fma(gl[2 * m + 1], f2_sub(u1, uf[2 * m + 1]), accw);
+                    gl[2 * m] = f2_muls(om, gl[2 * m]);
+                    gl[2 * m + 1] = f2_muls(om, gl[2 * m + 1]);
+                }
+                st_half<N, P, 0>(gt, t, gl);
+                gw += f2_hsum(accw);
+            }
+        }
+
+        f2 g[H];
+        int g_ax = -1;   // orientation of g in registers (-1: in its tile)
+        auto g_to_tile = [&]() {
+            if (g_ax >= 0) {
+                touch_g(g_ax);
+                if (t.active) {
+                    if (g_ax == 0) st_half<N, P, 0>(gt, t, g);
+                    else st_half<N, P, 1>(gt, t, g);
+                }
+                g_ax = -1;
+            }
+        };
+        for (int step = d.steps - 1; step >= 0; --step) {
+            if (exact) {
+                // recompute the sweeps of this step from its input, keeping every sweep output
+                f2 x[H];
+                state_to_xt(step - 1);
+                if (CHAN && (d.chan_op == 1 || (d.chan_op == 2 && step > 0))) {
+                    touch_x(2);
+                    bar();
+                    mix_rows<N, P>(gxt, C, a.chan + t.c * C, 1, t, x);
+                    x_sync = false;
+                    bar();   // every thread has read the group's tiles before they are overwritten
+                } else {
+                    touch_x(0);
+                    ld_half<N, P, 0>(xt, t, x);
+                }
+                for (int k = 0; k + 1 < sps; ++k) {
+                    const int s = step * sps + k;
+                    if (k == 1) {
+                        touch_x(0);
+                        if (t.active) st_half<N, P, 0>(xt, t, x);
+                        touch_x(1);
+                        ld_half<N, P, 1>(xt, t, x);
+                    }
+                    solve<N, P>(x, tab_inv + tab_off<N, P>(s, C, t), tab_e + tab_off<N, P>(s, C, t), t.h == 1);
+#pragma unroll
+                    for (int kk = 0; kk < H; ++kk) __stcg(sweep_scr + ((size_t)k * H + kk) * nthr, x[kk].v);
+                }
+            }
+            state_to_xt(step);
+            if (CHAN && d.chan_op == 2) {
+                // adjoint of the post-step coupling: its input is the state after the last sweep
+                g_to_tile();
+                touch_g(2);
+                touch_x(2);
+                bar();
+                chan_adjoint<N, P>(ggt, gxt, C, a.chan, t, gm);
+                g_last = 0; g_sync = false;
+                x_last = 0; x_sync = false;
+            }
+            for (int k = sps - 1; k >= 0; --k) {
+                const int s = step * sps + k, ax = sweep_axis(k);
+                if (exact && k != sps - 1) {
+                    f2 xs[H];
+#pragma unroll
+                    for (int kk = 0; kk < H; ++kk) xs[kk].v = __ldcg(sweep_scr + ((size_t)k * H + kk) * nthr);
+                    touch_x(ax);
+                    if (t.active) {
+                        if (ax == 0) st_half<N, P, 0>(xt, t, xs);
+                        else st_half<N, P, 1>(xt, t, xs);
+                    }
+                }
+                if (g_ax != ax) {
+                    g_to_tile();
+                    touch_g(ax);
+                    touch_x(ax);
+                    if (ax == 0) ld_half<N, P, 0>(gt, t, g);
+                    else ld_half<N, P, 1>(gt, t, g);
+                    g_ax = ax;
+                } else {
+                    touch_x(ax);
+                }
+                const size_t o = tab_off<N, P>(s, C, t);
+                const float scale = h_scale[s], tt = h_t[s];
+                const bool clamped = h_clamped[s] != 0;
+                const bool rebuild = !exact && k > 0;
+                if (ax == 0)
+                    reverse_sweep<N, P, 0>(g, xt, t, tbase, tab_r + o, tab_inv + o, tab_e + o, tab_m + o, scale, tt, onepe,
+                                           smooth, rebuild, clamped);
+                else
+                    reverse_sweep<N, P, 1>(g, xt, t, tbase + 32u, tab_r + o, tab_inv + o, tab_e + o, tab_m + o, scale, tt,
+                                           onepe, smooth, rebuild, clamped);
+            }
+            if (CHAN && d.chan_op == 1) {
+                // adjoint of the pre-step mix: needs g (rows) and the mix INPUT = state before this step
+                g_to_tile();
+                state_to_xt(step - 1);
+                touch_g(2);
+                touch_x(2);
+                bar();
+                chan_adjoint<N, P>(ggt, gxt, C, a.chan, t, gm);
+                g_last = 0; g_sync = false;
+                x_last = 0; x_sync = false;
+            }
+        }
+        g_to_tile();
+        touch_g(2);
+        if (a.need_gin)
+            tile_to_planes<N, P>(gt, a.gin, item, t.c, C, d.B, t.tid_c, nthr_c, d.skip ? a.gout : nullptr, sig, 1.0f);
+        // the next item overwrites both tiles with a block-wide pattern
+        __syncthreads();
+    }
+
+    // ------------------------------ partials: TMEM -> sum over the P pairs -> global [row][col]
+    tmem_wait_st();
+    float *pm = a.part_maps + ((size_t)blockIdx.x * C + t.c) * 4 * plane;
+    const int L = mirror(t.R, N);   // the line's position in the plane
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        float av[16];
+        tmem_ld16(tbase + kk * 16, av);
+        tmem_wait_ld();
+#pragma unroll
+        for (int o = 1; o < P; o <<= 1)
+#pragma unroll
+            for (int k = 0; k < H; ++k) av[k] += __shfl_xor_sync(kFullMask, av[k], o);
+        if (t.active && t.pp == 0) {
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const int along = t.h ? N - 1 - k : k;
+                const size_t cell = kk < 2 ? (size_t)L * N + along : (size_t)along * N + L;
+                pm[kk * plane + cell] = av[k];
+            }
+        }
+    }
+    const size_t set = ((size_t)blockIdx.x * G::WPC + t.wi) * C + t.c;
+#pragma unroll
+    for (int dd = 0; dd < PDE_MAX_CHANNELS; ++dd) {
+        const float sgm = warp_sum(gm[dd]);
+        if (lane == 0) a.part_chan[set * PDE_MAX_CHANNELS + dd] = sgm;
+    }
+    const float sgw = warp_sum(gw);
+    if (lane == 0) a.part_skip[set] = sgw;
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, (uint32_t)a.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+bool supported(const pde_adi_desc &d) {
+    if (env_int("PDE_B200_ADI_LEGACY", 0)) return false;
+    if (d.steps < 1 || d.B < 1) return false;
+    return d.N == 28 || d.N == 32;
+}
+
+size_t table_floats(const pde_adi_desc &d) { return 4 * stab_floats_per_table(d); }
+
+struct Plan {
+    int P, threads, wpc, grid, nitems, tmem_cols, blocks_per_sm;
+    size_t smem_fwd, smem_bwd, ck_slot;
+};
+
+static int choose_pairs(const pde_adi_desc &d, int sm_count) {
+    const int forced = env_int("PDE_B200_SPLIT_P", 0);
+    if (forced == 2 || (forced == 4 && d.C == 1)) return forced;
+    if (d.C == 1 && (d.B + 7) / 8 >= 2 * sm_count) return 4;
+    return 2;
+}
+
+template <int N, int P>
+static void fill_geo(const pde_adi_desc &d, Plan *p) {
+    using G = SG<N, P>;
+    p->wpc = G::WPC;
+    p->threads = G::WPC * 32 * d.C;
+    p->smem_fwd = (size_t)d.C * G::TILE * sizeof(float);
+    p->smem_bwd = 2 * p->smem_fwd;
+    p->ck_slot = (size_t)G::H * p->threads;
+}
+
+static int make_plan(const pde_adi_desc &d, Plan *p) {
+    DeviceProps props;
+    int rc = query_props(&props);
+    if (rc) return rc;
+    p->P = choose_pairs(d, props.sm_count);
+    if (d.N == 28) { if (p->P == 4) fill_geo<28, 4>(d, p); else fill_geo<28, 2>(d, p); }
+    else if (d.N == 32) { if (p->P == 4) fill_geo<32, 4>(d, p); else fill_geo<32, 2>(d, p); }
+    else return PDE_ERR_UNSUPPORTED;
+    p->nitems = (d.B + 2 * p->P - 1) / (2 * p->P);
+    const int warps = p->threads / 32;
+    const int blocks4 = (warps + 3) / 4;
+    p->tmem_cols = blocks4 * 64 <= 64 ? 64 : (blocks4 * 64 <= 128 ? 128 : (blocks4 * 64 <= 256 ? 256 : 512));
+    p->blocks_per_sm = 0;
+    p->grid = 0;
+    (void)props;
+    return PDE_OK;
+}
+
+size_t checkpoint_bytes(const pde_adi_desc &d) {
+    Plan p;
+    if (!supported(d) || make_plan(d, &p) != PDE_OK) return 0;
+    return (size_t)p.nitems * d.steps * p.ck_slot * 8 + 256;
+}
+
+template <int N, int P>
+static const void *bwd_ptr(bool chan) {
+    return chan ? reinterpret_cast<const void *>(sbwd_kernel<N, P, true>)
+                : reinterpret_cast<const void *>(sbwd_kernel<N, P, false>);
+}
+static const void *bwd_kernel_for(int N, int P, bool chan) {
+    if (N == 28) return P == 4 ? bwd_ptr<28, 4>(chan) : bwd_ptr<28, 2>(chan);
+    if (N == 32) return P == 4 ? bwd_ptr<32, 4>(chan) : bwd_ptr<32, 2>(chan);
+    return nullptr;
+}
+static const void *fwd_kernel_for(int N, int P) {
+    if (N == 28) return P == 4 ? reinterpret_cast<const void *>(sfwd_kernel<28, 4>) : reinterpret_cast<const void *>(sfwd_kernel<28, 2>);
+    if (N == 32) return P == 4 ? reinterpret_cast<const void *>(sfwd_kernel<32, 4>) : reinterpret_cast<const void *>(sfwd_kernel<32, 2>);
+    return nullptr;
+}
+
+static int plan_bwd_grid(const pde_adi_desc &d, Plan *p) {
+    DeviceProps props;
+    int rc = query_props(&props);
+    if (rc) return rc;
+    const void *kern = bwd_kernel_for(d.N, p->P, d.chan_op != 0);
+    if (!kern) return PDE_ERR_UNSUPPORTED;
+    if (p->smem_bwd > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
+    PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bwd));
+    // residency from first principles (the occupancy calculator answers 1 block / SM for kernels
+    // that allocate tensor memory)
+    cudaFuncAttributes fa;
+    PDE_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+    const int warps = p->threads / 32;
+    const int regs_per_warp = ((fa.numRegs + 7) / 8) * 8 * 32;
+    int occ = 65536 / (regs_per_warp * warps);
+    const int by_smem = (int)((size_t)(228 * 1024) / (p->smem_bwd + fa.sharedSizeBytes + 1024));
+    const int by_threads = 2048 / p->threads;
+    const int by_tmem = 512 / p->tmem_cols;
+    if (by_smem < occ) occ = by_smem;
+    if (by_threads < occ) occ = by_threads;
+    if (by_tmem < occ) occ = by_tmem;
+    const int cap_env = env_int("PDE_B200_SPLIT_BWD_OCC", 0);
+    if (cap_env > 0 && cap_env < occ) occ = cap_env;
+    if (occ < 1) occ = 1;
+    p->blocks_per_sm = occ;
+    if (env_int("PDE_B200_DEBUG", 0))
+        fprintf(stderr, "[pde_b200] split bwd plan: N=%d C=%d P=%d threads=%d smem=%zu regs=%d occ=%d tmem=%d\n", d.N, d.C,
+                p->P, p->threads, p->smem_bwd, fa.numRegs, occ, p->tmem_cols);
+    const int cap = props.sm_count * occ;
+    p->grid = p->nitems < cap ? p->nitems : cap;
+    if (p->grid < 1) p->grid = 1;
+    return PDE_OK;
+}
+
+struct WsLayout {
+    size_t scratch_floats, maps_floats, chan_floats, skip_floats;
+    int nsets_maps, nsets_small;
+};
+
+static void ws_layout(const pde_adi_desc &d, const Plan &p, int grid, WsLayout *w) {
+    w->scratch_floats = (size_t)grid * 2 * p.ck_slot * 2;   // two sweep outputs per block (exact mode)
+    w->nsets_maps = grid * d.C;
+    w->nsets_small = grid * p.wpc * d.C;
+    w->maps_floats = (size_t)w->nsets_maps * 4 * d.N * d.N;
+    w->chan_floats = (size_t)w->nsets_small * PDE_MAX_CHANNELS;
+    w->skip_floats = (size_t)w->nsets_small;
+}
+
+size_t workspace_bytes(const pde_adi_desc &d) {
+    Plan p;
+    if (!supported(d) || make_plan(d, &p) != PDE_OK) return 0;
+    if (plan_bwd_grid(d, &p) != PDE_OK) return 0;
+    WsLayout w;
+    ws_layout(d, p, p.grid, &w);
+    return (w.scratch_floats + w.maps_floats + w.chan_floats + w.skip_floats) * sizeof(float) + 512;
+}
+
+int prepare(const pde_adi_desc &d, const pde_adi_schedule &sch, const float *ab, const float *bb, const float *atc,
+            const float *btc, char *tables, cudaStream_t st) {
+    const int S = d.steps * sweeps_per_step(d);
+    const int n = S * d.C * d.N;
+    float *stab = reinterpret_cast<float *>(tables + kHeaderBytes) + 4 * table_elems(d);
+    if (n > 0) stables_kernel<<<(n + 127) / 128, 128, 0, st>>>(d, sch, ab, bb, atc, btc, stab);
+    return cuda_last_error();
+}
+
+static void fill_args(const pde_adi_desc &d, const char *tables, Args *a) {
+    a->d = d;
+    a->sps = sweeps_per_step(d);
+    a->S = d.steps * a->sps;
+    a->G = 1;
+    a->tables = tables;
+    a->stab = reinterpret_cast<const float *>(tables + kHeaderBytes) + 4 * table_elems(d);
+}
+
+int forward(const pde_adi_desc &d, const char *tables, const float *u, const float *chan, const float *skipw,
+            float *out, float *ckpt, cudaStream_t st) {
+    Plan p;
+    int rc = make_plan(d, &p);
+    if (rc) return rc;
+    DeviceProps props;
+    rc = query_props(&props);
+    if (rc) return rc;
+    const void *kern = fwd_kernel_for(d.N, p.P);
+    if (!kern) return PDE_ERR_UNSUPPORTED;
+    if (p.smem_fwd > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
+    PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_fwd));
+    int per_sm = 1;
+    PDE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, p.threads, p.smem_fwd));
+    if (per_sm < 1) per_sm = 1;
+    const int cap_env = env_int("PDE_B200_SPLIT_FWD_OCC", 0);
+    if (cap_env > 0 && cap_env < per_sm) per_sm = cap_env;
+    Args a{};
+    fill_args(d, tables, &a);
+    a.nitems = p.nitems;
+    a.u = u; a.chan = chan; a.skipw = skipw; a.out = out;
+    a.ckpt = ckpt ? reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ckpt) + 255u) & ~(uintptr_t)255u) : nullptr;
+    const int cap = props.sm_count * per_sm;
+    const int grid = p.nitems < cap ? p.nitems : cap;
+    if (env_int("PDE_B200_DEBUG", 0))
+        fprintf(stderr, "[pde_b200] split fwd plan: N=%d C=%d P=%d threads=%d smem=%zu occ=%d grid=%d\n", d.N, d.C, p.P,
+                p.threads, p.smem_fwd, per_sm, grid);
+    void *params[] = {&a};
+    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(p.threads), params, p.smem_fwd, st));
+    return cuda_last_error();
+}
+
+int backward(const pde_adi_desc &d, const char *tables, const float *u, const float *gout, const float *chan,
+             const float *skipw, const float *ckpt, float *gin, float *g_ab, float *g_bb, float *g_atc, float *g_btc,
+             float *g_chan, float *g_skip, void *workspace, size_t workspace_bytes_, cudaStream_t st) {
+    Plan p;
+    int rc = make_plan(d, &p);
+    if (rc) return rc;
+    rc = plan_bwd_grid(d, &p);
+    if (rc) return rc;
+    WsLayout w;
+    ws_layout(d, p, p.grid, &w);
+    const size_t need = (w.scratch_floats + w.maps_floats + w.chan_floats + w.skip_floats) * sizeof(float) + 512;
+    if (!workspace || workspace_bytes_ < need || !ckpt) return PDE_ERR_WORKSPACE;
+    float *ws = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255u) & ~(uintptr_t)255u);
+    Args a{};
+    fill_args(d, tables, &a);
+    a.nitems = p.nitems;
+    a.need_gin = gin != nullptr;
+    a.tmem_cols = p.tmem_cols;
+    a.u = u; a.gout = gout; a.chan = chan; a.skipw = skipw; a.gin = gin;
+    a.ckpt = const_cast<float *>(reinterpret_cast<const float *>((reinterpret_cast<uintptr_t>(ckpt) + 255u) & ~(uintptr_t)255u));
+    a.scratch = ws;
+    a.part_maps = ws + w.scratch_floats;
+    a.part_chan = a.part_maps + w.maps_floats;
+    a.part_skip = a.part_chan + w.chan_floats;
+    const void *kern = bwd_kernel_for(d.N, p.P, d.chan_op != 0);
+    void *params[] = {&a};
+    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(p.grid), dim3(p.threads), params, p.smem_bwd, st));
+    rc = cuda_last_error();
+    if (rc) return rc;
+    launch_finish(d, w.nsets_maps, w.nsets_small, a.part_maps, a.part_chan, a.part_skip, skipw, g_ab, g_atc, g_bb, g_btc,
+                  g_chan, g_skip, st);
+    return cuda_last_error();
+}
+
+}  // namespace split
+}  // namespace adi
+}  // namespace pde

@@ -83,12 +83,18 @@ class _AdiFunction(torch.autograd.Function):
             _cabi.check(L.pde_adi_prepare(byref(d), byref(sched), *[_ptr(p) for p in maps], _ptr(tables), _stream()),
                         "pde_adi_prepare")
             out = torch.empty_like(u)
-            _cabi.check(L.pde_adi_forward(byref(d), _ptr(tables), _ptr(u), _ptr(chan_c), _ptr(skip_c), _ptr(out),
-                                          _stream()), "pde_adi_forward")
+            # under autograd the forward kernel also writes the state at the end of every step for
+            # the backward kernel (0 bytes when the configuration is served by the kernels that
+            # rebuild the trajectory on-chip)
+            ck_bytes = L.pde_adi_checkpoint_bytes(byref(d)) if any(ctx.needs_input_grad) else 0
+            ckpt = _bytes(ck_bytes, u.device) if ck_bytes else None
+            _cabi.check(L.pde_adi_forward_train(byref(d), _ptr(tables), _ptr(u), _ptr(chan_c), _ptr(skip_c), _ptr(out),
+                                                _ptr(ckpt), _stream()), "pde_adi_forward_train")
         ctx.cfg = cfg
         ctx.has_chan = chan is not None
         ctx.has_skip = skipw is not None
-        ctx.save_for_backward(u, tables, *(t for t in (chan_c, skip_c) if t is not None))
+        ctx.has_ckpt = ckpt is not None
+        ctx.save_for_backward(u, tables, *(t for t in (chan_c, skip_c, ckpt) if t is not None))
         ctx.param_shapes = [p.shape for p in (alpha_base, beta_base, alpha_tc, beta_tc)]
         return out
 
@@ -102,20 +108,22 @@ class _AdiFunction(torch.autograd.Function):
         rest = saved[2:]
         chan = rest.pop(0) if ctx.has_chan else None
         skipw = rest.pop(0) if ctx.has_skip else None
+        ckpt = rest.pop(0) if ctx.has_ckpt else None
         gout = gout.contiguous().float()
         B = u.shape[0]
         d = cfg.desc(B)
         with torch.cuda.device(u.device):
-            ws_bytes = L.pde_adi_backward_workspace_bytes(byref(d))
+            ws_bytes = (L.pde_adi_backward_saved_workspace_bytes if ckpt is not None
+                        else L.pde_adi_backward_workspace_bytes)(byref(d))
             ws = _bytes(ws_bytes, u.device)
             gin = torch.empty_like(u) if ctx.needs_input_grad[0] else None
             gmaps = [torch.empty((cfg.C, cfg.N, cfg.N), dtype=torch.float32, device=u.device) for _ in range(4)]
             gchan = torch.empty((cfg.C, cfg.C), dtype=torch.float32, device=u.device) if chan is not None else None
             gskip = torch.empty((), dtype=torch.float32, device=u.device) if skipw is not None else None
-            _cabi.check(L.pde_adi_backward(byref(d), _ptr(tables), _ptr(u), _ptr(gout), _ptr(chan), _ptr(skipw),
-                                           _ptr(gin), _ptr(gmaps[0]), _ptr(gmaps[1]), _ptr(gmaps[2]), _ptr(gmaps[3]),
-                                           _ptr(gchan), _ptr(gskip), _ptr(ws), ws_bytes, _stream()),
-                        "pde_adi_backward")
+            _cabi.check(L.pde_adi_backward_saved(byref(d), _ptr(tables), _ptr(u), _ptr(gout), _ptr(chan), _ptr(skipw),
+                                                 _ptr(ckpt), _ptr(gin), _ptr(gmaps[0]), _ptr(gmaps[1]), _ptr(gmaps[2]),
+                                                 _ptr(gmaps[3]), _ptr(gchan), _ptr(gskip), _ptr(ws), ws_bytes,
+                                                 _stream()), "pde_adi_backward_saved")
         gmaps = [g.reshape(s) for g, s in zip(gmaps, ctx.param_shapes)]
         return (gin, gmaps[0], gmaps[1], gmaps[2], gmaps[3], gchan, gskip, None)
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PDE_B200_ABI_VERSION 1
+#define PDE_B200_ABI_VERSION 2
 
 #define PDE_OK 0
 #define PDE_ERR_INVALID (-1)      /* NULL pointer, negative size, inconsistent descriptor   */
@@ -88,6 +88,24 @@ int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sched,
 /* u, out: [B][C][N][N].  chan: [C][C] or NULL (chan_op == 0).  skip_weight: 1 value or NULL. */
 int pde_adi_forward(const pde_adi_desc *d, const void *tables, const float *u,
                     const float *chan, const float *skip_weight, float *out, void *stream);
+
+/* Training variants of pde_adi_forward / pde_adi_backward.  autograd keeps what forward computed for backward; here
+ * that is the state at the end of every step ("checkpoints", pde_adi_checkpoint_bytes(d) bytes,
+ * 256-byte aligned, opaque layout), so that the backward kernel does not recompute the forward
+ * trajectory.  pde_adi_checkpoint_bytes returns 0 when the configuration is served by kernels
+ * that rebuild the trajectory on-chip; ckpt may then be NULL.  pde_adi_backward (no ckpt) makes
+ * the checkpoints itself inside its (then batch-sized) workspace. */
+size_t pde_adi_checkpoint_bytes(const pde_adi_desc *d);
+size_t pde_adi_backward_saved_workspace_bytes(const pde_adi_desc *d);
+int pde_adi_forward_train(const pde_adi_desc *d, const void *tables, const float *u,
+                          const float *chan, const float *skip_weight, float *out, void *ckpt,
+                          void *stream);
+int pde_adi_backward_saved(const pde_adi_desc *d, const void *tables, const float *u, const float *gout,
+                           const float *chan, const float *skip_weight, const void *ckpt, float *gin,
+                           float *g_alpha_base, float *g_beta_base,
+                           float *g_alpha_time_coeff, float *g_beta_time_coeff,
+                           float *g_chan, float *g_skip_weight,
+                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* gin may be NULL (the layer is the first op of every reference model, so grad_input is
  * normally not needed).  Gradient outputs are OVERWRITTEN (not accumulated): four maps

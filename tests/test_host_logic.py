@@ -22,7 +22,7 @@ def test_cabi_library_exports_every_declared_symbol():
     lib = P._cabi.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pde_b200_abi_version() == 1
+    assert lib.pde_b200_abi_version() == 2
     assert b"unsupported" in lib.pde_b200_error_string(-2).lower() or b"not supported" in lib.pde_b200_error_string(-2)
 
 
@@ -33,7 +33,8 @@ def test_cabi_host_only_queries():
     cfg = P.AdiConfig(N=28, C=1, steps=4, dt=0.3, hx=1.0, hy=1.0, smooth=True)
     d = cfg.desc(256)
     n = lib.pde_adi_tables_bytes(ctypes.byref(d))
-    assert n == 4096 + 4 * (12 * 1 * 28 * 28) * 4
+    # header + the tables of both implementations (28 cells / line; 2 halves x 16 padded cells / line)
+    assert n == 4096 + 4 * (12 * 1 * 28 * 28) * 4 + 4 * (12 * 1 * 28 * 32) * 4
     bad = P.AdiConfig(N=30, C=1, steps=4, dt=0.3, hx=1.0, hy=1.0).desc(1)     # size not built
     assert lib.pde_adi_tables_bytes(ctypes.byref(bad)) == 0
     # struct layouts must match the header

@@ -146,16 +146,22 @@ __device__ __forceinline__ f2 shfl_xor_f2(f2 a, int m) {
 
 struct Lane {
     int c, wi, pp, h, R, tid_c;
+    int b0, b1;   // float offsets of the thread's half row / half column inside a tile
+    int tab;      // float4 offset of its coefficients inside the tables of one sweep
     bool active;
 };
 
 // AX == 0: the thread's half row (row R, half h); AX == 1: its half column (column R, rows of half h)
 template <int N, int P, int AX>
-__device__ __forceinline__ int half_base(const Lane &t) {
+__device__ __forceinline__ int half_base_of(int R, int h, int pp) {
     using G = SG<N, P>;
-    if (AX == 0) return row_off<N, P>(t.R) + (t.h * G::HS * P + t.pp) * 4;
-    const int hc = t.R >= G::H ? 1 : 0, kc = t.R - hc * G::H;
-    return t.h * (G::H * G::RS + G::HPAD) + ((hc * G::HS + (kc >> 1)) * P + t.pp) * 4 + (kc & 1) * 2;
+    if (AX == 0) return row_off<N, P>(R) + (h * G::HS * P + pp) * 4;
+    const int hc = R >= G::H ? 1 : 0, kc = R - hc * G::H;
+    return h * (G::H * G::RS + G::HPAD) + ((hc * G::HS + (kc >> 1)) * P + pp) * 4 + (kc & 1) * 2;
+}
+template <int N, int P, int AX>
+__device__ __forceinline__ int half_base(const Lane &t) {
+    return AX == 0 ? t.b0 : t.b1;
 }
 
 template <int N, int P, int AX>
@@ -299,8 +305,8 @@ __device__ __forceinline__ void ld_coef(const float4 *__restrict__ p, float (&v)
 
 // x[k] = sum_d mat[d * mstride] * (half row of channel d)
 template <int N, int P>
-__device__ __forceinline__ void mix_rows(const float *tiles, int C, const float *__restrict__ mat, int mstride,
-                                         const Lane &t, f2 (&x)[N / 2]) {
+__device__ __forceinline__ void mix_rows(const float *tiles, int cstride, int C, const float *__restrict__ mat,
+                                         int mstride, const Lane &t, f2 (&x)[N / 2]) {
     using G = SG<N, P>;
     const f2 zero = f2_bc(0.0f);
 #pragma unroll
@@ -308,7 +314,7 @@ __device__ __forceinline__ void mix_rows(const float *tiles, int C, const float 
     for (int dd = 0; dd < C; ++dd) {
         const float m = __ldg(mat + dd * mstride);
         f2 row[G::H];
-        ld_half<N, P, 0>(tiles + (size_t)dd * G::TILE, t, row);
+        ld_half<N, P, 0>(tiles + (size_t)dd * cstride, t, row);
 #pragma unroll
         for (int k = 0; k < G::H; ++k) x[k] = f2_fmas(m, row[k], x[k]);
     }
@@ -321,23 +327,29 @@ __device__ __forceinline__ void mix_rows(const float *tiles, int C, const float 
 //   the near half's last cell:          x = d*_{H-1} + e_{H-1} (that x)
 //   x_k = d*_k + e_k x_{k+1}                               k = H-2 .. 0
 // ------------------------------------------------------------------------------------------
-template <int N, int P>
-__device__ __forceinline__ void solve(f2 (&x)[N / 2], const float4 *__restrict__ tinv, const float4 *__restrict__ te,
-                                      bool far) {
-    using G = SG<N, P>;
-    constexpr int H = G::H;
-    float iv[4 * G::HQ], e[4 * G::HQ];
-    ld_coef<N, P>(tinv, iv);
-    ld_coef<N, P>(te, e);
-    x[0] = f2_muls(iv[0], x[0]);
+template <int N, int P, int NP>
+__device__ __forceinline__ void solve(f2 (&x)[NP][N / 2], const float (&iv)[4 * SG<N, P>::HQ],
+                                      const float (&e)[4 * SG<N, P>::HQ], bool far) {
+    constexpr int H = N / 2;
 #pragma unroll
-    for (int k = 1; k < H; ++k) x[k] = f2_fmas(e[k], x[k - 1], f2_muls(iv[k], x[k]));
-    f2 o = shfl_xor_f2(x[H - 1], P);
-    x[H - 1] = f2_fmas(far ? e[H - 1] : 0.0f, o, x[H - 1]);
-    o = shfl_xor_f2(x[H - 1], P);
-    x[H - 1] = f2_fmas(far ? 0.0f : e[H - 1], o, x[H - 1]);
+    for (int p = 0; p < NP; ++p) x[p][0] = f2_muls(iv[0], x[p][0]);
 #pragma unroll
-    for (int k = H - 2; k >= 0; --k) x[k] = f2_fmas(e[k], x[k + 1], x[k]);
+    for (int k = 1; k < H; ++k)
+#pragma unroll
+        for (int p = 0; p < NP; ++p) x[p][k] = f2_fmas(e[k], x[p][k - 1], f2_muls(iv[k], x[p][k]));
+    f2 o[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) o[p] = shfl_xor_f2(x[p][H - 1], P);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) x[p][H - 1] = f2_fmas(far ? e[H - 1] : 0.0f, o[p], x[p][H - 1]);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) o[p] = shfl_xor_f2(x[p][H - 1], P);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) x[p][H - 1] = f2_fmas(far ? 0.0f : e[H - 1], o[p], x[p][H - 1]);
+#pragma unroll
+    for (int k = H - 2; k >= 0; --k)
+#pragma unroll
+        for (int p = 0; p < NP; ++p) x[p][k] = f2_fmas(e[k], x[p][k + 1], x[p][k]);
 }
 
 // L2 prefetch of a contiguous region by one thread (TMA bulk prefetch: no registers, no smem)
@@ -363,6 +375,9 @@ __device__ __forceinline__ Lane make_lane() {
     t.active = line < N;
     t.R = t.active ? line : N - 1;
     t.tid_c = threadIdx.x - t.c * G::WPC * 32;
+    t.b0 = half_base_of<N, P, 0>(t.R, t.h, t.pp);
+    t.b1 = half_base_of<N, P, 1>(t.R, t.h, t.pp);
+    t.tab = (t.c * G::HQ * N + t.R) * 2 + t.h;
     return t;
 }
 
@@ -370,25 +385,33 @@ __device__ __forceinline__ Lane make_lane() {
 template <int N, int P>
 __device__ __forceinline__ size_t tab_off(int s, int C, const Lane &t) {
     using G = SG<N, P>;
-    return ((((size_t)s * C + t.c) * G::HQ) * N + t.R) * 2 + t.h;
+    return (size_t)(s * (C * G::HQ * N * 2) + t.tab);
 }
 
+// P == 4 serves the single-channel layers (one channel per block), P == 2 up to three channels
 template <int N, int P>
-constexpr int fwd_max_threads() { return P >= 4 ? SG<N, P>::WPC * 32 : SG<N, P>::WPC * 32 * PDE_MAX_CHANNELS; }
+constexpr int max_threads() { return P >= 4 ? SG<N, P>::WPC * 32 : SG<N, P>::WPC * 32 * 3; }
+// P == 4: two blocks of 7-8 warps per SM.  The register file is split over the four schedulers
+// (16 K registers each) and a block's warps are dealt round-robin, so two blocks put four warps on a
+// scheduler: 128 registers per thread, not 65536 / threads.
 
 // ------------------------------------------------------------------------------------------
-// forward
+// forward.  A block owns Q groups of P sample pairs (all channels).  Every sweep is one PHASE: the
+// thread loads its coefficients once and applies them to its half line of the Q groups in turn
+// (the state lives in the tiles between phases), so the coefficient traffic is amortised over Q.
+// The closing half sweep of a Strang step and the opening one of the next run back to back on
+// the registers (same orientation).
 // ------------------------------------------------------------------------------------------
-template <int N, int P>
-__global__ void __launch_bounds__(fwd_max_threads<N, P>(), P >= 4 ? 3 : 1) sfwd_kernel(const Args a) {
+template <int N, int P, int Q>
+__global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kernel(const Args a) {
     using G = SG<N, P>;
-    constexpr int H = G::H, TILE = G::TILE;
+    constexpr int H = G::H, TILE = G::TILE, HQ4 = 4 * G::HQ;
     extern __shared__ __align__(16) float smem[];
     const pde_adi_desc &d = a.d;
     const Lane t = make_lane<N, P>();
-    const int C = d.C, nthr = blockDim.x, nthr_c = G::WPC * 32;
+    const int C = d.C, nthr = blockDim.x;
     const bool far = t.h == 1;
-    float *my = smem + (size_t)t.c * TILE;
+    float *my = smem + (size_t)t.c * Q * TILE;   // this channel's Q tiles
     const size_t T = stab_floats_per_table(d);
     const float4 *tinv = reinterpret_cast<const float4 *>(a.stab + T);
     const float4 *te = reinterpret_cast<const float4 *>(a.stab + 2 * T);
@@ -396,72 +419,90 @@ __global__ void __launch_bounds__(fwd_max_threads<N, P>(), P >= 4 ? 3 : 1) sfwd_
     if (d.skip) sig = 1.0f / (1.0f + expf(-__ldg(a.skipw)));
     const float om = 1.0f - sig;
     const size_t plane = (size_t)N * N;
-    const size_t ck_slot = (size_t)H * nthr;   // f2 per (item, step)
-    const int last_ax = a.sps == 3 ? 0 : 1;
+    const size_t ck_slot = (size_t)H * nthr;   // f2 per (group, step)
+    const int sps = a.sps, S = a.S;
+    __shared__ short h_slot[PDE_MAX_SWEEPS];
+    {
+        const Header *hdr = reinterpret_cast<const Header *>(a.tables);
+        for (int i = threadIdx.x; i < S; i += nthr) h_slot[i] = hdr->slot[i];
+    }
+    __syncthreads();
 
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         if (threadIdx.x == 0) {   // the next item's planes start their trip from HBM to L2 now
-            const long long nb = (long long)(item + gridDim.x) * 2 * P;
+            const long long nb = (long long)(item + gridDim.x) * Q * 2 * P;
             if (nb < d.B) {
-                const long long ns = (d.B - nb) < 2 * P ? (d.B - nb) : 2 * P;
+                const long long ns = (d.B - nb) < 2 * P * Q ? (d.B - nb) : 2 * P * Q;
                 prefetch_region_l2(a.u + (size_t)nb * C * plane, (size_t)ns * C * plane * sizeof(float));
             }
         }
-        planes_to_tile<N, P>(a.u, my, item, t.c, C, d.B, t.tid_c, nthr_c);
-        __syncthreads();
-        f2 x[H];
-        bool in_regs = false;   // x holds the state as rows
-        for (int step = 0; step < d.steps; ++step) {
-            const int s0 = step * a.sps;
-            if (d.chan_op == 1) {
-                if (in_regs) {
-                    if (t.active) st_half<N, P, 0>(my, t, x);
-                    __syncthreads();
-                }
-                mix_rows<N, P>(smem, C, a.chan + t.c * C, 1, t, x);
-                __syncthreads();
-            } else if (!in_regs) {
-                ld_half<N, P, 0>(my, t, x);
-            }
-            solve<N, P>(x, tinv + tab_off<N, P>(s0, C, t), te + tab_off<N, P>(s0, C, t), far);
-            if (t.active) st_half<N, P, 0>(my, t, x);
+#pragma unroll 1
+        for (int q = 0; q < Q; ++q) PlaneIO<N, P>::to_tile(a.u, my + q * TILE, item * Q + q, t.c, C, d.B, t.tid_c);
+        int cur_ax = 2;   // orientation of the last phase (2: block-wide pattern)
+        // u <- M u over the channels of every group (rows); leaves the tiles in row orientation
+        auto mix_phase = [&]() {
             __syncthreads();
-            ld_half<N, P, 1>(my, t, x);
-            solve<N, P>(x, tinv + tab_off<N, P>(s0 + 1, C, t), te + tab_off<N, P>(s0 + 1, C, t), far);
-            if (a.sps == 3) {
-                if (t.active) st_half<N, P, 1>(my, t, x);
+#pragma unroll 1
+            for (int q = 0; q < Q; ++q) {
+                f2 x[H];
+                mix_rows<N, P>(smem + q * TILE, Q * TILE, C, a.chan + t.c * C, 1, t, x);
                 __syncthreads();
-                ld_half<N, P, 0>(my, t, x);
-                solve<N, P>(x, tinv + tab_off<N, P>(s0 + 2, C, t), te + tab_off<N, P>(s0 + 2, C, t), far);
-                in_regs = true;
+                if (t.active) st_half<N, P, 0>(my + q * TILE, t, x);
             }
-            if (a.ckpt) {   // state after the last sweep of the step, in the orientation it is in
-                unsigned long long *ck = reinterpret_cast<unsigned long long *>(a.ckpt) +
-                                         ((size_t)item * d.steps + step) * ck_slot + threadIdx.x;
+            cur_ax = 0;
+        };
+        int s = 0;
+        while (s < S) {
+            const int k = s % sps, step = s / sps, ax = sweep_axis(k);
+            if (k == 0 && d.chan_op == 1) mix_phase();
+            // the next sweep has the same orientation and (Strang: same time, time step, spacing) the same tables
+            const bool fuse = sps == 3 && k == 2 && s + 1 < S && d.chan_op == 0 && h_slot[s] == h_slot[s + 1];
+            float iv[HQ4], e[HQ4];
+            ld_coef<N, P>(tinv + tab_off<N, P>(s, C, t), iv);
+            ld_coef<N, P>(te + tab_off<N, P>(s, C, t), e);
+            if (cur_ax != ax) {
+                __syncthreads();
+                cur_ax = ax;
+            }
+            constexpr int NP = 1;   // groups advanced together (2 measured slower: 128 registers, spills)
+#pragma unroll 1
+            for (int q = 0; q < Q; q += NP) {
+                float *tile = my + q * TILE;
+                f2 x[NP][H];
 #pragma unroll
-                for (int k = 0; k < H; ++k) __stcs(ck + (size_t)k * nthr, x[k].v);
-            }
-            if (a.sps != 3) {   // Lie: the state sits in registers as columns
-                if (t.active) st_half<N, P, 1>(my, t, x);
-                __syncthreads();
-                in_regs = false;
-            }
-            if (d.chan_op == 2) {
-                if (in_regs) {
-                    if (t.active) st_half<N, P, 0>(my, t, x);
-                    __syncthreads();
+                for (int p = 0; p < NP; ++p) {
+                    if (ax == 0) ld_half<N, P, 0>(tile + p * TILE, t, x[p]);
+                    else ld_half<N, P, 1>(tile + p * TILE, t, x[p]);
                 }
-                mix_rows<N, P>(smem, C, a.chan + t.c * C, 1, t, x);
-                __syncthreads();
-                in_regs = true;
+                solve<N, P, NP>(x, iv, e, far);
+                if (k == sps - 1 && a.ckpt) {   // state after the last sweep of the step
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        unsigned long long *ck = reinterpret_cast<unsigned long long *>(a.ckpt) +
+                                                 ((size_t)(item * Q + q + p) * d.steps + step) * ck_slot + threadIdx.x;
+#pragma unroll
+                        for (int kk = 0; kk < H; ++kk) __stcs(ck + (size_t)kk * nthr, x[p][kk].v);
+                    }
+                }
+                if (fuse) solve<N, P, NP>(x, iv, e, far);
+                if (t.active) {
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        if (ax == 0) st_half<N, P, 0>(tile + p * TILE, t, x[p]);
+                        else st_half<N, P, 1>(tile + p * TILE, t, x[p]);
+                    }
+                }
             }
+            if (k == sps - 1 && d.chan_op == 2) mix_phase();
+            s += fuse ? 2 : 1;
         }
-        if (in_regs) {
-            if (t.active) st_half<N, P, 0>(my, t, x);
-            __syncthreads();
+        __syncthreads();
+        if (a.out) {
+#pragma unroll 1
+            for (int q = 0; q < Q; ++q)
+                PlaneIO<N, P>::from_tile(my + q * TILE, a.out, item * Q + q, t.c, C, d.B, t.tid_c, d.skip ? a.u : nullptr,
+                                         sig, om);
         }
-        (void)last_ax;
-        if (a.out) tile_to_planes<N, P>(my, a.out, item, t.c, C, d.B, t.tid_c, nthr_c, d.skip ? a.u : nullptr, sig, om);
         __syncthreads();
     }
 }
@@ -487,32 +528,59 @@ __device__ __forceinline__ void tmem_accumulate16(uint32_t tacc, const float (&z
     tmem_st16(tacc + 16, a1);
 }
 
-// One reversed sweep for the thread's half line (orientation AX).
-//   g : adjoint of the sweep output -> adjoint of the sweep input, in registers
+// Two adjacent cells (2m, 2m+1) of the thread's half line, straight from / to a tile.
+template <int N, int P, int AX>
+__device__ __forceinline__ void ld_duo(const float *tile, const Lane &t, int m, f2 &lo, f2 &hi) {
+    using G = SG<N, P>;
+    if (AX == 0) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(tile + t.b0 + m * P * 4);
+        lo.v = v.x;
+        hi.v = v.y;
+    } else {
+        lo.v = *reinterpret_cast<const unsigned long long *>(tile + t.b1 + (2 * m) * G::RS);
+        hi.v = *reinterpret_cast<const unsigned long long *>(tile + t.b1 + (2 * m + 1) * G::RS);
+    }
+}
+template <int N, int P, int AX>
+__device__ __forceinline__ void st_duo(float *tile, const Lane &t, int m, f2 lo, f2 hi) {
+    using G = SG<N, P>;
+    if (AX == 0) {
+        ulonglong2 v;
+        v.x = lo.v;
+        v.y = hi.v;
+        *reinterpret_cast<ulonglong2 *>(tile + t.b0 + m * P * 4) = v;
+    } else {
+        *reinterpret_cast<unsigned long long *>(tile + t.b1 + (2 * m) * G::RS) = lo.v;
+        *reinterpret_cast<unsigned long long *>(tile + t.b1 + (2 * m + 1) * G::RS) = hi.v;
+    }
+}
+
+// One reversed sweep for the thread's half line of ONE group (orientation AX); the coefficients
+// are in registers and serve all groups of the block.
+//   gt: tile with the adjoint of the sweep output -> adjoint of the sweep input
 //       w_k = g_k + e_{k-1} w_{k-1};  the far half's closing cell also takes e w of the near half's last cell
 //       lambda_{H-1} = inv w (far) | inv (w + r lambda of the closing cell) (near)
 //       lambda_k = inv_k (w_k + r_{k+1} lambda_{k+1})
-//   xt: tile holding the sweep OUTPUT; (L x)_k, v_k = lambda_k (L x)_k summed over the two samples,
-//       and (if `rebuild`) the sweep INPUT x_in = (1 + eps) x - r (L x) written back in place.
-//   v -> smoothing^T -> clamp mask -> TMEM accumulators of this sweep's kind.
+//   xt: tile with the sweep OUTPUT -> (if rebuilt) the sweep INPUT x_in = (1 + eps) x - r (L x);
+//       the state is streamed through a window of two cell pairs, results leave as soon as they exist
+//   vacc_k += lambda_k (L x)_k summed over the two samples
 template <int N, int P, int AX>
-__device__ __forceinline__ void reverse_sweep(f2 (&g)[N / 2], float *xt, const Lane &t, uint32_t tacc,
-                                              const float4 *tr, const float4 *tinv, const float4 *te, const float4 *tm,
-                                              float scale, float tt, float onepe, bool smooth, bool rebuild,
-                                              bool clamped) {
+__device__ __forceinline__ void reverse_core(float *gt, float *xt, const Lane &t, float (&vacc)[16],
+                                             const float (&r)[4 * SG<N, P>::HQ], const float (&iv)[4 * SG<N, P>::HQ],
+                                             float onepe, bool far, bool rebuild) {
     using G = SG<N, P>;
-    constexpr int H = G::H;
-    const bool far = t.h == 1;
-    float r[4 * G::HQ], iv[4 * G::HQ], e[4 * G::HQ];
-    ld_coef<N, P>(te, e);
-    ld_coef<N, P>(tinv, iv);
-    ld_coef<N, P>(tr, r);
-    f2 x[H];
-    ld_half<N, P, AX>(xt, t, x);
+    constexpr int H = N / 2, HCH = G::HCH;
+    f2 g[H];
+    ld_half<N, P, AX>(gt, t, g);
+    f2 c_lo, c_hi, n_lo, n_hi;
+    ld_duo<N, P, AX>(xt, t, HCH - 1, c_lo, c_hi);
+    if (HCH >= 2) ld_duo<N, P, AX>(xt, t, HCH - 2, n_lo, n_hi);
+    // e_k = r_k / pivot_k is rebuilt as r_k * inv_k (scalar, off the dependent chain) instead of
+    // being loaded: a third less coefficient traffic and 16 registers less
 #pragma unroll
-    for (int k = 1; k < H; ++k) g[k] = f2_fmas(e[k - 1], g[k - 1], g[k]);
+    for (int k = 1; k < H; ++k) g[k] = f2_fmas(r[k - 1] * iv[k - 1], g[k - 1], g[k]);
     {
-        const f2 z = shfl_xor_f2(f2_muls(e[H - 1], g[H - 1]), P);
+        const f2 z = shfl_xor_f2(f2_muls(r[H - 1] * iv[H - 1], g[H - 1]), P);
         g[H - 1] = f2_fmas(far ? 1.0f : 0.0f, z, g[H - 1]);
     }
     f2 lam = f2_muls(iv[H - 1], g[H - 1]);
@@ -520,21 +588,38 @@ __device__ __forceinline__ void reverse_sweep(f2 (&g)[N / 2], float *xt, const L
         const f2 z = shfl_xor_f2(f2_muls(r[H - 1], lam), P);
         lam = f2_fmas(far ? 0.0f : iv[H - 1], z, lam);
     }
-    f2 xnext = shfl_xor_f2(x[H - 1], P);   // the cell across the junction (sweep output)
-    float v[16];
+    f2 xnext = shfl_xor_f2(c_hi, P);   // the cell across the junction (sweep output)
+    const bool wr = rebuild && t.active;
 #pragma unroll
-    for (int k = H; k < 16; ++k) v[k] = 0.0f;
-#pragma unroll
-    for (int k = H - 1; k >= 0; --k) {
-        if (k < H - 1) lam = f2_fmas(r[k + 1] * iv[k], g[k + 1], f2_muls(iv[k], g[k]));
-        g[k] = lam;
-        const f2 cur = x[k];
-        const f2 lx = (k == 0) ? f2_sub(xnext, cur) : f2_fmas(-2.0f, cur, f2_add(x[k - 1], xnext));
-        v[k] = f2_hsum(f2_mul(lam, lx));
-        x[k] = f2_fmas(-r[k], lx, f2_muls(onepe, cur));
-        xnext = cur;
+    for (int m = HCH - 1; m >= 0; --m) {
+        const int k1 = 2 * m + 1, k0 = 2 * m;
+        // cell k1
+        if (k1 < H - 1) lam = f2_fmas(r[k1 + 1] * iv[k1], lam, f2_muls(iv[k1], g[k1]));
+        const f2 lam1 = lam;
+        f2 lx = f2_fmas(-2.0f, c_hi, f2_add(c_lo, xnext));
+        vacc[k1] += f2_hsum(f2_mul(lam, lx));
+        const f2 o_hi = f2_fmas(-r[k1], lx, f2_muls(onepe, c_hi));
+        xnext = c_hi;
+        // cell k0
+        lam = f2_fmas(r[k0 + 1] * iv[k0], lam, f2_muls(iv[k0], g[k0]));
+        lx = (m == 0) ? f2_sub(xnext, c_lo) : f2_fmas(-2.0f, c_lo, f2_add(n_hi, xnext));
+        vacc[k0] += f2_hsum(f2_mul(lam, lx));
+        const f2 o_lo = f2_fmas(-r[k0], lx, f2_muls(onepe, c_lo));
+        xnext = c_lo;
+        if (t.active) st_duo<N, P, AX>(gt, t, m, lam, lam1);
+        if (wr) st_duo<N, P, AX>(xt, t, m, o_lo, o_hi);
+        c_lo = n_lo;
+        c_hi = n_hi;
+        if (m >= 2) ld_duo<N, P, AX>(xt, t, m - 2, n_lo, n_hi);
     }
-    if (rebuild && t.active) st_half<N, P, AX>(xt, t, x);
+}
+
+// v (summed over the block's groups) -> smoothing^T -> clamp mask -> TMEM accumulators
+template <int N, int P>
+__device__ __forceinline__ void reverse_finish(float (&v)[16], uint32_t tacc, const float4 *tm, float scale, float tt,
+                                               bool smooth, bool clamped) {
+    using G = SG<N, P>;
+    constexpr int H = G::H;
     if (smooth) {
         const float k3 = scale * (1.0f / 3.0f);
         const float vj = __shfl_xor_sync(kFullMask, v[H - 1], P);
@@ -559,19 +644,21 @@ __device__ __forceinline__ void reverse_sweep(f2 (&g)[N / 2], float *xt, const L
     tmem_accumulate16(tacc, v, tt);
 }
 
-// Adjoint of a channel op.  On entry (after a barrier) the g tiles hold the adjoint of the op's
-// output as rows, the x tiles the op's INPUT:  gm[dd] += sum g_c x_dd ;  g_c <- sum_c' mat[c'][c] g_c'.
+// Adjoint of a channel op on one group.  On entry (after a barrier) the g tiles hold the adjoint of
+// the op's output as rows, the x tiles the op's INPUT:
+//   gm[dd] += sum g_c x_dd ;  g_c <- sum_c' mat[c'][c] g_c'.
 template <int N, int P>
-__device__ __forceinline__ void chan_adjoint(float *ggt, const float *gxt, int C, const float *__restrict__ mat,
-                                             const Lane &t, float (&gm)[PDE_MAX_CHANNELS]) {
+__device__ __forceinline__ void chan_adjoint(float *ggt, const float *gxt, int cstride, int C,
+                                             const float *__restrict__ mat, const Lane &t,
+                                             float (&gm)[PDE_MAX_CHANNELS]) {
     using G = SG<N, P>;
     constexpr int H = G::H;
     {
         f2 g[H];
-        ld_half<N, P, 0>(ggt + (size_t)t.c * G::TILE, t, g);
+        ld_half<N, P, 0>(ggt + (size_t)t.c * cstride, t, g);
         for (int dd = 0; dd < C; ++dd) {
             f2 x[H];
-            ld_half<N, P, 0>(gxt + (size_t)dd * G::TILE, t, x);
+            ld_half<N, P, 0>(gxt + (size_t)dd * cstride, t, x);
             f2 acc = f2_bc(0.0f);
 #pragma unroll
             for (int k = 0; k < H; ++k) acc = f2_fma(g[k], x[k], acc);
@@ -579,18 +666,15 @@ __device__ __forceinline__ void chan_adjoint(float *ggt, const float *gxt, int C
         }
     }
     f2 gn[H];
-    mix_rows<N, P>(ggt, C, mat + t.c, C, t, gn);
+    mix_rows<N, P>(ggt, cstride, C, mat + t.c, C, t, gn);
     __syncthreads();
-    if (t.active) st_half<N, P, 0>(ggt + (size_t)t.c * G::TILE, t, gn);
+    if (t.active) st_half<N, P, 0>(ggt + (size_t)t.c * cstride, t, gn);
 }
 
-template <int N, int P>
-constexpr int bwd_max_threads() { return P >= 4 ? SG<N, P>::WPC * 32 : SG<N, P>::WPC * 32 * PDE_MAX_CHANNELS; }
-
-template <int N, int P, bool CHAN>
-__global__ void __launch_bounds__(bwd_max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kernel(const Args a) {
+template <int N, int P, int Q, bool CHAN>
+__global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kernel(const Args a) {
     using G = SG<N, P>;
-    constexpr int H = G::H, TILE = G::TILE;
+    constexpr int H = G::H, TILE = G::TILE, HQ4 = 4 * G::HQ;
     extern __shared__ __align__(16) float smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ float h_scale[PDE_MAX_SWEEPS], h_t[PDE_MAX_SWEEPS];
@@ -598,9 +682,11 @@ __global__ void __launch_bounds__(bwd_max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_
     const pde_adi_desc &d = a.d;
     const Lane t = make_lane<N, P>();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int C = d.C, nthr = blockDim.x, nthr_c = G::WPC * 32;
-    float *gxt = smem, *ggt = smem + (size_t)C * TILE;
-    float *xt = gxt + (size_t)t.c * TILE, *gt = ggt + (size_t)t.c * TILE;
+    const int C = d.C, nthr = blockDim.x;
+    const bool far = t.h == 1;
+    constexpr int CS = Q * TILE;   // channel stride
+    float *gxt = smem, *ggt = smem + (size_t)C * CS;
+    float *xt = gxt + (size_t)t.c * CS, *gt = ggt + (size_t)t.c * CS;   // this channel's Q tiles
 
     if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)a.tmem_cols);
     const Header *hdr = reinterpret_cast<const Header *>(a.tables);
@@ -638,28 +724,28 @@ __global__ void __launch_bounds__(bwd_max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_
     float gw = 0.0f;
     const int sps = a.sps;
     const int last_ax = (sps == 3) ? 0 : 1;
-    // exact mode: outputs of the first sps-1 sweeps of the step being reversed, per block
+    // exact mode: outputs of the first sps-1 sweeps of the step being reversed, per block and group
     unsigned long long *sweep_scr =
-        reinterpret_cast<unsigned long long *>(a.scratch) + (size_t)blockIdx.x * 2 * ck_slot + threadIdx.x;
+        reinterpret_cast<unsigned long long *>(a.scratch) + (size_t)blockIdx.x * Q * 2 * ck_slot + threadIdx.x;
 
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         const unsigned long long *ck_item =
-            reinterpret_cast<const unsigned long long *>(a.ckpt) + (size_t)item * d.steps * ck_slot + threadIdx.x;
+            reinterpret_cast<const unsigned long long *>(a.ckpt) + (size_t)item * Q * d.steps * ck_slot + threadIdx.x;
         if (threadIdx.x == 0) {   // next item: checkpoints and planes on their way to L2
             const long long ni = (long long)item + gridDim.x;
-            const long long nb = ni * 2 * P;
+            const long long nb = ni * Q * 2 * P;
             if (nb < d.B) {
-                const long long ns = (d.B - nb) < 2 * P ? (d.B - nb) : 2 * P;
+                const long long ns = (d.B - nb) < 2 * P * Q ? (d.B - nb) : 2 * P * Q;
                 prefetch_region_l2(a.gout + (size_t)nb * C * plane, (size_t)ns * C * plane * sizeof(float));
-                prefetch_region_l2(reinterpret_cast<const unsigned long long *>(a.ckpt) + (size_t)ni * d.steps * ck_slot,
-                                   (size_t)d.steps * ck_slot * 8);
+                prefetch_region_l2(reinterpret_cast<const unsigned long long *>(a.ckpt) + (size_t)ni * Q * d.steps * ck_slot,
+                                   (size_t)((ns + 2 * P - 1) / (2 * P)) * d.steps * ck_slot * 8);
                 if (d.skip || d.chan_op == 1 || exact)
                     prefetch_region_l2(a.u + (size_t)nb * C * plane, (size_t)ns * C * plane * sizeof(float));
             }
         }
-        // Which orientation last touched a tile, and whether a barrier has passed since: a thread only
-        // reads and writes its own half line within one orientation, so a barrier is needed exactly
-        // when the orientation changes (2 = block-wide access pattern).
+        // Which orientation last touched the tiles, and whether a barrier has passed since: a thread
+        // only reads and writes its own half line within one orientation, so a barrier is needed
+        // exactly when the orientation changes (2 = block-wide access pattern).
         int x_last = 2, g_last = 2;
         bool x_sync = true, g_sync = true;
         auto bar = [&]() {
@@ -677,168 +763,161 @@ __global__ void __launch_bounds__(bwd_max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_
             g_last = o;
             g_sync = false;
         };
-        auto ck_load = [&](int step, f2 (&x)[H]) {
-#pragma unroll
-            for (int k = 0; k < H; ++k) x[k].v = __ldcs(ck_item + ((size_t)step * H + k) * nthr);
-        };
-        // x tile <- state after the last sweep of `step` (step == -1: the layer input)
+        // x tiles <- state after the last sweep of `step` (step == -1: the layer input)
         auto state_to_xt = [&](int step) {
             if (step < 0) {
                 touch_x(2);
-                planes_to_tile<N, P>(a.u, xt, item, t.c, C, d.B, t.tid_c, nthr_c);
+#pragma unroll 1
+                for (int q = 0; q < Q; ++q) PlaneIO<N, P>::to_tile(a.u, xt + q * TILE, item * Q + q, t.c, C, d.B, t.tid_c);
             } else {
-                f2 xs[H];
-                ck_load(step, xs);
                 touch_x(last_ax);
-                if (t.active) {
-                    if (last_ax == 0) st_half<N, P, 0>(xt, t, xs);
-                    else st_half<N, P, 1>(xt, t, xs);
+#pragma unroll 1
+                for (int q = 0; q < Q; ++q) {
+                    f2 xs[H];
+#pragma unroll
+                    for (int k = 0; k < H; ++k)
+                        xs[k].v = __ldcs(ck_item + (((size_t)q * d.steps + step) * H + k) * nthr);
+                    if (t.active) {
+                        if (last_ax == 0) st_half<N, P, 0>(xt + q * TILE, t, xs);
+                        else st_half<N, P, 1>(xt + q * TILE, t, xs);
+                    }
                 }
             }
+        };
+        // x tiles (rows) <- channel op applied to the x tiles
+        auto mix_xt = [&]() {
+            touch_x(2);
+            bar();
+#pragma unroll 1
+            for (int q = 0; q < Q; ++q) {
+                f2 x[H];
+                mix_rows<N, P>(gxt + q * TILE, CS, C, a.chan + t.c * C, 1, t, x);
+                __syncthreads();
+                if (t.active) st_half<N, P, 0>(xt + q * TILE, t, x);
+            }
+            x_last = 0;
+            x_sync = false;
+        };
+        auto adjoint_chan = [&]() {
+            touch_g(2);
+            touch_x(2);
+            bar();
+#pragma unroll 1
+            for (int q = 0; q < Q; ++q) chan_adjoint<N, P>(ggt + q * TILE, gxt + q * TILE, CS, C, a.chan, t, gm);
+            g_last = 0; g_sync = false;
+            x_last = 0; x_sync = false;
         };
 
         touch_g(2);
-        planes_to_tile<N, P>(a.gout, gt, item, t.c, C, d.B, t.tid_c, nthr_c);
+#pragma unroll 1
+        for (int q = 0; q < Q; ++q) PlaneIO<N, P>::to_tile(a.gout, gt + q * TILE, item * Q + q, t.c, C, d.B, t.tid_c);
         if (d.skip) {
             // out = sig u0 + om uF:  dL/dw += sig' * sum gout (u0 - uF),  g <- om * gout
-            f2 uf[H];
             state_to_xt(d.steps - 1);
-            if (d.chan_op == 2) {
-                touch_x(2);
-                bar();
-                mix_rows<N, P>(gxt, C, a.chan + t.c * C, 1, t, uf);
-                x_sync = false;
-            } else {
-                touch_x(0);
-                ld_half<N, P, 0>(xt, t, uf);
-            }
+            if (d.chan_op == 2) mix_xt();
+            touch_x(0);
             touch_g(0);
-            f2 gl[H];
-            ld_half<N, P, 0>(gt, t, gl);
-            if (t.active) {
-                f2 accw = f2_bc(0.0f);
-                const int i = mirror(t.R, N);
-                const float2 zero2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+            for (int q = 0; q < Q; ++q) {
+                f2 uf[H], gl[H];
+                ld_half<N, P, 0>(xt + q * TILE, t, uf);
+                ld_half<N, P, 0>(gt + q * TILE, t, gl);
+                if (t.active) {
+                    f2 accw = f2_bc(0.0f);
+                    const int i = mirror(t.R, N);
+                    const float2 zero2 = make_float2(0.f, 0.f);
+                    const int ba = ((item * Q + q) * P + t.pp) * 2, bb = ba + 1;
 #pragma unroll
-                for (int m = 0; m < G::HCH; ++m) {
-                    // cells k = 2m, 2m+1 of the half row: columns 2m, 2m+1 (near) or N-1-2m, N-2-2m (far)
-                    const int j0 = t.h ? N - 2 - 2 * m : 2 * m;
-                    const int ba = (item * P + t.pp) * 2, bb = ba + 1;
-                    const float2 wa = ba < d.B ? __ldg(reinterpret_cast<const float2 *>(a.u + ((size_t)ba * C + t.c) * plane + (size_t)i * N + j0)) : zero2;
-                    const float2 wb = bb < d.B ? __ldg(reinterpret_cast<const float2 *>(a.u + ((size_t)bb * C + t.c) * plane + (size_t)i * N + j0)) : zero2;
-                    const f2 u0 = t.h ? f2_make(wa.y, wb.y) : f2_make(wa.x, wb.x);
-                    const f2 u1 = t.h ? f2_make(wa.x, wb.x) : f2_make(wa.y, wb.y);
-                    accw = f2_fma(gl[2 * m], f2_sub(u0, uf[2 * m]), accw);
-                    accw = f2_fma(gl[2 * m + 1], f2_sub(u1, uf[2 * m + 1]), accw);
-                    gl[2 * m] = f2_muls(om, gl[2 * m]);
-                    gl[2 * m + 1] = f2_muls(om, gl[2 * m + 1]);
+                    for (int m = 0; m < G::HCH; ++m) {
+                        // cells k = 2m, 2m+1 of the half row: columns 2m, 2m+1 (near) or N-1-2m, N-2-2m (far)
+                        const int j0 = t.h ? N - 2 - 2 * m : 2 * m;
+                        const float2 wa = ba < d.B ? __ldg(reinterpret_cast<const float2 *>(a.u + ((size_t)ba * C + t.c) * plane + (size_t)i * N + j0)) : zero2;
+                        const float2 wb = bb < d.B ? __ldg(reinterpret_cast<const float2 *>(a.u + ((size_t)bb * C + t.c) * plane + (size_t)i * N + j0)) : zero2;
+                        const f2 u0 = t.h ? f2_make(wa.y, wb.y) : f2_make(wa.x, wb.x);
+                        const f2 u1 = t.h ? f2_make(wa.x, wb.x) : f2_make(wa.y, wb.y);
+                        accw = f2_fma(gl[2 * m], f2_sub(u0, uf[2 * m]), accw);
+                        accw = f2_fma(gl[2 * m + 1], f2_sub(u1, uf[2 * m + 1]), accw);
+                        gl[2 * m] = f2_muls(om, gl[2 * m]);
+                        gl[2 * m + 1] = f2_muls(om, gl[2 * m + 1]);
+                    }
+                    st_half<N, P, 0>(gt + q * TILE, t, gl);
+                    gw += f2_hsum(accw);
                 }
-                st_half<N, P, 0>(gt, t, gl);
-                gw += f2_hsum(accw);
             }
         }
 
-        f2 g[H];
-        int g_ax = -1;   // orientation of g in registers (-1: in its tile)
-        auto g_to_tile = [&]() {
-            if (g_ax >= 0) {
-                touch_g(g_ax);
-                if (t.active) {
-                    if (g_ax == 0) st_half<N, P, 0>(gt, t, g);
-                    else st_half<N, P, 1>(gt, t, g);
-                }
-                g_ax = -1;
-            }
-        };
         for (int step = d.steps - 1; step >= 0; --step) {
             if (exact) {
                 // recompute the sweeps of this step from its input, keeping every sweep output
-                f2 x[H];
                 state_to_xt(step - 1);
-                if (CHAN && (d.chan_op == 1 || (d.chan_op == 2 && step > 0))) {
-                    touch_x(2);
-                    bar();
-                    mix_rows<N, P>(gxt, C, a.chan + t.c * C, 1, t, x);
-                    x_sync = false;
-                    bar();   // every thread has read the group's tiles before they are overwritten
-                } else {
-                    touch_x(0);
-                    ld_half<N, P, 0>(xt, t, x);
-                }
+                if (CHAN && (d.chan_op == 1 || (d.chan_op == 2 && step > 0))) mix_xt();
                 for (int k = 0; k + 1 < sps; ++k) {
-                    const int s = step * sps + k;
-                    if (k == 1) {
-                        touch_x(0);
-                        if (t.active) st_half<N, P, 0>(xt, t, x);
-                        touch_x(1);
-                        ld_half<N, P, 1>(xt, t, x);
-                    }
-                    solve<N, P>(x, tab_inv + tab_off<N, P>(s, C, t), tab_e + tab_off<N, P>(s, C, t), t.h == 1);
+                    const int s = step * sps + k, ax = sweep_axis(k);
+                    float iv[HQ4], e[HQ4];
+                    ld_coef<N, P>(tab_inv + tab_off<N, P>(s, C, t), iv);
+                    ld_coef<N, P>(tab_e + tab_off<N, P>(s, C, t), e);
+                    touch_x(ax);
+#pragma unroll 1
+                    for (int q = 0; q < Q; ++q) {
+                        f2 x[1][H];
+                        if (ax == 0) ld_half<N, P, 0>(xt + q * TILE, t, x[0]);
+                        else ld_half<N, P, 1>(xt + q * TILE, t, x[0]);
+                        solve<N, P, 1>(x, iv, e, far);
 #pragma unroll
-                    for (int kk = 0; kk < H; ++kk) __stcg(sweep_scr + ((size_t)k * H + kk) * nthr, x[kk].v);
+                        for (int kk = 0; kk < H; ++kk) __stcg(sweep_scr + (((size_t)q * 2 + k) * H + kk) * nthr, x[0][kk].v);
+                        if (t.active) {
+                            if (ax == 0) st_half<N, P, 0>(xt + q * TILE, t, x[0]);
+                            else st_half<N, P, 1>(xt + q * TILE, t, x[0]);
+                        }
+                    }
                 }
             }
             state_to_xt(step);
-            if (CHAN && d.chan_op == 2) {
-                // adjoint of the post-step coupling: its input is the state after the last sweep
-                g_to_tile();
-                touch_g(2);
-                touch_x(2);
-                bar();
-                chan_adjoint<N, P>(ggt, gxt, C, a.chan, t, gm);
-                g_last = 0; g_sync = false;
-                x_last = 0; x_sync = false;
-            }
+            // adjoint of the post-step coupling: its input is the state after the last sweep
+            if (CHAN && d.chan_op == 2) adjoint_chan();
             for (int k = sps - 1; k >= 0; --k) {
                 const int s = step * sps + k, ax = sweep_axis(k);
-                if (exact && k != sps - 1) {
-                    f2 xs[H];
-#pragma unroll
-                    for (int kk = 0; kk < H; ++kk) xs[kk].v = __ldcg(sweep_scr + ((size_t)k * H + kk) * nthr);
-                    touch_x(ax);
-                    if (t.active) {
-                        if (ax == 0) st_half<N, P, 0>(xt, t, xs);
-                        else st_half<N, P, 1>(xt, t, xs);
-                    }
-                }
-                if (g_ax != ax) {
-                    g_to_tile();
-                    touch_g(ax);
-                    touch_x(ax);
-                    if (ax == 0) ld_half<N, P, 0>(gt, t, g);
-                    else ld_half<N, P, 1>(gt, t, g);
-                    g_ax = ax;
-                } else {
-                    touch_x(ax);
-                }
                 const size_t o = tab_off<N, P>(s, C, t);
-                const float scale = h_scale[s], tt = h_t[s];
-                const bool clamped = h_clamped[s] != 0;
+                float r[HQ4], iv[HQ4];
+                ld_coef<N, P>(tab_r + o, r);
+                ld_coef<N, P>(tab_inv + o, iv);
                 const bool rebuild = !exact && k > 0;
-                if (ax == 0)
-                    reverse_sweep<N, P, 0>(g, xt, t, tbase, tab_r + o, tab_inv + o, tab_e + o, tab_m + o, scale, tt, onepe,
-                                           smooth, rebuild, clamped);
-                else
-                    reverse_sweep<N, P, 1>(g, xt, t, tbase + 32u, tab_r + o, tab_inv + o, tab_e + o, tab_m + o, scale, tt,
-                                           onepe, smooth, rebuild, clamped);
+                const bool reload = exact && k != sps - 1;
+                touch_g(ax);
+                touch_x(ax);
+                float vacc[16];
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) vacc[kk] = 0.0f;
+#pragma unroll 1
+                for (int q = 0; q < Q; ++q) {
+                    if (reload) {   // exact mode: this sweep's output comes back from the block's scratch
+                        f2 x[H];
+#pragma unroll
+                        for (int kk = 0; kk < H; ++kk) x[kk].v = __ldcg(sweep_scr + (((size_t)q * 2 + k) * H + kk) * nthr);
+                        if (t.active) {
+                            if (ax == 0) st_half<N, P, 0>(xt + q * TILE, t, x);
+                            else st_half<N, P, 1>(xt + q * TILE, t, x);
+                        }
+                    }
+                    if (ax == 0) reverse_core<N, P, 0>(gt + q * TILE, xt + q * TILE, t, vacc, r, iv, onepe, far, rebuild);
+                    else reverse_core<N, P, 1>(gt + q * TILE, xt + q * TILE, t, vacc, r, iv, onepe, far, rebuild);
+                }
+                reverse_finish<N, P>(vacc, tbase + (ax ? 32u : 0u), tab_m + o, h_scale[s], h_t[s], smooth, h_clamped[s] != 0);
             }
             if (CHAN && d.chan_op == 1) {
                 // adjoint of the pre-step mix: needs g (rows) and the mix INPUT = state before this step
-                g_to_tile();
                 state_to_xt(step - 1);
-                touch_g(2);
-                touch_x(2);
-                bar();
-                chan_adjoint<N, P>(ggt, gxt, C, a.chan, t, gm);
-                g_last = 0; g_sync = false;
-                x_last = 0; x_sync = false;
+                adjoint_chan();
             }
         }
-        g_to_tile();
         touch_g(2);
-        if (a.need_gin)
-            tile_to_planes<N, P>(gt, a.gin, item, t.c, C, d.B, t.tid_c, nthr_c, d.skip ? a.gout : nullptr, sig, 1.0f);
-        // the next item overwrites both tiles with a block-wide pattern
+        if (a.need_gin) {
+#pragma unroll 1
+            for (int q = 0; q < Q; ++q)
+                PlaneIO<N, P>::from_tile(gt + q * TILE, a.gin, item * Q + q, t.c, C, d.B, t.tid_c, d.skip ? a.gout : nullptr,
+                                         sig, 1.0f);
+        }
+        // the next item overwrites both tile sets with a block-wide pattern
         __syncthreads();
     }
 
@@ -882,31 +961,25 @@ __global__ void __launch_bounds__(bwd_max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_
 // ------------------------------------------------------------------------------------------
 bool supported(const pde_adi_desc &d) {
     if (env_int("PDE_B200_ADI_LEGACY", 0)) return false;
-    if (d.steps < 1 || d.B < 1) return false;
+    if (d.steps < 1 || d.B < 1 || d.C > 3) return false;
     return d.N == 28 || d.N == 32;
 }
 
 size_t table_floats(const pde_adi_desc &d) { return 4 * stab_floats_per_table(d); }
 
-struct Plan {
-    int P, threads, wpc, grid, nitems, tmem_cols, blocks_per_sm;
-    size_t smem_fwd, smem_bwd, ck_slot;
-};
+constexpr int kMaxQ = 4;
 
-static int choose_pairs(const pde_adi_desc &d, int sm_count) {
-    const int forced = env_int("PDE_B200_SPLIT_P", 0);
-    if (forced == 2 || (forced == 4 && d.C == 1)) return forced;
-    if (d.C == 1 && (d.B + 7) / 8 >= 2 * sm_count) return 4;
-    return 2;
-}
+struct Plan {
+    int P, Qf, Qb, threads, wpc, ngroups, tmem_cols;
+    size_t tile_bytes, ck_slot;   // one tile (P pairs of one channel); f2 per (group, step)
+};
 
 template <int N, int P>
 static void fill_geo(const pde_adi_desc &d, Plan *p) {
     using G = SG<N, P>;
     p->wpc = G::WPC;
     p->threads = G::WPC * 32 * d.C;
-    p->smem_fwd = (size_t)d.C * G::TILE * sizeof(float);
-    p->smem_bwd = 2 * p->smem_fwd;
+    p->tile_bytes = (size_t)G::TILE * sizeof(float);
     p->ck_slot = (size_t)G::H * p->threads;
 }
 
@@ -914,73 +987,110 @@ static int make_plan(const pde_adi_desc &d, Plan *p) {
     DeviceProps props;
     int rc = query_props(&props);
     if (rc) return rc;
-    p->P = choose_pairs(d, props.sm_count);
+    const int sm = props.sm_count;
+    // pairs per group: 4 for the single-channel layers once the batch fills the GPU with such groups
+    p->P = 2;
+    if (d.C == 1 && d.chan_op == 0) {
+        const int forced = env_int("PDE_B200_SPLIT_P", 0);
+        if (forced == 4 || (forced != 2 && (d.B + 7) / 8 >= 2 * sm)) p->P = 4;
+    }
     if (d.N == 28) { if (p->P == 4) fill_geo<28, 4>(d, p); else fill_geo<28, 2>(d, p); }
     else if (d.N == 32) { if (p->P == 4) fill_geo<32, 4>(d, p); else fill_geo<32, 2>(d, p); }
     else return PDE_ERR_UNSUPPORTED;
-    p->nitems = (d.B + 2 * p->P - 1) / (2 * p->P);
+    p->ngroups = (d.B + 2 * p->P - 1) / (2 * p->P);
+    // groups per block: as many as still leave two blocks of work per SM (and fit shared memory)
+    auto pick = [&](int qmax, size_t tiles_per_group, const char *env) {
+        int q = qmax;
+        while (q > 1 && ((p->ngroups + q - 1) / q < 2 * sm || (size_t)q * tiles_per_group * p->tile_bytes > 110 * 1024)) q >>= 1;
+        const int forced = env_int(env, 0);
+        if (forced == 1 || forced == 2 || (forced == 4 && qmax == 4)) q = forced;
+        return q;
+    };
+    p->Qf = pick(p->P == 4 ? 4 : 2, (size_t)d.C, "PDE_B200_SPLIT_QF");
+    p->Qb = 1;   // measured: the backward kernel gains nothing from sharing coefficient loads
+    { const int f = env_int("PDE_B200_SPLIT_QB", 0); if (f == 1 || f == 2) p->Qb = f; }
     const int warps = p->threads / 32;
     const int blocks4 = (warps + 3) / 4;
     p->tmem_cols = blocks4 * 64 <= 64 ? 64 : (blocks4 * 64 <= 128 ? 128 : (blocks4 * 64 <= 256 ? 256 : 512));
-    p->blocks_per_sm = 0;
-    p->grid = 0;
-    (void)props;
     return PDE_OK;
 }
 
 size_t checkpoint_bytes(const pde_adi_desc &d) {
     Plan p;
     if (!supported(d) || make_plan(d, &p) != PDE_OK) return 0;
-    return (size_t)p.nitems * d.steps * p.ck_slot * 8 + 256;
+    const size_t groups = (size_t)((p.ngroups + kMaxQ - 1) / kMaxQ) * kMaxQ;
+    return groups * d.steps * p.ck_slot * 8 + 256;
 }
 
-template <int N, int P>
+template <int N, int P, int Q>
 static const void *bwd_ptr(bool chan) {
-    return chan ? reinterpret_cast<const void *>(sbwd_kernel<N, P, true>)
-                : reinterpret_cast<const void *>(sbwd_kernel<N, P, false>);
+    if (P == 4) return reinterpret_cast<const void *>(sbwd_kernel<N, P, Q, false>);
+    return chan ? reinterpret_cast<const void *>(sbwd_kernel<N, 2, Q, true>)
+                : reinterpret_cast<const void *>(sbwd_kernel<N, 2, Q, false>);
 }
-static const void *bwd_kernel_for(int N, int P, bool chan) {
-    if (N == 28) return P == 4 ? bwd_ptr<28, 4>(chan) : bwd_ptr<28, 2>(chan);
-    if (N == 32) return P == 4 ? bwd_ptr<32, 4>(chan) : bwd_ptr<32, 2>(chan);
+template <int N>
+static const void *bwd_kernel_n(int P, int Q, bool chan) {
+    if (P == 4) return Q == 2 ? bwd_ptr<N, 4, 2>(false) : bwd_ptr<N, 4, 1>(false);
+    return Q == 2 ? bwd_ptr<N, 2, 2>(chan) : bwd_ptr<N, 2, 1>(chan);
+}
+static const void *bwd_kernel_for(int N, int P, int Q, bool chan) {
+    if (N == 28) return bwd_kernel_n<28>(P, Q, chan);
+    if (N == 32) return bwd_kernel_n<32>(P, Q, chan);
     return nullptr;
 }
-static const void *fwd_kernel_for(int N, int P) {
-    if (N == 28) return P == 4 ? reinterpret_cast<const void *>(sfwd_kernel<28, 4>) : reinterpret_cast<const void *>(sfwd_kernel<28, 2>);
-    if (N == 32) return P == 4 ? reinterpret_cast<const void *>(sfwd_kernel<32, 4>) : reinterpret_cast<const void *>(sfwd_kernel<32, 2>);
+template <int N>
+static const void *fwd_kernel_n(int P, int Q) {
+    if (P == 4)
+        return Q == 4 ? reinterpret_cast<const void *>(sfwd_kernel<N, 4, 4>)
+                      : (Q == 2 ? reinterpret_cast<const void *>(sfwd_kernel<N, 4, 2>)
+                                : reinterpret_cast<const void *>(sfwd_kernel<N, 4, 1>));
+    return Q == 2 ? reinterpret_cast<const void *>(sfwd_kernel<N, 2, 2>) : reinterpret_cast<const void *>(sfwd_kernel<N, 2, 1>);
+}
+static const void *fwd_kernel_for(int N, int P, int Q) {
+    if (N == 28) return fwd_kernel_n<28>(P, Q);
+    if (N == 32) return fwd_kernel_n<32>(P, Q);
     return nullptr;
 }
 
-static int plan_bwd_grid(const pde_adi_desc &d, Plan *p) {
+struct BwdLaunch {
+    int grid, nitems, occ;
+    size_t smem;
+};
+
+static int plan_bwd_grid(const pde_adi_desc &d, const Plan &p, BwdLaunch *b) {
     DeviceProps props;
     int rc = query_props(&props);
     if (rc) return rc;
-    const void *kern = bwd_kernel_for(d.N, p->P, d.chan_op != 0);
+    const void *kern = bwd_kernel_for(d.N, p.P, p.Qb, d.chan_op != 0);
     if (!kern) return PDE_ERR_UNSUPPORTED;
-    if (p->smem_bwd > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
-    PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bwd));
+    b->smem = (size_t)2 * d.C * p.Qb * p.tile_bytes;
+    if (b->smem > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
+    PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     // residency from first principles (the occupancy calculator answers 1 block / SM for kernels
     // that allocate tensor memory)
     cudaFuncAttributes fa;
     PDE_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
-    const int warps = p->threads / 32;
+    // registers: 16 K per scheduler, a block's warps dealt round-robin over the four schedulers
+    const int warps = p.threads / 32;
     const int regs_per_warp = ((fa.numRegs + 7) / 8) * 8 * 32;
-    int occ = 65536 / (regs_per_warp * warps);
-    const int by_smem = (int)((size_t)(228 * 1024) / (p->smem_bwd + fa.sharedSizeBytes + 1024));
-    const int by_threads = 2048 / p->threads;
-    const int by_tmem = 512 / p->tmem_cols;
+    int occ = 16384 / (regs_per_warp * ((warps + 3) / 4));
+    const int by_smem = (int)((size_t)(228 * 1024) / (b->smem + fa.sharedSizeBytes + 1024));
+    const int by_threads = 2048 / p.threads;
+    const int by_tmem = 512 / p.tmem_cols;
     if (by_smem < occ) occ = by_smem;
     if (by_threads < occ) occ = by_threads;
     if (by_tmem < occ) occ = by_tmem;
     const int cap_env = env_int("PDE_B200_SPLIT_BWD_OCC", 0);
     if (cap_env > 0 && cap_env < occ) occ = cap_env;
     if (occ < 1) occ = 1;
-    p->blocks_per_sm = occ;
+    b->occ = occ;
+    b->nitems = (p.ngroups + p.Qb - 1) / p.Qb;
     if (env_int("PDE_B200_DEBUG", 0))
-        fprintf(stderr, "[pde_b200] split bwd plan: N=%d C=%d P=%d threads=%d smem=%zu regs=%d occ=%d tmem=%d\n", d.N, d.C,
-                p->P, p->threads, p->smem_bwd, fa.numRegs, occ, p->tmem_cols);
+        fprintf(stderr, "[pde_b200] split bwd plan: N=%d C=%d P=%d Q=%d threads=%d smem=%zu regs=%d occ=%d tmem=%d\n", d.N,
+                d.C, p.P, p.Qb, p.threads, b->smem, fa.numRegs, occ, p.tmem_cols);
     const int cap = props.sm_count * occ;
-    p->grid = p->nitems < cap ? p->nitems : cap;
-    if (p->grid < 1) p->grid = 1;
+    b->grid = b->nitems < cap ? b->nitems : cap;
+    if (b->grid < 1) b->grid = 1;
     return PDE_OK;
 }
 
@@ -990,7 +1100,7 @@ struct WsLayout {
 };
 
 static void ws_layout(const pde_adi_desc &d, const Plan &p, int grid, WsLayout *w) {
-    w->scratch_floats = (size_t)grid * 2 * p.ck_slot * 2;   // two sweep outputs per block (exact mode)
+    w->scratch_floats = (size_t)grid * p.Qb * 2 * p.ck_slot * 2;   // two sweep outputs per block and group (exact mode)
     w->nsets_maps = grid * d.C;
     w->nsets_small = grid * p.wpc * d.C;
     w->maps_floats = (size_t)w->nsets_maps * 4 * d.N * d.N;
@@ -1000,10 +1110,11 @@ static void ws_layout(const pde_adi_desc &d, const Plan &p, int grid, WsLayout *
 
 size_t workspace_bytes(const pde_adi_desc &d) {
     Plan p;
+    BwdLaunch b;
     if (!supported(d) || make_plan(d, &p) != PDE_OK) return 0;
-    if (plan_bwd_grid(d, &p) != PDE_OK) return 0;
+    if (plan_bwd_grid(d, p, &b) != PDE_OK) return 0;
     WsLayout w;
-    ws_layout(d, p, p.grid, &w);
+    ws_layout(d, p, b.grid, &w);
     return (w.scratch_floats + w.maps_floats + w.chan_floats + w.skip_floats) * sizeof(float) + 512;
 }
 
@@ -1033,27 +1144,28 @@ int forward(const pde_adi_desc &d, const char *tables, const float *u, const flo
     DeviceProps props;
     rc = query_props(&props);
     if (rc) return rc;
-    const void *kern = fwd_kernel_for(d.N, p.P);
+    const void *kern = fwd_kernel_for(d.N, p.P, p.Qf);
     if (!kern) return PDE_ERR_UNSUPPORTED;
-    if (p.smem_fwd > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
-    PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_fwd));
+    const size_t smem = (size_t)d.C * p.Qf * p.tile_bytes;
+    if (smem > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
+    PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    PDE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, p.threads, p.smem_fwd));
+    PDE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, p.threads, smem));
     if (per_sm < 1) per_sm = 1;
     const int cap_env = env_int("PDE_B200_SPLIT_FWD_OCC", 0);
     if (cap_env > 0 && cap_env < per_sm) per_sm = cap_env;
     Args a{};
     fill_args(d, tables, &a);
-    a.nitems = p.nitems;
+    a.nitems = (p.ngroups + p.Qf - 1) / p.Qf;
     a.u = u; a.chan = chan; a.skipw = skipw; a.out = out;
     a.ckpt = ckpt ? reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ckpt) + 255u) & ~(uintptr_t)255u) : nullptr;
     const int cap = props.sm_count * per_sm;
-    const int grid = p.nitems < cap ? p.nitems : cap;
+    const int grid = a.nitems < cap ? a.nitems : cap;
     if (env_int("PDE_B200_DEBUG", 0))
-        fprintf(stderr, "[pde_b200] split fwd plan: N=%d C=%d P=%d threads=%d smem=%zu occ=%d grid=%d\n", d.N, d.C, p.P,
-                p.threads, p.smem_fwd, per_sm, grid);
+        fprintf(stderr, "[pde_b200] split fwd plan: N=%d C=%d P=%d Q=%d threads=%d smem=%zu occ=%d grid=%d\n", d.N, d.C, p.P,
+                p.Qf, p.threads, smem, per_sm, grid);
     void *params[] = {&a};
-    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(p.threads), params, p.smem_fwd, st));
+    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(p.threads), params, smem, st));
     return cuda_last_error();
 }
 
@@ -1061,18 +1173,19 @@ int backward(const pde_adi_desc &d, const char *tables, const float *u, const fl
              const float *skipw, const float *ckpt, float *gin, float *g_ab, float *g_bb, float *g_atc, float *g_btc,
              float *g_chan, float *g_skip, void *workspace, size_t workspace_bytes_, cudaStream_t st) {
     Plan p;
+    BwdLaunch b;
     int rc = make_plan(d, &p);
     if (rc) return rc;
-    rc = plan_bwd_grid(d, &p);
+    rc = plan_bwd_grid(d, p, &b);
     if (rc) return rc;
     WsLayout w;
-    ws_layout(d, p, p.grid, &w);
+    ws_layout(d, p, b.grid, &w);
     const size_t need = (w.scratch_floats + w.maps_floats + w.chan_floats + w.skip_floats) * sizeof(float) + 512;
     if (!workspace || workspace_bytes_ < need || !ckpt) return PDE_ERR_WORKSPACE;
     float *ws = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255u) & ~(uintptr_t)255u);
     Args a{};
     fill_args(d, tables, &a);
-    a.nitems = p.nitems;
+    a.nitems = b.nitems;
     a.need_gin = gin != nullptr;
     a.tmem_cols = p.tmem_cols;
     a.u = u; a.gout = gout; a.chan = chan; a.skipw = skipw; a.gin = gin;
@@ -1081,9 +1194,9 @@ int backward(const pde_adi_desc &d, const char *tables, const float *u, const fl
     a.part_maps = ws + w.scratch_floats;
     a.part_chan = a.part_maps + w.maps_floats;
     a.part_skip = a.part_chan + w.chan_floats;
-    const void *kern = bwd_kernel_for(d.N, p.P, d.chan_op != 0);
+    const void *kern = bwd_kernel_for(d.N, p.P, p.Qb, d.chan_op != 0);
     void *params[] = {&a};
-    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(p.grid), dim3(p.threads), params, p.smem_bwd, st));
+    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(b.grid), dim3(p.threads), params, b.smem, st));
     rc = cuda_last_error();
     if (rc) return rc;
     launch_finish(d, w.nsets_maps, w.nsets_small, a.part_maps, a.part_chan, a.part_skip, skipw, g_ab, g_atc, g_bb, g_btc,

@@ -28,8 +28,11 @@ def parity():
         K.case("fashion_dt5", "fashion", B=8, perturb=False, dt=5.0),
     ]
     worst = 0.0
-    for forced in ("2", "4"):
+    for forced, qf, qb in (("2", "1", "1"), ("2", "2", "2"), ("4", "4", "2"), ("4", "2", "1")):
         os.environ["PDE_B200_SPLIT_P"] = forced
+        os.environ["PDE_B200_SPLIT_QF"] = qf
+        os.environ["PDE_B200_SPLIT_QB"] = qb
+        forced = f"{forced} Q={qf}/{qb}"
         for c in cases:
             params, io = K.make_params(c), K.make_io(c)
             want = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
@@ -49,16 +52,20 @@ def parity():
                 flag = "ok " if m <= 1e-5 else "BAD"
                 print(f"P={forced} {c.name:14s} gin={int(need_gin)} {flag} max={m:.2e} " +
                       " ".join(f"{k}={v:.1e}" for k, v in errs.items() if not v <= 1e-5))
-    os.environ.pop("PDE_B200_SPLIT_P", None)
+    for k in ("PDE_B200_SPLIT_P", "PDE_B200_SPLIT_QF", "PDE_B200_SPLIT_QB"):
+        os.environ.pop(k, None)
     print("worst", worst)
 
 
 def timing():
+    variants = [("1", "", ""), ("0", "", ""), ("0", "4", "1"), ("0", "2", "1"), ("0", "1", "1")]
     for name, B in (("fashion", 262144), ("mnist", 131072), ("cifar10_pde1", 65536)):
         kind, ctor, _, _ = bench.LAYERS[name]
         c = K.case("t", kind, B=B, perturb=False, **ctor)
-        for legacy in ("1", "0"):
+        for legacy, qf, qb in variants:
             os.environ["PDE_B200_ADI_LEGACY"] = legacy
+            os.environ["PDE_B200_SPLIT_QF"] = qf
+            os.environ["PDE_B200_SPLIT_QB"] = qb
             layer = runners.make_cuda_layer(c)
             u = torch.randn(B, *c.shape, device="cuda")
             g = torch.randn(B, *c.shape, device="cuda")
@@ -79,10 +86,11 @@ def timing():
                 torch.cuda.synchronize()
                 ts = [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])]
                 best = [min(a, b) for a, b in zip(best, ts)]
-            print(f"{name} B={B} legacy={legacy}: fwd(eval) {best[0]:.3f}  fwd(train) {best[1]:.3f}  bwd {best[2]:.3f} ms")
+            print(f"{name} B={B} legacy={legacy} qf={qf or '-'} qb={qb or '-'}: fwd(eval) {best[0]:.3f}  fwd(train) {best[1]:.3f}  bwd {best[2]:.3f} ms")
             del layer, u, g, x, y
             torch.cuda.empty_cache()
-    os.environ.pop("PDE_B200_ADI_LEGACY", None)
+    for k in ("PDE_B200_ADI_LEGACY", "PDE_B200_SPLIT_QF", "PDE_B200_SPLIT_QB"):
+        os.environ.pop(k, None)
 
 
 if __name__ == "__main__":

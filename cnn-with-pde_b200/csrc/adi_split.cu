@@ -419,7 +419,6 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
     if (d.skip) sig = 1.0f / (1.0f + expf(-__ldg(a.skipw)));
     const float om = 1.0f - sig;
     const size_t plane = (size_t)N * N;
-    const size_t ck_slot = (size_t)H * nthr;   // f2 per (group, step)
     const int sps = a.sps, S = a.S;
     __shared__ short h_slot[PDE_MAX_SWEEPS];
     {
@@ -475,13 +474,25 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
                     else ld_half<N, P, 1>(tile + p * TILE, t, x[p]);
                 }
                 solve<N, P, NP>(x, iv, e, far);
-                if (k == sps - 1 && a.ckpt) {   // state after the last sweep of the step
+                if (k == sps - 1 && a.ckpt && t.active) {
+                    // state after the last sweep of the step, written as a tile image: the backward
+                    // kernel brings it back with one bulk copy per step
 #pragma unroll
                     for (int p = 0; p < NP; ++p) {
-                        unsigned long long *ck = reinterpret_cast<unsigned long long *>(a.ckpt) +
-                                                 ((size_t)(item * Q + q + p) * d.steps + step) * ck_slot + threadIdx.x;
+                        float *ck = a.ckpt + (((size_t)(item * Q + q + p) * d.steps + step) * C + t.c) * TILE;
+                        if (ax == 0) {
 #pragma unroll
-                        for (int kk = 0; kk < H; ++kk) __stcs(ck + (size_t)kk * nthr, x[p][kk].v);
+                            for (int m = 0; m < G::HCH; ++m) {
+                                ulonglong2 v;
+                                v.x = x[p][2 * m].v;
+                                v.y = x[p][2 * m + 1].v;
+                                __stcs(reinterpret_cast<ulonglong2 *>(ck + t.b0 + m * P * 4), v);
+                            }
+                        } else {
+#pragma unroll
+                            for (int kk = 0; kk < H; ++kk)
+                                __stcs(reinterpret_cast<unsigned long long *>(ck + t.b1 + kk * G::RS), x[p][kk].v);
+                        }
                     }
                 }
                 if (fuse) solve<N, P, NP>(x, iv, e, far);
@@ -671,30 +682,79 @@ __device__ __forceinline__ void chan_adjoint(float *ggt, const float *gxt, int c
     if (t.active) st_half<N, P, 0>(ggt + (size_t)t.c * cstride, t, gn);
 }
 
-template <int N, int P, int Q, bool CHAN>
+// gout planes of group `grp` -> tile, asynchronously (LDGSTS): every 4-byte cell goes straight from
+// global memory to its slot in the interleaved / mirrored tile, no registers, no wait.  Samples
+// beyond the batch are zero-filled.  Completion: cp_async_wait_all() + a barrier.
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, bool valid) {
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int N, int P>
+__device__ __forceinline__ void planes_to_tile_async(const float *__restrict__ g, float *tile, int grp, int c, int C,
+                                                     int B, int tid_c) {
+    using IO = PlaneIO<N, P>;
+#pragma unroll
+    for (int it = 0; it < IO::IT; ++it) {
+        const int idx = tid_c + it * IO::NTHR;
+        if (idx < P * IO::F2) {
+            const int pp = idx % P, f = idx / P;
+            const int ba = (grp * P + pp) * 2, bb = ba + 1;
+            const bool va = ba < B, vb = bb < B;
+            const float *sa = g + ((size_t)(va ? ba : 0) * C + c) * (N * N) + 2 * f;
+            const float *sb = g + ((size_t)(vb ? bb : 0) * C + c) * (N * N) + 2 * f;
+            bool hc;
+            float *dst = tile + IO::tile_off(f, pp, hc);
+            // chunk = {cell lo: a, b; cell hi: a, b}; in the far half the two columns swap
+            cp_async4(dst + (hc ? 2 : 0), sa, va);
+            cp_async4(dst + (hc ? 3 : 1), sb, vb);
+            cp_async4(dst + (hc ? 0 : 2), sa + 1, va);
+            cp_async4(dst + (hc ? 1 : 3), sb + 1, vb);
+        }
+    }
+}
+
+// Backward kernel.  One group of P sample pairs (all channels) per block iteration; both tile sets
+// are double buffered and filled asynchronously one stage ahead:
+//   x tiles: TMA bulk copies of the checkpoints (the forward kernel wrote them as tile images),
+//            stream (item, last step) ... (item, step 0), (next item, last step) ...
+//   g tiles: the next item's gout planes by LDGSTS while the current item is reversed.
+template <int N, int P, bool CHAN>
 __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kernel(const Args a) {
     using G = SG<N, P>;
     constexpr int H = G::H, TILE = G::TILE, HQ4 = 4 * G::HQ;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     __shared__ uint32_t tmem_slot;
-    __shared__ float h_scale[PDE_MAX_SWEEPS], h_t[PDE_MAX_SWEEPS];
-    __shared__ int h_clamped[PDE_MAX_SWEEPS];
+    __shared__ __align__(8) uint64_t xbar[2];
     const pde_adi_desc &d = a.d;
     const Lane t = make_lane<N, P>();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = d.C, nthr = blockDim.x;
     const bool far = t.h == 1;
-    constexpr int CS = Q * TILE;   // channel stride
-    float *gxt = smem, *ggt = smem + (size_t)C * CS;
-    float *xt = gxt + (size_t)t.c * CS, *gt = ggt + (size_t)t.c * CS;   // this channel's Q tiles
+    const int CS = TILE;                 // channel stride inside a tile set
+    const int SET = C * TILE;            // floats per tile set
+    constexpr bool GDB = P >= 4;         // second g set: the next item's gout arrives while this one is reversed
+    // tile sets by offset from the one shared-memory base (pointer arrays indexed at run time would
+    // end up in local memory and turn every tile access into a generic load)
+    auto xset = [&](int b) { return smem + b * SET; };
+    auto gset = [&](int b) { return smem + (2 + (GDB ? b : 0)) * SET; };
+    // coefficient stage: r and 1/pivot of one sweep (all channels), double buffered, filled by TMA
+    // one sweep ahead -- the tables do not survive in what is left of L1 beside the tiles
+    const int CT = C * G::HQ * N * 2 * 4;   // floats per table per sweep
+    float *cbuf = smem + (GDB ? 4 : 3) * SET;
+    __shared__ __align__(8) uint64_t cbar[2];
 
     if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)a.tmem_cols);
-    const Header *hdr = reinterpret_cast<const Header *>(a.tables);
-    for (int i = threadIdx.x; i < a.S; i += nthr) {
-        h_scale[i] = hdr->scale[i];
-        h_t[i] = hdr->t[i];
-        h_clamped[i] = hdr->clamped[i];
+    if (threadIdx.x == 0) {
+        mbar_init(&xbar[0], 1);
+        mbar_init(&xbar[1], 1);
+        mbar_init(&cbar[0], 1);
+        mbar_init(&cbar[1], 1);
+        mbar_fence_init();
     }
+    const Header *hdr = reinterpret_cast<const Header *>(a.tables);
     tmem_fence_before_sync();
     __syncthreads();
     tmem_fence_after_sync();
@@ -714,7 +774,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
     const float4 *tab_e = reinterpret_cast<const float4 *>(a.stab + 2 * T);
     const float4 *tab_m = reinterpret_cast<const float4 *>(a.stab + 3 * T);
     const size_t plane = (size_t)N * N;
-    const size_t ck_slot = (size_t)H * nthr;
+    const size_t ck_step = (size_t)SET;   // floats per (group, step): a tile image per channel
     float sig = 0.0f;
     if (d.skip) sig = 1.0f / (1.0f + expf(-__ldg(a.skipw)));
     const float om = 1.0f - sig;
@@ -724,26 +784,69 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
     float gw = 0.0f;
     const int sps = a.sps;
     const int last_ax = (sps == 3) ? 0 : 1;
-    // exact mode: outputs of the first sps-1 sweeps of the step being reversed, per block and group
+    // exact mode: outputs of the first sps-1 sweeps of the step being reversed, per block
+    const size_t scr_slot = (size_t)H * nthr;
     unsigned long long *sweep_scr =
-        reinterpret_cast<unsigned long long *>(a.scratch) + (size_t)blockIdx.x * Q * 2 * ck_slot + threadIdx.x;
+        reinterpret_cast<unsigned long long *>(a.scratch) + (size_t)blockIdx.x * 2 * scr_slot + threadIdx.x;
+    // the layer input is needed in the spare x buffer at step 0 (pre-step mix adjoint, exact
+    // recomputation): the first checkpoint of the next item then waits for the end of the item
+    const bool defer_cross = exact || (CHAN && d.chan_op == 1);
+
+    // ---- asynchronous x stream
+    uint32_t xphase = 0u;      // bit b: parity the next wait on buffer b expects
+    uint32_t xpending = 0u;    // bit b: a fill of buffer b has not been waited for yet
+    auto x_fill = [&](int b, int item, int step) {   // call after a barrier that ends every use of buffer b
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            const uint32_t bytes = (uint32_t)(SET * sizeof(float));
+            mbar_expect_tx(&xbar[b], bytes);
+            tma_load_1d(xset(b), a.ckpt + ((size_t)item * d.steps + step) * ck_step, bytes, &xbar[b]);
+        }
+        xpending |= 1u << b;
+    };
+    auto x_wait = [&](int b) {
+        if (xpending & (1u << b)) {
+            mbar_wait(&xbar[b], (xphase >> b) & 1u);
+            xphase ^= 1u << b;
+            xpending &= ~(1u << b);
+        }
+    };
+    uint32_t cphase = 0u;
+    auto c_fill = [&](int b, int s) {   // call after a barrier that ends every read of buffer b
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            const uint32_t bytes = (uint32_t)(CT * sizeof(float));
+            mbar_expect_tx(&cbar[b], 2 * bytes);
+            tma_load_1d(cbuf + (size_t)(2 * b) * CT, a.stab + (size_t)s * CT, bytes, &cbar[b]);
+            tma_load_1d(cbuf + (size_t)(2 * b + 1) * CT, a.stab + T + (size_t)s * CT, bytes, &cbar[b]);
+        }
+    };
+    int xb = 0, gb = 0, cb = 0;
+    if (blockIdx.x < a.nitems) {
+        x_fill(0, blockIdx.x, d.steps - 1);
+        c_fill(0, a.S - 1);
+        if (GDB) {
+            planes_to_tile_async<N, P>(a.gout, gset(0) + (size_t)t.c * CS, blockIdx.x, t.c, C, d.B, t.tid_c);
+            cp_async_commit();
+        }
+    }
 
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-        const unsigned long long *ck_item =
-            reinterpret_cast<const unsigned long long *>(a.ckpt) + (size_t)item * Q * d.steps * ck_slot + threadIdx.x;
-        if (threadIdx.x == 0) {   // next item: checkpoints and planes on their way to L2
-            const long long ni = (long long)item + gridDim.x;
-            const long long nb = ni * Q * 2 * P;
-            if (nb < d.B) {
-                const long long ns = (d.B - nb) < 2 * P * Q ? (d.B - nb) : 2 * P * Q;
-                prefetch_region_l2(a.gout + (size_t)nb * C * plane, (size_t)ns * C * plane * sizeof(float));
-                prefetch_region_l2(reinterpret_cast<const unsigned long long *>(a.ckpt) + (size_t)ni * Q * d.steps * ck_slot,
-                                   (size_t)((ns + 2 * P - 1) / (2 * P)) * d.steps * ck_slot * 8);
-                if (d.skip || d.chan_op == 1 || exact)
-                    prefetch_region_l2(a.u + (size_t)nb * C * plane, (size_t)ns * C * plane * sizeof(float));
+        const int next_item = item + gridDim.x;
+        float *ggt = gset(gb), *gt = ggt + (size_t)t.c * CS;
+        if (GDB) {
+            cp_async_wait_all();
+            __syncthreads();   // this item's gout tile is complete; nobody still reads the other g set
+            if (next_item < a.nitems) {
+                planes_to_tile_async<N, P>(a.gout, gset(gb ^ 1) + (size_t)t.c * CS, next_item, t.c, C, d.B, t.tid_c);
+                cp_async_commit();
             }
+        } else {
+            __syncthreads();   // the previous item's grad_input has left the g set
+            PlaneIO<N, P>::to_tile(a.gout, gt, item, t.c, C, d.B, t.tid_c);
+            __syncthreads();
         }
-        // Which orientation last touched the tiles, and whether a barrier has passed since: a thread
+        // Which orientation last touched a tile set, and whether a barrier has passed since: a thread
         // only reads and writes its own half line within one orientation, so a barrier is needed
         // exactly when the orientation changes (2 = block-wide access pattern).
         int x_last = 2, g_last = 2;
@@ -763,162 +866,163 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
             g_last = o;
             g_sync = false;
         };
-        // x tiles <- state after the last sweep of `step` (step == -1: the layer input)
-        auto state_to_xt = [&](int step) {
-            if (step < 0) {
-                touch_x(2);
-#pragma unroll 1
-                for (int q = 0; q < Q; ++q) PlaneIO<N, P>::to_tile(a.u, xt + q * TILE, item * Q + q, t.c, C, d.B, t.tid_c);
-            } else {
-                touch_x(last_ax);
-#pragma unroll 1
-                for (int q = 0; q < Q; ++q) {
-                    f2 xs[H];
-#pragma unroll
-                    for (int k = 0; k < H; ++k)
-                        xs[k].v = __ldcs(ck_item + (((size_t)q * d.steps + step) * H + k) * nthr);
-                    if (t.active) {
-                        if (last_ax == 0) st_half<N, P, 0>(xt + q * TILE, t, xs);
-                        else st_half<N, P, 1>(xt + q * TILE, t, xs);
-                    }
-                }
-            }
-        };
-        // x tiles (rows) <- channel op applied to the x tiles
-        auto mix_xt = [&]() {
-            touch_x(2);
-            bar();
-#pragma unroll 1
-            for (int q = 0; q < Q; ++q) {
-                f2 x[H];
-                mix_rows<N, P>(gxt + q * TILE, CS, C, a.chan + t.c * C, 1, t, x);
-                __syncthreads();
-                if (t.active) st_half<N, P, 0>(xt + q * TILE, t, x);
-            }
-            x_last = 0;
-            x_sync = false;
-        };
-        auto adjoint_chan = [&]() {
+        auto adjoint_chan = [&](const float *gx) {   // gx: tile set with the op's input (read only)
             touch_g(2);
-            touch_x(2);
             bar();
-#pragma unroll 1
-            for (int q = 0; q < Q; ++q) chan_adjoint<N, P>(ggt + q * TILE, gxt + q * TILE, CS, C, a.chan, t, gm);
-            g_last = 0; g_sync = false;
-            x_last = 0; x_sync = false;
+            chan_adjoint<N, P>(ggt, gx, CS, C, a.chan, t, gm);
+            g_last = 0;
+            g_sync = false;
         };
 
-        touch_g(2);
-#pragma unroll 1
-        for (int q = 0; q < Q; ++q) PlaneIO<N, P>::to_tile(a.gout, gt + q * TILE, item * Q + q, t.c, C, d.B, t.tid_c);
         if (d.skip) {
             // out = sig u0 + om uF:  dL/dw += sig' * sum gout (u0 - uF),  g <- om * gout
-            state_to_xt(d.steps - 1);
-            if (d.chan_op == 2) mix_xt();
-            touch_x(0);
+            x_wait(xb);
+            f2 uf[H], gl[H];
+            if (d.chan_op == 2) mix_rows<N, P>(xset(xb), CS, C, a.chan + t.c * C, 1, t, uf);   // uF = K (last state)
+            else ld_half<N, P, 0>(xset(xb) + (size_t)t.c * CS, t, uf);
             touch_g(0);
-#pragma unroll 1
-            for (int q = 0; q < Q; ++q) {
-                f2 uf[H], gl[H];
-                ld_half<N, P, 0>(xt + q * TILE, t, uf);
-                ld_half<N, P, 0>(gt + q * TILE, t, gl);
-                if (t.active) {
-                    f2 accw = f2_bc(0.0f);
-                    const int i = mirror(t.R, N);
-                    const float2 zero2 = make_float2(0.f, 0.f);
-                    const int ba = ((item * Q + q) * P + t.pp) * 2, bb = ba + 1;
+            ld_half<N, P, 0>(gt, t, gl);
+            if (t.active) {
+                f2 accw = f2_bc(0.0f);
+                const int i = mirror(t.R, N);
+                const float2 zero2 = make_float2(0.f, 0.f);
+                const int ba = (item * P + t.pp) * 2, bb = ba + 1;
 #pragma unroll
-                    for (int m = 0; m < G::HCH; ++m) {
-                        // cells k = 2m, 2m+1 of the half row: columns 2m, 2m+1 (near) or N-1-2m, N-2-2m (far)
-                        const int j0 = t.h ? N - 2 - 2 * m : 2 * m;
-                        const float2 wa = ba < d.B ? __ldg(reinterpret_cast<const float2 *>(a.u + ((size_t)ba * C + t.c) * plane + (size_t)i * N + j0)) : zero2;
-                        const float2 wb = bb < d.B ? __ldg(reinterpret_cast<const float2 *>(a.u + ((size_t)bb * C + t.c) * plane + (size_t)i * N + j0)) : zero2;
-                        const f2 u0 = t.h ? f2_make(wa.y, wb.y) : f2_make(wa.x, wb.x);
-                        const f2 u1 = t.h ? f2_make(wa.x, wb.x) : f2_make(wa.y, wb.y);
-                        accw = f2_fma(gl[2 * m], f2_sub(u0, uf[2 * m]), accw);
-                        accw = f2_fma(gl[2 * m + 1], f2_sub(u1, uf[2 * m + 1]), accw);
-                        gl[2 * m] = f2_muls(om, gl[2 * m]);
-                        gl[2 * m + 1] = f2_muls(om, gl[2 * m + 1]);
-                    }
-                    st_half<N, P, 0>(gt + q * TILE, t, gl);
-                    gw += f2_hsum(accw);
+                for (int m = 0; m < G::HCH; ++m) {
+                    // cells k = 2m, 2m+1 of the half row: columns 2m, 2m+1 (near) or N-1-2m, N-2-2m (far)
+                    const int j0 = t.h ? N - 2 - 2 * m : 2 * m;
+                    const float2 wa = ba < d.B ? __ldg(reinterpret_cast<const float2 *>(a.u + ((size_t)ba * C + t.c) * plane + (size_t)i * N + j0)) : zero2;
+                    const float2 wb = bb < d.B ? __ldg(reinterpret_cast<const float2 *>(a.u + ((size_t)bb * C + t.c) * plane + (size_t)i * N + j0)) : zero2;
+                    const f2 u0 = t.h ? f2_make(wa.y, wb.y) : f2_make(wa.x, wb.x);
+                    const f2 u1 = t.h ? f2_make(wa.x, wb.x) : f2_make(wa.y, wb.y);
+                    accw = f2_fma(gl[2 * m], f2_sub(u0, uf[2 * m]), accw);
+                    accw = f2_fma(gl[2 * m + 1], f2_sub(u1, uf[2 * m + 1]), accw);
+                    gl[2 * m] = f2_muls(om, gl[2 * m]);
+                    gl[2 * m + 1] = f2_muls(om, gl[2 * m + 1]);
                 }
+                st_half<N, P, 0>(gt, t, gl);
+                gw += f2_hsum(accw);
             }
+            x_last = 0;   // rows of the x set were read (all channels if coupled)
+            x_sync = false;
         }
 
         for (int step = d.steps - 1; step >= 0; --step) {
+            float *gxt = xset(xb), *xt = gxt + (size_t)t.c * CS;       // state after the last sweep of `step`
+            float *gxs = xset(xb ^ 1), *xs = gxs + (size_t)t.c * CS;   // spare: the stage ahead
+            // every use of the spare buffer (previous step) ends here; start the stage ahead
+            bar();
+            if (step > 0) x_fill(xb ^ 1, item, step - 1);
+            else if (!defer_cross && next_item < a.nitems) x_fill(xb ^ 1, next_item, d.steps - 1);
+            x_wait(xb);
             if (exact) {
-                // recompute the sweeps of this step from its input, keeping every sweep output
-                state_to_xt(step - 1);
-                if (CHAN && (d.chan_op == 1 || (d.chan_op == 2 && step > 0))) mix_xt();
+                // recompute the sweeps of this step from its input (spare buffer), keeping every sweep output
+                f2 x[1][H];
+                if (step > 0) {
+                    x_wait(xb ^ 1);
+                } else {
+                    PlaneIO<N, P>::to_tile(a.u, xs, item, t.c, C, d.B, t.tid_c);
+                    __syncthreads();
+                }
+                if (CHAN && (d.chan_op == 1 || (d.chan_op == 2 && step > 0))) {
+                    mix_rows<N, P>(gxs, CS, C, a.chan + t.c * C, 1, t, x[0]);
+                    __syncthreads();   // every thread has read the spare set before it is used as scratch
+                } else if (step > 0 && last_ax == 1) {
+                    ld_half<N, P, 0>(xs, t, x[0]);
+                    __syncthreads();
+                } else {
+                    ld_half<N, P, 0>(xs, t, x[0]);
+                }
                 for (int k = 0; k + 1 < sps; ++k) {
-                    const int s = step * sps + k, ax = sweep_axis(k);
+                    const int s = step * sps + k;
                     float iv[HQ4], e[HQ4];
                     ld_coef<N, P>(tab_inv + tab_off<N, P>(s, C, t), iv);
                     ld_coef<N, P>(tab_e + tab_off<N, P>(s, C, t), e);
-                    touch_x(ax);
-#pragma unroll 1
-                    for (int q = 0; q < Q; ++q) {
-                        f2 x[1][H];
-                        if (ax == 0) ld_half<N, P, 0>(xt + q * TILE, t, x[0]);
-                        else ld_half<N, P, 1>(xt + q * TILE, t, x[0]);
-                        solve<N, P, 1>(x, iv, e, far);
-#pragma unroll
-                        for (int kk = 0; kk < H; ++kk) __stcg(sweep_scr + (((size_t)q * 2 + k) * H + kk) * nthr, x[0][kk].v);
-                        if (t.active) {
-                            if (ax == 0) st_half<N, P, 0>(xt + q * TILE, t, x[0]);
-                            else st_half<N, P, 1>(xt + q * TILE, t, x[0]);
-                        }
+                    if (k == 1) {
+                        if (t.active) st_half<N, P, 0>(xs, t, x[0]);
+                        __syncthreads();
+                        ld_half<N, P, 1>(xs, t, x[0]);
                     }
+                    solve<N, P, 1>(x, iv, e, far);
+#pragma unroll
+                    for (int kk = 0; kk < H; ++kk) __stcg(sweep_scr + ((size_t)k * H + kk) * nthr, x[0][kk].v);
                 }
+                __syncthreads();
+                if (step > 0) x_fill(xb ^ 1, item, step - 1);   // the spare buffer was used as scratch
+                x_last = 2;
+                x_sync = true;
             }
-            state_to_xt(step);
             // adjoint of the post-step coupling: its input is the state after the last sweep
-            if (CHAN && d.chan_op == 2) adjoint_chan();
+            if (CHAN && d.chan_op == 2) {
+                adjoint_chan(gxt);
+                x_last = 0;
+                x_sync = false;
+            }
             for (int k = sps - 1; k >= 0; --k) {
                 const int s = step * sps + k, ax = sweep_axis(k);
                 const size_t o = tab_off<N, P>(s, C, t);
+                // per-sweep scalars straight from the header (shared memory is full)
+                const float sw_scale = __ldg(&hdr->scale[s]), sw_t = __ldg(&hdr->t[s]);
+                const bool sw_clamped = __ldg(&hdr->clamped[s]) != 0;
+                // every thread has its registers loaded from the other coefficient buffer (previous sweep)
+                bar();
+                {
+                    const int ns = s > 0 ? s - 1 : (next_item < a.nitems ? a.S - 1 : -1);
+                    if (ns >= 0) c_fill(cb ^ 1, ns);
+                }
+                mbar_wait(&cbar[cb], (cphase >> cb) & 1u);
+                cphase ^= 1u << cb;
                 float r[HQ4], iv[HQ4];
-                ld_coef<N, P>(tab_r + o, r);
-                ld_coef<N, P>(tab_inv + o, iv);
+                {
+                    const float4 *cr = reinterpret_cast<const float4 *>(cbuf + (size_t)(2 * cb) * CT) + t.tab;
+                    const float4 *ci = reinterpret_cast<const float4 *>(cbuf + (size_t)(2 * cb + 1) * CT) + t.tab;
+#pragma unroll
+                    for (int q = 0; q < G::HQ; ++q) {
+                        const float4 a4 = cr[q * G::QS], b4 = ci[q * G::QS];
+                        r[4 * q] = a4.x; r[4 * q + 1] = a4.y; r[4 * q + 2] = a4.z; r[4 * q + 3] = a4.w;
+                        iv[4 * q] = b4.x; iv[4 * q + 1] = b4.y; iv[4 * q + 2] = b4.z; iv[4 * q + 3] = b4.w;
+                    }
+                }
+                cb ^= 1;
                 const bool rebuild = !exact && k > 0;
-                const bool reload = exact && k != sps - 1;
                 touch_g(ax);
                 touch_x(ax);
                 float vacc[16];
 #pragma unroll
                 for (int kk = 0; kk < 16; ++kk) vacc[kk] = 0.0f;
-#pragma unroll 1
-                for (int q = 0; q < Q; ++q) {
-                    if (reload) {   // exact mode: this sweep's output comes back from the block's scratch
-                        f2 x[H];
+                if (exact && k != sps - 1) {   // this sweep's output comes back from the block's scratch
+                    f2 x[H];
 #pragma unroll
-                        for (int kk = 0; kk < H; ++kk) x[kk].v = __ldcg(sweep_scr + (((size_t)q * 2 + k) * H + kk) * nthr);
-                        if (t.active) {
-                            if (ax == 0) st_half<N, P, 0>(xt + q * TILE, t, x);
-                            else st_half<N, P, 1>(xt + q * TILE, t, x);
-                        }
+                    for (int kk = 0; kk < H; ++kk) x[kk].v = __ldcg(sweep_scr + ((size_t)k * H + kk) * nthr);
+                    if (t.active) {
+                        if (ax == 0) st_half<N, P, 0>(xt, t, x);
+                        else st_half<N, P, 1>(xt, t, x);
                     }
-                    if (ax == 0) reverse_core<N, P, 0>(gt + q * TILE, xt + q * TILE, t, vacc, r, iv, onepe, far, rebuild);
-                    else reverse_core<N, P, 1>(gt + q * TILE, xt + q * TILE, t, vacc, r, iv, onepe, far, rebuild);
                 }
-                reverse_finish<N, P>(vacc, tbase + (ax ? 32u : 0u), tab_m + o, h_scale[s], h_t[s], smooth, h_clamped[s] != 0);
+                if (ax == 0) reverse_core<N, P, 0>(gt, xt, t, vacc, r, iv, onepe, far, rebuild);
+                else reverse_core<N, P, 1>(gt, xt, t, vacc, r, iv, onepe, far, rebuild);
+                reverse_finish<N, P>(vacc, tbase + (ax ? 32u : 0u), tab_m + o, sw_scale, sw_t, smooth, sw_clamped);
             }
             if (CHAN && d.chan_op == 1) {
                 // adjoint of the pre-step mix: needs g (rows) and the mix INPUT = state before this step
-                state_to_xt(step - 1);
-                adjoint_chan();
+                if (step > 0) {
+                    x_wait(xb ^ 1);
+                } else {
+                    bar();
+                    PlaneIO<N, P>::to_tile(a.u, xs, item, t.c, C, d.B, t.tid_c);
+                }
+                adjoint_chan(gxs);
             }
+            xb ^= 1;
         }
         touch_g(2);
-        if (a.need_gin) {
-#pragma unroll 1
-            for (int q = 0; q < Q; ++q)
-                PlaneIO<N, P>::from_tile(gt + q * TILE, a.gin, item * Q + q, t.c, C, d.B, t.tid_c, d.skip ? a.gout : nullptr,
-                                         sig, 1.0f);
+        if (a.need_gin)
+            PlaneIO<N, P>::from_tile(gt, a.gin, item, t.c, C, d.B, t.tid_c, d.skip ? a.gout : nullptr, sig, 1.0f);
+        if (defer_cross && next_item < a.nitems) {
+            __syncthreads();   // the layer input in the spare buffer has been consumed
+            x_fill(xb, next_item, d.steps - 1);
         }
-        // the next item overwrites both tile sets with a block-wide pattern
-        __syncthreads();
+        if (GDB) gb ^= 1;
     }
 
     // ------------------------------ partials: TMEM -> sum over the P pairs -> global [row][col]
@@ -971,7 +1075,7 @@ constexpr int kMaxQ = 4;
 
 struct Plan {
     int P, Qf, Qb, threads, wpc, ngroups, tmem_cols;
-    size_t tile_bytes, ck_slot;   // one tile (P pairs of one channel); f2 per (group, step)
+    size_t tile_bytes, scr_slot;   // one tile (P pairs of one channel); f2 per sweep output of a block (exact mode)
 };
 
 template <int N, int P>
@@ -980,7 +1084,7 @@ static void fill_geo(const pde_adi_desc &d, Plan *p) {
     p->wpc = G::WPC;
     p->threads = G::WPC * 32 * d.C;
     p->tile_bytes = (size_t)G::TILE * sizeof(float);
-    p->ck_slot = (size_t)G::H * p->threads;
+    p->scr_slot = (size_t)G::H * p->threads;
 }
 
 static int make_plan(const pde_adi_desc &d, Plan *p) {
@@ -1008,7 +1112,6 @@ static int make_plan(const pde_adi_desc &d, Plan *p) {
     };
     p->Qf = pick(p->P == 4 ? 4 : 2, (size_t)d.C, "PDE_B200_SPLIT_QF");
     p->Qb = 1;   // measured: the backward kernel gains nothing from sharing coefficient loads
-    { const int f = env_int("PDE_B200_SPLIT_QB", 0); if (f == 1 || f == 2) p->Qb = f; }
     const int warps = p->threads / 32;
     const int blocks4 = (warps + 3) / 4;
     p->tmem_cols = blocks4 * 64 <= 64 ? 64 : (blocks4 * 64 <= 128 ? 128 : (blocks4 * 64 <= 256 ? 256 : 512));
@@ -1018,24 +1121,20 @@ static int make_plan(const pde_adi_desc &d, Plan *p) {
 size_t checkpoint_bytes(const pde_adi_desc &d) {
     Plan p;
     if (!supported(d) || make_plan(d, &p) != PDE_OK) return 0;
+    // one tile image per (group, step, channel)
     const size_t groups = (size_t)((p.ngroups + kMaxQ - 1) / kMaxQ) * kMaxQ;
-    return groups * d.steps * p.ck_slot * 8 + 256;
+    return groups * d.steps * d.C * p.tile_bytes + 256;
 }
 
-template <int N, int P, int Q>
-static const void *bwd_ptr(bool chan) {
-    if (P == 4) return reinterpret_cast<const void *>(sbwd_kernel<N, P, Q, false>);
-    return chan ? reinterpret_cast<const void *>(sbwd_kernel<N, 2, Q, true>)
-                : reinterpret_cast<const void *>(sbwd_kernel<N, 2, Q, false>);
-}
 template <int N>
-static const void *bwd_kernel_n(int P, int Q, bool chan) {
-    if (P == 4) return Q == 2 ? bwd_ptr<N, 4, 2>(false) : bwd_ptr<N, 4, 1>(false);
-    return Q == 2 ? bwd_ptr<N, 2, 2>(chan) : bwd_ptr<N, 2, 1>(chan);
+static const void *bwd_kernel_n(int P, bool chan) {
+    if (P == 4) return reinterpret_cast<const void *>(sbwd_kernel<N, 4, false>);
+    return chan ? reinterpret_cast<const void *>(sbwd_kernel<N, 2, true>)
+                : reinterpret_cast<const void *>(sbwd_kernel<N, 2, false>);
 }
-static const void *bwd_kernel_for(int N, int P, int Q, bool chan) {
-    if (N == 28) return bwd_kernel_n<28>(P, Q, chan);
-    if (N == 32) return bwd_kernel_n<32>(P, Q, chan);
+static const void *bwd_kernel_for(int N, int P, bool chan) {
+    if (N == 28) return bwd_kernel_n<28>(P, chan);
+    if (N == 32) return bwd_kernel_n<32>(P, chan);
     return nullptr;
 }
 template <int N>
@@ -1061,9 +1160,10 @@ static int plan_bwd_grid(const pde_adi_desc &d, const Plan &p, BwdLaunch *b) {
     DeviceProps props;
     int rc = query_props(&props);
     if (rc) return rc;
-    const void *kern = bwd_kernel_for(d.N, p.P, p.Qb, d.chan_op != 0);
+    const void *kern = bwd_kernel_for(d.N, p.P, d.chan_op != 0);
     if (!kern) return PDE_ERR_UNSUPPORTED;
-    b->smem = (size_t)2 * d.C * p.Qb * p.tile_bytes;
+    // x tile sets double buffered, g sets too for P == 4, two coefficient stages of two tables
+    b->smem = (size_t)(p.P >= 4 ? 4 : 3) * d.C * p.tile_bytes + (size_t)4 * d.C * ((d.N / 2 + 3) / 4) * d.N * 2 * 16;
     if (b->smem > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
     PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     // residency from first principles (the occupancy calculator answers 1 block / SM for kernels
@@ -1084,10 +1184,10 @@ static int plan_bwd_grid(const pde_adi_desc &d, const Plan &p, BwdLaunch *b) {
     if (cap_env > 0 && cap_env < occ) occ = cap_env;
     if (occ < 1) occ = 1;
     b->occ = occ;
-    b->nitems = (p.ngroups + p.Qb - 1) / p.Qb;
+    b->nitems = p.ngroups;
     if (env_int("PDE_B200_DEBUG", 0))
-        fprintf(stderr, "[pde_b200] split bwd plan: N=%d C=%d P=%d Q=%d threads=%d smem=%zu regs=%d occ=%d tmem=%d\n", d.N,
-                d.C, p.P, p.Qb, p.threads, b->smem, fa.numRegs, occ, p.tmem_cols);
+        fprintf(stderr, "[pde_b200] split bwd plan: N=%d C=%d P=%d threads=%d smem=%zu regs=%d occ=%d tmem=%d\n", d.N,
+                d.C, p.P, p.threads, b->smem, fa.numRegs, occ, p.tmem_cols);
     const int cap = props.sm_count * occ;
     b->grid = b->nitems < cap ? b->nitems : cap;
     if (b->grid < 1) b->grid = 1;
@@ -1100,7 +1200,7 @@ struct WsLayout {
 };
 
 static void ws_layout(const pde_adi_desc &d, const Plan &p, int grid, WsLayout *w) {
-    w->scratch_floats = (size_t)grid * p.Qb * 2 * p.ck_slot * 2;   // two sweep outputs per block and group (exact mode)
+    w->scratch_floats = (size_t)grid * 2 * p.scr_slot * 2;   // two sweep outputs per block (exact mode)
     w->nsets_maps = grid * d.C;
     w->nsets_small = grid * p.wpc * d.C;
     w->maps_floats = (size_t)w->nsets_maps * 4 * d.N * d.N;
@@ -1194,7 +1294,7 @@ int backward(const pde_adi_desc &d, const char *tables, const float *u, const fl
     a.part_maps = ws + w.scratch_floats;
     a.part_chan = a.part_maps + w.maps_floats;
     a.part_skip = a.part_chan + w.chan_floats;
-    const void *kern = bwd_kernel_for(d.N, p.P, p.Qb, d.chan_op != 0);
+    const void *kern = bwd_kernel_for(d.N, p.P, d.chan_op != 0);
     void *params[] = {&a};
     PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(b.grid), dim3(p.threads), params, b.smem, st));
     rc = cuda_last_error();

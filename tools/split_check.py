@@ -58,7 +58,7 @@ def parity():
 
 
 def timing():
-    variants = [("1", "", ""), ("0", "", ""), ("0", "4", "1"), ("0", "2", "1"), ("0", "1", "1")]
+    variants = [("1", "", ""), ("0", "", ""), ("0", "2", "")]
     for name, B in (("fashion", 262144), ("mnist", 131072), ("cifar10_pde1", 65536)):
         kind, ctor, _, _ = bench.LAYERS[name]
         c = K.case("t", kind, B=B, perturb=False, **ctor)

@@ -1169,7 +1169,9 @@ extern "C" int pde_adi_forward_train(const pde_adi_desc *d, const void *tables, 
     if (d->skip && !skipw) return PDE_ERR_INVALID;
     if (!aligned16(u) || !aligned16(out)) return PDE_ERR_INVALID;
     if (d->B == 0) return PDE_OK;
-    if (split::supported(*d))
+    // with checkpoints to write: the half-line kernel (its backward twin needs them); plain
+    // inference: the whole-line kernel below, which is the faster forward
+    if (ckpt && split::supported(*d))
         return split::forward(*d, static_cast<const char *>(tables), u, chan, skipw, out, static_cast<float *>(ckpt),
                               static_cast<cudaStream_t>(stream));
     DeviceProps props;

@@ -402,53 +402,109 @@ constexpr int max_threads() { return P >= 4 ? SG<N, P>::WPC * 32 : SG<N, P>::WPC
 // The closing half sweep of a Strang step and the opening one of the next run back to back on
 // the registers (same orientation).
 // ------------------------------------------------------------------------------------------
+// planes (u or gout) of group `grp` -> tile, asynchronously (LDGSTS): every 4-byte cell goes straight from
+// global memory to its slot in the interleaved / mirrored tile, no registers, no wait.  Samples
+// beyond the batch are zero-filled.  Completion: cp_async_wait_all() + a barrier.
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, bool valid) {
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int N, int P>
+__device__ __forceinline__ void planes_to_tile_async(const float *__restrict__ g, float *tile, int grp, int c, int C,
+                                                     int B, int tid_c) {
+    using IO = PlaneIO<N, P>;
+#pragma unroll
+    for (int it = 0; it < IO::IT; ++it) {
+        const int idx = tid_c + it * IO::NTHR;
+        if (idx < P * IO::F2) {
+            const int pp = idx % P, f = idx / P;
+            const int ba = (grp * P + pp) * 2, bb = ba + 1;
+            const bool va = ba < B, vb = bb < B;
+            const float *sa = g + ((size_t)(va ? ba : 0) * C + c) * (N * N) + 2 * f;
+            const float *sb = g + ((size_t)(vb ? bb : 0) * C + c) * (N * N) + 2 * f;
+            bool hc;
+            float *dst = tile + IO::tile_off(f, pp, hc);
+            // chunk = {cell lo: a, b; cell hi: a, b}; in the far half the two columns swap
+            cp_async4(dst + (hc ? 2 : 0), sa, va);
+            cp_async4(dst + (hc ? 3 : 1), sb, vb);
+            cp_async4(dst + (hc ? 0 : 2), sa + 1, va);
+            cp_async4(dst + (hc ? 1 : 3), sb + 1, vb);
+        }
+    }
+}
+
 template <int N, int P, int Q>
 __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kernel(const Args a) {
     using G = SG<N, P>;
     constexpr int H = G::H, TILE = G::TILE, HQ4 = 4 * G::HQ;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t cbar[2];
+    __shared__ short h_slot[PDE_MAX_SWEEPS];
     const pde_adi_desc &d = a.d;
     const Lane t = make_lane<N, P>();
     const int C = d.C, nthr = blockDim.x;
     const bool far = t.h == 1;
-    float *my = smem + (size_t)t.c * Q * TILE;   // this channel's Q tiles
+    const int SET = C * Q * TILE;   // floats per tile set: Q groups of every channel
+    // coefficient stage: 1/pivot and r/pivot of one sweep (all channels), double buffered, filled
+    // by TMA one phase ahead
+    const int CT = C * G::HQ * N * 2 * 4;
+    float *cbuf = smem + SET;
     const size_t T = stab_floats_per_table(d);
-    const float4 *tinv = reinterpret_cast<const float4 *>(a.stab + T);
-    const float4 *te = reinterpret_cast<const float4 *>(a.stab + 2 * T);
     float sig = 0.0f;
     if (d.skip) sig = 1.0f / (1.0f + expf(-__ldg(a.skipw)));
     const float om = 1.0f - sig;
-    const size_t plane = (size_t)N * N;
     const int sps = a.sps, S = a.S;
-    __shared__ short h_slot[PDE_MAX_SWEEPS];
     {
         const Header *hdr = reinterpret_cast<const Header *>(a.tables);
         for (int i = threadIdx.x; i < S; i += nthr) h_slot[i] = hdr->slot[i];
     }
+    if (threadIdx.x == 0) {
+        mbar_init(&cbar[0], 1);
+        mbar_init(&cbar[1], 1);
+        mbar_fence_init();
+    }
     __syncthreads();
+    uint32_t cphase = 0u;
+    auto c_fill = [&](int b, int s) {   // call after a barrier that ends every read of buffer b
+        if (threadIdx.x == 0) {
+            fence_proxy_async();
+            const uint32_t bytes = (uint32_t)(CT * sizeof(float));
+            mbar_expect_tx(&cbar[b], 2 * bytes);
+            tma_load_1d(cbuf + (size_t)(2 * b) * CT, a.stab + T + (size_t)s * CT, bytes, &cbar[b]);
+            tma_load_1d(cbuf + (size_t)(2 * b + 1) * CT, a.stab + 2 * T + (size_t)s * CT, bytes, &cbar[b]);
+        }
+    };
+    const size_t plane = (size_t)N * N;
+    int cb = 0;
+    if (blockIdx.x < a.nitems) c_fill(0, 0);
 
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const int next_item = item + gridDim.x;
+        float *set = smem;
+        float *my = set + (size_t)t.c * Q * TILE;   // this channel's Q tiles
         if (threadIdx.x == 0) {   // the next item's planes start their trip from HBM to L2 now
-            const long long nb = (long long)(item + gridDim.x) * Q * 2 * P;
+            const long long nb = (long long)next_item * Q * 2 * P;
             if (nb < d.B) {
                 const long long ns = (d.B - nb) < 2 * P * Q ? (d.B - nb) : 2 * P * Q;
                 prefetch_region_l2(a.u + (size_t)nb * C * plane, (size_t)ns * C * plane * sizeof(float));
             }
         }
+        __syncthreads();   // the previous item's output has left the tiles
 #pragma unroll 1
         for (int q = 0; q < Q; ++q) PlaneIO<N, P>::to_tile(a.u, my + q * TILE, item * Q + q, t.c, C, d.B, t.tid_c);
-        int cur_ax = 2;   // orientation of the last phase (2: block-wide pattern)
         // u <- M u over the channels of every group (rows); leaves the tiles in row orientation
         auto mix_phase = [&]() {
             __syncthreads();
 #pragma unroll 1
             for (int q = 0; q < Q; ++q) {
                 f2 x[H];
-                mix_rows<N, P>(smem + q * TILE, Q * TILE, C, a.chan + t.c * C, 1, t, x);
+                mix_rows<N, P>(set + q * TILE, Q * TILE, C, a.chan + t.c * C, 1, t, x);
                 __syncthreads();
                 if (t.active) st_half<N, P, 0>(my + q * TILE, t, x);
             }
-            cur_ax = 0;
         };
         int s = 0;
         while (s < S) {
@@ -456,56 +512,61 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
             if (k == 0 && d.chan_op == 1) mix_phase();
             // the next sweep has the same orientation and (Strang: same time, time step, spacing) the same tables
             const bool fuse = sps == 3 && k == 2 && s + 1 < S && d.chan_op == 0 && h_slot[s] == h_slot[s + 1];
-            float iv[HQ4], e[HQ4];
-            ld_coef<N, P>(tinv + tab_off<N, P>(s, C, t), iv);
-            ld_coef<N, P>(te + tab_off<N, P>(s, C, t), e);
-            if (cur_ax != ax) {
-                __syncthreads();
-                cur_ax = ax;
+            const int s_next = s + (fuse ? 2 : 1);
+            // phase boundary: the tiles change orientation and every thread has taken its coefficients
+            // out of the other stage
+            __syncthreads();
+            {
+                const int ns = s_next < S ? s_next : (next_item < a.nitems ? 0 : -1);
+                if (ns >= 0) c_fill(cb ^ 1, ns);
             }
-            constexpr int NP = 1;   // groups advanced together (2 measured slower: 128 registers, spills)
-#pragma unroll 1
-            for (int q = 0; q < Q; q += NP) {
-                float *tile = my + q * TILE;
-                f2 x[NP][H];
+            mbar_wait(&cbar[cb], (cphase >> cb) & 1u);
+            cphase ^= 1u << cb;
+            float iv[HQ4], e[HQ4];
+            {
+                const float4 *ci = reinterpret_cast<const float4 *>(cbuf + (size_t)(2 * cb) * CT) + t.tab;
+                const float4 *ce = reinterpret_cast<const float4 *>(cbuf + (size_t)(2 * cb + 1) * CT) + t.tab;
 #pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    if (ax == 0) ld_half<N, P, 0>(tile + p * TILE, t, x[p]);
-                    else ld_half<N, P, 1>(tile + p * TILE, t, x[p]);
+                for (int q = 0; q < G::HQ; ++q) {
+                    const float4 a4 = ci[q * G::QS], b4 = ce[q * G::QS];
+                    iv[4 * q] = a4.x; iv[4 * q + 1] = a4.y; iv[4 * q + 2] = a4.z; iv[4 * q + 3] = a4.w;
+                    e[4 * q] = b4.x; e[4 * q + 1] = b4.y; e[4 * q + 2] = b4.z; e[4 * q + 3] = b4.w;
                 }
-                solve<N, P, NP>(x, iv, e, far);
+            }
+            cb ^= 1;
+#pragma unroll 1
+            for (int q = 0; q < Q; ++q) {
+                float *tile = my + q * TILE;
+                f2 x[1][H];
+                if (ax == 0) ld_half<N, P, 0>(tile, t, x[0]);
+                else ld_half<N, P, 1>(tile, t, x[0]);
+                solve<N, P, 1>(x, iv, e, far);
                 if (k == sps - 1 && a.ckpt && t.active) {
                     // state after the last sweep of the step, written as a tile image: the backward
                     // kernel brings it back with one bulk copy per step
+                    float *ck = a.ckpt + (((size_t)(item * Q + q) * d.steps + step) * C + t.c) * TILE;
+                    if (ax == 0) {
 #pragma unroll
-                    for (int p = 0; p < NP; ++p) {
-                        float *ck = a.ckpt + (((size_t)(item * Q + q + p) * d.steps + step) * C + t.c) * TILE;
-                        if (ax == 0) {
-#pragma unroll
-                            for (int m = 0; m < G::HCH; ++m) {
-                                ulonglong2 v;
-                                v.x = x[p][2 * m].v;
-                                v.y = x[p][2 * m + 1].v;
-                                __stcs(reinterpret_cast<ulonglong2 *>(ck + t.b0 + m * P * 4), v);
-                            }
-                        } else {
-#pragma unroll
-                            for (int kk = 0; kk < H; ++kk)
-                                __stcs(reinterpret_cast<unsigned long long *>(ck + t.b1 + kk * G::RS), x[p][kk].v);
+                        for (int m = 0; m < G::HCH; ++m) {
+                            ulonglong2 v;
+                            v.x = x[0][2 * m].v;
+                            v.y = x[0][2 * m + 1].v;
+                            __stcs(reinterpret_cast<ulonglong2 *>(ck + t.b0 + m * P * 4), v);
                         }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < H; ++kk)
+                            __stcs(reinterpret_cast<unsigned long long *>(ck + t.b1 + kk * G::RS), x[0][kk].v);
                     }
                 }
-                if (fuse) solve<N, P, NP>(x, iv, e, far);
+                if (fuse) solve<N, P, 1>(x, iv, e, far);
                 if (t.active) {
-#pragma unroll
-                    for (int p = 0; p < NP; ++p) {
-                        if (ax == 0) st_half<N, P, 0>(tile + p * TILE, t, x[p]);
-                        else st_half<N, P, 1>(tile + p * TILE, t, x[p]);
-                    }
+                    if (ax == 0) st_half<N, P, 0>(tile, t, x[0]);
+                    else st_half<N, P, 1>(tile, t, x[0]);
                 }
             }
             if (k == sps - 1 && d.chan_op == 2) mix_phase();
-            s += fuse ? 2 : 1;
+            s = s_next;
         }
         __syncthreads();
         if (a.out) {
@@ -514,7 +575,6 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
                 PlaneIO<N, P>::from_tile(my + q * TILE, a.out, item * Q + q, t.c, C, d.B, t.tid_c, d.skip ? a.u : nullptr,
                                          sig, om);
         }
-        __syncthreads();
     }
 }
 
@@ -680,40 +740,6 @@ __device__ __forceinline__ void chan_adjoint(float *ggt, const float *gxt, int c
     mix_rows<N, P>(ggt, cstride, C, mat + t.c, C, t, gn);
     __syncthreads();
     if (t.active) st_half<N, P, 0>(ggt + (size_t)t.c * cstride, t, gn);
-}
-
-// gout planes of group `grp` -> tile, asynchronously (LDGSTS): every 4-byte cell goes straight from
-// global memory to its slot in the interleaved / mirrored tile, no registers, no wait.  Samples
-// beyond the batch are zero-filled.  Completion: cp_async_wait_all() + a barrier.
-__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, bool valid) {
-    const int n = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int N, int P>
-__device__ __forceinline__ void planes_to_tile_async(const float *__restrict__ g, float *tile, int grp, int c, int C,
-                                                     int B, int tid_c) {
-    using IO = PlaneIO<N, P>;
-#pragma unroll
-    for (int it = 0; it < IO::IT; ++it) {
-        const int idx = tid_c + it * IO::NTHR;
-        if (idx < P * IO::F2) {
-            const int pp = idx % P, f = idx / P;
-            const int ba = (grp * P + pp) * 2, bb = ba + 1;
-            const bool va = ba < B, vb = bb < B;
-            const float *sa = g + ((size_t)(va ? ba : 0) * C + c) * (N * N) + 2 * f;
-            const float *sb = g + ((size_t)(vb ? bb : 0) * C + c) * (N * N) + 2 * f;
-            bool hc;
-            float *dst = tile + IO::tile_off(f, pp, hc);
-            // chunk = {cell lo: a, b; cell hi: a, b}; in the far half the two columns swap
-            cp_async4(dst + (hc ? 2 : 0), sa, va);
-            cp_async4(dst + (hc ? 3 : 1), sb, vb);
-            cp_async4(dst + (hc ? 0 : 2), sa + 1, va);
-            cp_async4(dst + (hc ? 1 : 3), sb + 1, vb);
-        }
-    }
 }
 
 // Backward kernel.  One group of P sample pairs (all channels) per block iteration; both tile sets
@@ -1066,7 +1092,14 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
 bool supported(const pde_adi_desc &d) {
     if (env_int("PDE_B200_ADI_LEGACY", 0)) return false;
     if (d.steps < 1 || d.B < 1 || d.C > 3) return false;
-    return d.N == 28 || d.N == 32;
+    if (d.N != 28 && d.N != 32) return false;
+    // Below two groups of two sample pairs per SM the call is latency bound either way: stay with
+    // the whole-line kernels (one pair per warp spreads a small batch over more SMs, one launch
+    // less).  PDE_B200_ADI_SPLIT=1 / PDE_B200_SPLIT_P force the half-line kernels (tests).
+    if (env_int("PDE_B200_ADI_SPLIT", 0) || env_int("PDE_B200_SPLIT_P", 0)) return true;
+    DeviceProps props;
+    if (query_props(&props) != PDE_OK) return false;
+    return (d.B + 3) / 4 >= 2 * props.sm_count;
 }
 
 size_t table_floats(const pde_adi_desc &d) { return 4 * stab_floats_per_table(d); }
@@ -1105,7 +1138,7 @@ static int make_plan(const pde_adi_desc &d, Plan *p) {
     // groups per block: as many as still leave two blocks of work per SM (and fit shared memory)
     auto pick = [&](int qmax, size_t tiles_per_group, const char *env) {
         int q = qmax;
-        while (q > 1 && ((p->ngroups + q - 1) / q < 2 * sm || (size_t)q * tiles_per_group * p->tile_bytes > 110 * 1024)) q >>= 1;
+        while (q > 1 && ((p->ngroups + q - 1) / q < 2 * sm || (size_t)q * tiles_per_group * p->tile_bytes > 101 * 1024)) q >>= 1;
         const int forced = env_int(env, 0);
         if (forced == 1 || forced == 2 || (forced == 4 && qmax == 4)) q = forced;
         return q;
@@ -1246,7 +1279,8 @@ int forward(const pde_adi_desc &d, const char *tables, const float *u, const flo
     if (rc) return rc;
     const void *kern = fwd_kernel_for(d.N, p.P, p.Qf);
     if (!kern) return PDE_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)d.C * p.Qf * p.tile_bytes;
+    // Qf groups of tiles, two coefficient stages of two tables
+    const size_t smem = (size_t)d.C * p.Qf * p.tile_bytes + (size_t)4 * d.C * ((d.N / 2 + 3) / 4) * d.N * 2 * 16;
     if (smem > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
     PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;

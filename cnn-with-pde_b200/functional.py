@@ -5,6 +5,8 @@ coefficient tables of the call): the backward kernels rebuild the forward states
 """
 from __future__ import annotations
 
+import os
+
 from ctypes import byref
 from dataclasses import dataclass
 
@@ -86,7 +88,11 @@ class _AdiFunction(torch.autograd.Function):
             # under autograd the forward kernel also writes the state at the end of every step for
             # the backward kernel (0 bytes when the configuration is served by the kernels that
             # rebuild the trajectory on-chip)
-            ck_bytes = L.pde_adi_checkpoint_bytes(byref(d)) if any(ctx.needs_input_grad) else 0
+            # PDE_B200_NO_CKPT=1 trades them for a recomputation inside pde_adi_backward (saves
+            # num_steps x the input in memory between forward and backward)
+            # (needs_input_grad ignores torch.no_grad(), hence the explicit check)
+            want_ck = torch.is_grad_enabled() and any(ctx.needs_input_grad) and not os.environ.get("PDE_B200_NO_CKPT")
+            ck_bytes = L.pde_adi_checkpoint_bytes(byref(d)) if want_ck else 0
             ckpt = _bytes(ck_bytes, u.device) if ck_bytes else None
             _cabi.check(L.pde_adi_forward_train(byref(d), _ptr(tables), _ptr(u), _ptr(chan_c), _ptr(skip_c), _ptr(out),
                                                 _ptr(ckpt), _stream()), "pde_adi_forward_train")

@@ -128,3 +128,78 @@ def test_cuda_rejects_cpu_tensors_and_bad_shapes():
         layer(torch.zeros(2, 1, 28, 28))
     with pytest.raises(ValueError):
         layer(torch.zeros(2, 3, 28, 28, device="cuda"))
+
+
+# ------------------------------------------------------------------ half-line (split) kernels
+_SPLIT_CASES = [
+    K.case("split_fashion", "fashion", B=9),
+    K.case("split_mnist", "mnist", B=5),
+    K.case("split_cifar10_pde2", "cifar10", B=3, **K.SCRIPT_INSTANCES["cifar10_pde2"]),
+    K.case("split_cifar2", "cifar2", B=5, **K.SCRIPT_INSTANCES["cifar2_diffusion1"]),
+    K.case("split_svhn", "svhn", B=5, **K.SCRIPT_INSTANCES["svhn"]),
+]
+
+
+@pytest.mark.parametrize("pairs,qf", [("2", "1"), ("2", "2"), ("4", "4"), ("4", "1")], ids=lambda v: str(v))
+def test_cuda_split_kernel_variants(monkeypatch, pairs, qf):
+    """28x28 and 32x32 planes take the half-line kernels (adi_split.cu); every pairs-per-group /
+    groups-per-block instantiation must agree with the oracle (the defaults depend on the batch)."""
+    monkeypatch.setenv("PDE_B200_SPLIT_P", pairs)
+    monkeypatch.setenv("PDE_B200_SPLIT_QF", qf)
+    for c in _SPLIT_CASES:
+        params, io = K.make_params(c), K.make_io(c)
+        want = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+        got = runners.run_cuda(c, params=params, io=io)
+        _assert_close(got, want, TOL, f"{c.name} P={pairs} Qf={qf}")
+
+
+@pytest.mark.parametrize("env", ["PDE_B200_NO_CKPT", "PDE_B200_ADI_LEGACY"])
+def test_cuda_backward_without_saved_checkpoints(monkeypatch, env):
+    """pde_adi_backward without checkpoints from the forward call (it makes them in its workspace),
+    and the whole-line kernels of adi.cu on the sizes the half-line kernels normally serve."""
+    monkeypatch.setenv(env, "1")
+    monkeypatch.setenv("PDE_B200_ADI_SPLIT", "1")   # small batches default to the whole-line kernels
+    for c in _SPLIT_CASES + [K.case("split_fashion_dt5", "fashion", B=8, perturb=False, dt=5.0)]:
+        params, io = K.make_params(c), K.make_io(c)
+        want = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+        got = runners.run_cuda(c, params=params, io=io)
+        _assert_close(got, want, TOL, f"{c.name} {env}")
+
+
+def test_cuda_split_large_batch_properties():
+    """Batch large enough for four pairs per group and several groups per block: adjoint identity
+    <J v, w> = <v, J^T w> and linearity, fashion layer (smoothing, dt = 0.3)."""
+    import torch
+    c = K.case("prop_fashion", "fashion", B=8200)
+    layer = runners.make_cuda_layer(c)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    v = torch.randn(c.B, *c.shape, device="cuda", generator=gen)
+    w = torch.randn(c.B, *c.shape, device="cuda", generator=gen)
+    x = v.clone().requires_grad_(True)
+    y = layer(x)
+    (gin,) = torch.autograd.grad(y, x, w)
+    lhs = (y.double() * w.double()).sum().item()
+    rhs = (v.double() * gin.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+    with torch.no_grad():
+        y_eval = layer(v)            # inference takes the whole-line forward kernel
+        y2 = layer(2.5 * v)
+    assert runners.rel_l2(y_eval.cpu().numpy(), y.detach().cpu().numpy()) <= 2e-6
+    assert runners.rel_l2(y2.cpu().numpy(), 2.5 * y.detach().cpu().numpy()) <= 2e-6
+    # the first and the last sample of the batch against the oracle (ragged last group: 8200 = 1025 * 8)
+    params = K.make_params(c)
+    for sl in (slice(0, 2), slice(c.B - 2, c.B)):
+        c2 = K.case("prop_fashion_2", "fashion", B=2)
+        want = runners.run_oracle(c2, params=params, io=(v[sl].cpu().numpy(), w[sl].cpu().numpy()), dtype=np.float32,
+                                  forward_only=True)
+        assert runners.rel_l2(y[sl].detach().cpu().numpy(), want["y"]) <= TOL
+
+
+@pytest.mark.parametrize("c", [c for c in K.GOLDEN_CASES if c.kind in ("mnist", "fashion", "svhn", "cifar10", "cifar2")],
+                         ids=lambda c: c.name)
+def test_cuda_split_matches_reference_fixture(monkeypatch, c):
+    """The half-line kernels against the fixtures generated from the unmodified reference."""
+    monkeypatch.setenv("PDE_B200_ADI_SPLIT", "1")
+    params, io, ref = golden_io.load(c)
+    got = runners.run_cuda(c, params=params, io=io)
+    _assert_close(got, ref, TOL, c.name + " (half-line kernels) vs reference fixture")

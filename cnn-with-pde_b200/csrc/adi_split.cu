@@ -427,11 +427,17 @@ __device__ __forceinline__ void planes_to_tile_async(const float *__restrict__ g
             const float *sb = g + ((size_t)(vb ? bb : 0) * C + c) * (N * N) + 2 * f;
             bool hc;
             float *dst = tile + IO::tile_off(f, pp, hc);
-            // chunk = {cell lo: a, b; cell hi: a, b}; in the far half the two columns swap
-            cp_async4(dst + (hc ? 2 : 0), sa, va);
-            cp_async4(dst + (hc ? 3 : 1), sb, vb);
-            cp_async4(dst + (hc ? 0 : 2), sa + 1, va);
-            cp_async4(dst + (hc ? 1 : 3), sb + 1, vb);
+            // chunk = {cell lo: a, b; cell hi: a, b}; in the far half the two columns swap.  The four
+            // 4-byte copies of a lane start at a component that rotates with the chunk index, so that the
+            // 32 lanes of one instruction hit 32 different banks (chunks are 16 floats apart for P == 4)
+            const int rot = (f >> 1) & 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int comp = (k + rot) & 3;               // 0: a lo-column, 1: b lo-column, 2: a hi, 3: b hi
+                const bool isb = comp & 1;
+                const float *src = (isb ? sb : sa) + (comp >> 1);
+                cp_async4(dst + (hc ? (comp ^ 2) : comp), src, isb ? vb : va);
+            }
         }
     }
 }

@@ -64,7 +64,7 @@ class AdiConfig:
 class _AdiFunction(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg: AdiConfig):
+    def forward(ctx, u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg: AdiConfig, grad_mode: bool = True):
         _require_cuda(u, "PDE layer input")
         L = _cabi.lib()
         u = u.contiguous()
@@ -90,8 +90,9 @@ class _AdiFunction(torch.autograd.Function):
             # rebuild the trajectory on-chip)
             # PDE_B200_NO_CKPT=1 trades them for a recomputation inside pde_adi_backward (saves
             # num_steps x the input in memory between forward and backward)
-            # (needs_input_grad ignores torch.no_grad(), hence the explicit check)
-            want_ck = torch.is_grad_enabled() and any(ctx.needs_input_grad) and not os.environ.get("PDE_B200_NO_CKPT")
+            # (needs_input_grad ignores torch.no_grad() and grad mode is always off inside forward():
+            # the caller passes the mode it saw)
+            want_ck = grad_mode and any(ctx.needs_input_grad) and not os.environ.get("PDE_B200_NO_CKPT")
             ck_bytes = L.pde_adi_checkpoint_bytes(byref(d)) if want_ck else 0
             ckpt = _bytes(ck_bytes, u.device) if ck_bytes else None
             _cabi.check(L.pde_adi_forward_train(byref(d), _ptr(tables), _ptr(u), _ptr(chan_c), _ptr(skip_c), _ptr(out),
@@ -131,11 +132,11 @@ class _AdiFunction(torch.autograd.Function):
                                                  _ptr(gmaps[3]), _ptr(gchan), _ptr(gskip), _ptr(ws), ws_bytes,
                                                  _stream()), "pde_adi_backward_saved")
         gmaps = [g.reshape(s) for g, s in zip(gmaps, ctx.param_shapes)]
-        return (gin, gmaps[0], gmaps[1], gmaps[2], gmaps[3], gchan, gskip, None)
+        return (gin, gmaps[0], gmaps[1], gmaps[2], gmaps[3], gchan, gskip, None, None)
 
 
 def adi_layer(u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg: AdiConfig):
-    return _AdiFunction.apply(u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg)
+    return _AdiFunction.apply(u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg, torch.is_grad_enabled())
 
 
 # ------------------------------------------------------------------- explicit, frozen ghost ring

@@ -16,6 +16,8 @@ named after its script.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -133,9 +135,35 @@ class MultiScaleExtractor(nn.Module):
         self.attention3 = SpatialAttention(channels, input_size)
         self.combine_weights = nn.Parameter(torch.ones(3) / 3)
 
+    # The three branches read the same input and are independent until the combine: at the script's
+    # batch (512) one PDE layer fills less than one wave of the GPU, so the branches run on three
+    # streams (fork / join around the current stream; captured as parallel branches of a CUDA graph;
+    # autograd replays each branch's backward on its own stream).  SURVEY section 8(f) rank 1.
+    concurrent_branches = True
+
+    def _side_streams(self, device):
+        cache = self.__dict__.setdefault("_streams", {})
+        if device not in cache:
+            cache[device] = [torch.cuda.Stream(device=device) for _ in range(2)]
+        return cache[device]
+
     def forward(self, x):
-        feats = [att(pde(x)) for pde, att in ((self.pde1, self.attention1), (self.pde2, self.attention2),
-                                              (self.pde3, self.attention3))]
+        branches = ((self.pde1, self.attention1), (self.pde2, self.attention2), (self.pde3, self.attention3))
+        if x.is_cuda and self.concurrent_branches and not os.environ.get("PDE_B200_SERIAL_BRANCHES"):
+            cur = torch.cuda.current_stream(x.device)
+            sides = self._side_streams(x.device)
+            for s in sides:
+                s.wait_stream(cur)          # fork: x is ready
+            feats = [None, None, None]
+            for i, (pde, att) in enumerate(branches[1:], start=1):
+                with torch.cuda.stream(sides[i - 1]):
+                    feats[i] = att(pde(x))
+            feats[0] = branches[0][1](branches[0][0](x))
+            for i, s in enumerate(sides, start=1):
+                cur.wait_stream(s)          # join
+                feats[i].record_stream(cur)
+        else:
+            feats = [att(pde(x)) for pde, att in branches]
         w = F.softmax(self.combine_weights, dim=0)
         combined = w[0] * feats[0] + w[1] * feats[1] + w[2] * feats[2]
         return (combined, *feats)

@@ -88,13 +88,17 @@ class FlatGradSync:
 
 
 def make_optimizer(model: nn.Module, r: Recipe, capturable: bool):
+    # the scripts' AdamW recipe; on CUDA the fused implementation (one kernel per parameter group
+    # instead of ~30 multi-tensor launches per step; same update rule, capturable)
+    on_cuda = all(p.is_cuda for p in model.parameters())
+    extra = {"fused": True, "capturable": capturable} if on_cuda else {"capturable": capturable}
     if r.split_groups:
         coef = [p for n, p in model.named_parameters() if "alpha" in n or "beta" in n]
         rest = [p for n, p in model.named_parameters() if not ("alpha" in n or "beta" in n)]
         groups = [{"params": coef, "lr": r.lr, "weight_decay": 1e-6},
                   {"params": rest, "lr": r.lr * 0.5, "weight_decay": r.weight_decay}]
-        return torch.optim.AdamW(groups, capturable=capturable)
-    return torch.optim.AdamW(model.parameters(), lr=r.lr, weight_decay=r.weight_decay, capturable=capturable)
+        return torch.optim.AdamW(groups, **extra)
+    return torch.optim.AdamW(model.parameters(), lr=r.lr, weight_decay=r.weight_decay, **extra)
 
 
 def _dist_env():

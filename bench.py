@@ -76,6 +76,7 @@ class ClockSampler:
     def __init__(self, index=0, period=0.02):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
+        self.armed = False   # samples count only once the timed region has started (begin())
         self.max_mhz = None
         self._stop = threading.Event()
         self._thr = None
@@ -105,14 +106,20 @@ class ClockSampler:
         }
         while not self._stop.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                if self.armed:
+                    self.samples.append(mhz)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
             self._stop.wait(self.period)
+
+    def begin(self):
+        self.armed = True
+        return self
 
     def stop(self):
         self._stop.set()
@@ -173,10 +180,14 @@ def run_b200(args):
 
     # ---------------------------------------------------------------- kernel-only (HBM-resident)
     x = u.clone().requires_grad_(True)
+    # NVML is initialised and polling before the warm-up (its first calls take the driver's locks for
+    # milliseconds); samples count from begin() on
+    sampler = ClockSampler(index=local).start() if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step(x)
     sync_all()
-    sampler = ClockSampler(index=local).start() if rank == 0 else None
+    if sampler:
+        sampler.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

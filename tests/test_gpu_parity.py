@@ -203,3 +203,26 @@ def test_cuda_split_matches_reference_fixture(monkeypatch, c):
     params, io, ref = golden_io.load(c)
     got = runners.run_cuda(c, params=params, io=io)
     _assert_close(got, ref, TOL, c.name + " (half-line kernels) vs reference fixture")
+
+
+def test_cuda_split_shapes_and_tails(monkeypatch):
+    """Half-line kernels off the beaten path: two channels, 28 x 28 with three channels, batches that
+    leave the last group ragged, no grad_input, zero time coefficients crossing a clamp."""
+    monkeypatch.setenv("PDE_B200_ADI_SPLIT", "1")
+    todo = [
+        (K.case("split_c2", "cifar10", B=7, size=32, channels=2, dt=0.002, num_steps=3, dx=1.0, dy=1.0), True),
+        (K.case("split_svhn28", "svhn", B=5, size=28, channels=3, num_steps=3), True),
+        (K.case("split_cifar2_c1", "cifar2", B=11, size=32, channels=1, dt=0.002, num_steps=4), True),
+        (K.case("split_fashion_nogin", "fashion", B=13), False),
+        (K.case("split_cifar10_nogin", "cifar10", B=6, **K.SCRIPT_INSTANCES["cifar10_pde3"]), False),
+    ]
+    for forced in ("", "4"):
+        if forced:
+            monkeypatch.setenv("PDE_B200_SPLIT_P", forced)
+        for c, need_gin in todo:
+            params, io = K.make_params(c), K.make_io(c)
+            want = runners.run_oracle(c, params=params, io=io, dtype=np.float32, need_gin=need_gin)
+            got = runners.run_cuda(c, params=params, io=io, need_gin=need_gin)
+            if not need_gin:
+                assert got["gin"] is None
+            _assert_close(got, want, TOL, f"{c.name} P={forced or 'default'}")

@@ -35,6 +35,12 @@ def test_cabi_host_only_queries():
     n = lib.pde_adi_tables_bytes(ctypes.byref(d))
     # header + the tables of both implementations (28 cells / line; 2 halves x 16 padded cells / line)
     assert n == 4096 + 4 * (12 * 1 * 28 * 28) * 4 + 4 * (12 * 1 * 28 * 32) * 4
+    if not torch.cuda.is_available():
+        # without a device the half-line kernels cannot be planned: no checkpoints are asked for and
+        # the size queries answer 0 instead of guessing
+        assert lib.pde_adi_checkpoint_bytes(ctypes.byref(d)) == 0
+        big = cfg.desc(1 << 16)
+        assert lib.pde_adi_checkpoint_bytes(ctypes.byref(big)) == 0
     bad = P.AdiConfig(N=30, C=1, steps=4, dt=0.3, hx=1.0, hy=1.0).desc(1)     # size not built
     assert lib.pde_adi_tables_bytes(ctypes.byref(bad)) == 0
     # struct layouts must match the header

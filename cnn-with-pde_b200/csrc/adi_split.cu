@@ -215,28 +215,68 @@ struct PlaneIO {
         return row_off<N, P>(mirror(i, N)) + (((hc ? G::HS : 0) + m) * P + pp) * 4;
     }
 
+    // Which pair, cell pair and tile slot a thread handles in step `it` of a plane copy.  When a step
+    // of the block advances a whole number of plane rows (all shipped sizes but 28 x 28 with two pairs),
+    // the pair and the column part are per-thread constants and only the row moves: no divisions in
+    // the loops.
+    static constexpr bool REGULAR = (NTHR % P == 0) && ((NTHR / P) % (N / 2) == 0);
+    static constexpr int FSTEP = NTHR / P, RSTEP = FSTEP / (N / 2);
+    struct Thread {
+        int pp, f0, i0, colo;
+        bool hc;
+    };
+    __device__ static __forceinline__ Thread thread(int tid_c) {
+        Thread th;
+        th.pp = tid_c % P;
+        th.f0 = tid_c / P;
+        th.i0 = th.f0 / (N / 2);
+        const int j0 = 2 * (th.f0 % (N / 2));
+        th.hc = j0 >= G::H;
+        const int m = th.hc ? (N - 2 - j0) / 2 : j0 / 2;
+        th.colo = (((th.hc ? G::HS : 0) + m) * P + th.pp) * 4;
+        return th;
+    }
+    struct Slot {
+        int pp, f, off;
+        bool hc, in;
+    };
+    __device__ static __forceinline__ Slot slot(const Thread &th, int tid_c, int it) {
+        Slot sl;
+        if (REGULAR) {
+            sl.pp = th.pp;
+            sl.f = th.f0 + it * FSTEP;
+            sl.hc = th.hc;
+            const int i = th.i0 + it * RSTEP;
+            sl.in = i < N;
+            sl.off = row_off<N, P>(mirror(i < N ? i : 0, N)) + th.colo;
+        } else {
+            const int idx = tid_c + it * NTHR;
+            sl.pp = idx % P;
+            sl.f = idx / P;
+            sl.in = idx < P * F2;
+            sl.off = tile_off(sl.in ? sl.f : 0, sl.pp, sl.hc);
+        }
+        return sl;
+    }
+
     __device__ static __forceinline__ void to_tile(const float *__restrict__ g, float *tile, int item, int c, int C, int B,
                                                    int tid_c) {
         const float2 zero = make_float2(0.f, 0.f);
+        const Thread th = thread(tid_c);
         float2 a[IT], b[IT];
 #pragma unroll
         for (int it = 0; it < IT; ++it) {
-            const int idx = tid_c + it * NTHR;
-            const int pp = idx % P, f = idx / P;
-            const int ba = (item * P + pp) * 2, bb = ba + 1;
-            const bool in = idx < P * F2;
-            a[it] = (in && ba < B) ? __ldcs(reinterpret_cast<const float2 *>(g + ((size_t)ba * C + c) * (N * N)) + f) : zero;
-            b[it] = (in && bb < B) ? __ldcs(reinterpret_cast<const float2 *>(g + ((size_t)bb * C + c) * (N * N)) + f) : zero;
+            const Slot sl = slot(th, tid_c, it);
+            const int ba = (item * P + sl.pp) * 2, bb = ba + 1;
+            a[it] = (sl.in && ba < B) ? __ldcs(reinterpret_cast<const float2 *>(g + ((size_t)ba * C + c) * (N * N)) + sl.f) : zero;
+            b[it] = (sl.in && bb < B) ? __ldcs(reinterpret_cast<const float2 *>(g + ((size_t)bb * C + c) * (N * N)) + sl.f) : zero;
         }
 #pragma unroll
         for (int it = 0; it < IT; ++it) {
-            const int idx = tid_c + it * NTHR;
-            if (idx < P * F2) {
-                bool hc;
-                const int o = tile_off(idx / P, idx % P, hc);
-                *reinterpret_cast<float4 *>(tile + o) = hc ? make_float4(a[it].y, b[it].y, a[it].x, b[it].x)
-                                                           : make_float4(a[it].x, b[it].x, a[it].y, b[it].y);
-            }
+            const Slot sl = slot(th, tid_c, it);
+            if (sl.in)
+                *reinterpret_cast<float4 *>(tile + sl.off) = sl.hc ? make_float4(a[it].y, b[it].y, a[it].x, b[it].x)
+                                                                   : make_float4(a[it].x, b[it].x, a[it].y, b[it].y);
         }
     }
 
@@ -245,26 +285,25 @@ struct PlaneIO {
     __device__ static __forceinline__ void from_tile(const float *tile, float *__restrict__ g, int item, int c, int C,
                                                      int B, int tid_c, const float *__restrict__ w, float sig, float om) {
         const float2 zero = make_float2(0.f, 0.f);
+        const Thread th = thread(tid_c);
         float2 wa[IT], wb[IT];
         if (w) {
 #pragma unroll
             for (int it = 0; it < IT; ++it) {
-                const int idx = tid_c + it * NTHR;
-                const int pp = idx % P, f = idx / P;
-                const int ba = (item * P + pp) * 2, bb = ba + 1;
-                const bool in = idx < P * F2;
-                wa[it] = (in && ba < B) ? __ldcs(reinterpret_cast<const float2 *>(w + ((size_t)ba * C + c) * (N * N)) + f) : zero;
-                wb[it] = (in && bb < B) ? __ldcs(reinterpret_cast<const float2 *>(w + ((size_t)bb * C + c) * (N * N)) + f) : zero;
+                const Slot sl = slot(th, tid_c, it);
+                const int ba = (item * P + sl.pp) * 2, bb = ba + 1;
+                wa[it] = (sl.in && ba < B) ? __ldcs(reinterpret_cast<const float2 *>(w + ((size_t)ba * C + c) * (N * N)) + sl.f) : zero;
+                wb[it] = (sl.in && bb < B) ? __ldcs(reinterpret_cast<const float2 *>(w + ((size_t)bb * C + c) * (N * N)) + sl.f) : zero;
             }
         }
 #pragma unroll
         for (int it = 0; it < IT; ++it) {
-            const int idx = tid_c + it * NTHR;
-            if (idx < P * F2) {
-                const int pp = idx % P, f = idx / P;
-                const int ba = (item * P + pp) * 2, bb = ba + 1;
-                bool hc;
-                const float4 v = *reinterpret_cast<const float4 *>(tile + tile_off(f, pp, hc));
+            const Slot sl = slot(th, tid_c, it);
+            if (sl.in) {
+                const int f = sl.f;
+                const bool hc = sl.hc;
+                const int ba = (item * P + sl.pp) * 2, bb = ba + 1;
+                const float4 v = *reinterpret_cast<const float4 *>(tile + sl.off);
                 float2 a = hc ? make_float2(v.z, v.x) : make_float2(v.x, v.z);
                 float2 b = hc ? make_float2(v.w, v.y) : make_float2(v.y, v.w);
                 if (w) {
@@ -416,17 +455,18 @@ template <int N, int P>
 __device__ __forceinline__ void planes_to_tile_async(const float *__restrict__ g, float *tile, int grp, int c, int C,
                                                      int B, int tid_c) {
     using IO = PlaneIO<N, P>;
+    const typename IO::Thread th = IO::thread(tid_c);
 #pragma unroll
     for (int it = 0; it < IO::IT; ++it) {
-        const int idx = tid_c + it * IO::NTHR;
-        if (idx < P * IO::F2) {
-            const int pp = idx % P, f = idx / P;
-            const int ba = (grp * P + pp) * 2, bb = ba + 1;
+        const typename IO::Slot sl = IO::slot(th, tid_c, it);
+        if (sl.in) {
+            const int f = sl.f;
+            const bool hc = sl.hc;
+            const int ba = (grp * P + sl.pp) * 2, bb = ba + 1;
             const bool va = ba < B, vb = bb < B;
             const float *sa = g + ((size_t)(va ? ba : 0) * C + c) * (N * N) + 2 * f;
             const float *sb = g + ((size_t)(vb ? bb : 0) * C + c) * (N * N) + 2 * f;
-            bool hc;
-            float *dst = tile + IO::tile_off(f, pp, hc);
+            float *dst = tile + sl.off;
             // chunk = {cell lo: a, b; cell hi: a, b}; in the far half the two columns swap.  The four
             // 4-byte copies of a lane start at a component that rotates with the chunk index, so that the
             // 32 lanes of one instruction hit 32 different banks (chunks are 16 floats apart for P == 4)

@@ -117,6 +117,9 @@ __global__ void header_kernel(pde_adi_desc d, pde_adi_schedule sch, char *tables
     }
     hdr->amp_bound = amp;
     hdr->mode_exact = (amp > kAmpLimit || !(amp == amp)) ? 1 : 0;
+    int any = 0;
+    for (int s = 0; s < S; ++s) any |= hdr->clamped[s];
+    hdr->any_clamped = any;
     int nslots = 0;
     for (int s = 0; s < S; ++s) {
         int u = -1;

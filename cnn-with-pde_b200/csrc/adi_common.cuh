@@ -18,7 +18,8 @@ constexpr float kAmpLimit = 256.0f;  // see DESIGN.md "reverse reconstruction"
 struct Header {
     int mode_exact;
     float amp_bound;
-    int pad[2];
+    int any_clamped;   // 1 if any cell of any sweep sits outside the clamp interval
+    int pad;
     float scale[PDE_MAX_SWEEPS];
     float t[PDE_MAX_SWEEPS];
     unsigned rmax_bits[PDE_MAX_SWEEPS];

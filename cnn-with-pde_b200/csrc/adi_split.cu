@@ -629,8 +629,8 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
 // ------------------------------------------------------------------------------------------
 
 // Per-pixel gradient accumulators in TMEM: 64 columns per warp = {A0, A1, B0, B1} x 16, one TMEM
-// lane per thread.  acc0 += z, acc1 += t * z for the kind (alpha / beta) of the sweep.
-__device__ __forceinline__ void tmem_accumulate16(uint32_t tacc, const float (&z)[16], float tt) {
+// lane per thread.  acc0 += m0 * z, acc1 += m1 * z (m0 = dt/h^2, m1 = t dt/h^2) for the kind (alpha / beta) of the sweep.
+__device__ __forceinline__ void tmem_accumulate16(uint32_t tacc, const float (&z)[16], float m0, float m1) {
     float a0[16], a1[16];
     tmem_wait_st();
     tmem_ld16(tacc, a0);
@@ -638,8 +638,8 @@ __device__ __forceinline__ void tmem_accumulate16(uint32_t tacc, const float (&z
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        a0[i] += z[i];
-        a1[i] = fmaf(tt, z[i], a1[i]);
+        a0[i] = fmaf(m0, z[i], a0[i]);
+        a1[i] = fmaf(m1, z[i], a1[i]);
     }
     tmem_st16(tacc, a0);
     tmem_st16(tacc + 16, a1);
@@ -731,34 +731,41 @@ __device__ __forceinline__ void reverse_core(float *gt, float *xt, const Lane &t
     }
 }
 
-// v (summed over the block's groups) -> smoothing^T -> clamp mask -> TMEM accumulators
+// The smoothing adjoint along a half line: v_k <- (v_{k-1} + v_k + v_{k+1}) / 3, with the replicate
+// padding's end taps put back on the edge cell (k = 0) and the neighbour across the junction
+// (k = H-1) fetched from the other half.
+template <int N, int P>
+__device__ __forceinline__ void smooth_adjoint(float (&v)[16]) {
+    constexpr int H = N / 2;
+    const float third = 1.0f / 3.0f;
+    const float vj = __shfl_xor_sync(kFullMask, v[H - 1], P);
+    float lo = v[0];
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        const float cur = v[k];
+        const float hi = (k == H - 1) ? vj : v[k + 1];
+        v[k] = ((lo + cur) + hi) * third;
+        lo = cur;
+    }
+}
+
+// v (summed over the block's groups) -> smoothing^T -> clamp mask -> x dt/h^2 -> TMEM accumulators.
+// When no sweep of the call has a clamped cell, the mask is all ones and the (linear) smoothing
+// adjoint commutes with the sums over sweeps and samples: it is then applied once, to the
+// accumulators, when the kernel ends (`smooth_now` false).
 template <int N, int P>
 __device__ __forceinline__ void reverse_finish(float (&v)[16], uint32_t tacc, const float4 *tm, float scale, float tt,
-                                               bool smooth, bool clamped) {
+                                               bool smooth_now, bool clamped) {
     using G = SG<N, P>;
     constexpr int H = G::H;
-    if (smooth) {
-        const float k3 = scale * (1.0f / 3.0f);
-        const float vj = __shfl_xor_sync(kFullMask, v[H - 1], P);
-        float lo = v[0];
-#pragma unroll
-        for (int k = 0; k < H; ++k) {
-            const float cur = v[k];
-            const float hi = (k == H - 1) ? vj : v[k + 1];
-            v[k] = ((lo + cur) + hi) * k3;
-            lo = cur;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < H; ++k) v[k] *= scale;
-    }
+    if (smooth_now) smooth_adjoint<N, P>(v);
     if (clamped) {
         float m[4 * G::HQ];
         ld_coef<N, P>(tm, m);
 #pragma unroll
         for (int k = 0; k < H; ++k) v[k] *= m[k];
     }
-    tmem_accumulate16(tacc, v, tt);
+    tmem_accumulate16(tacc, v, scale, tt * scale);
 }
 
 // Adjoint of a channel op on one group.  On entry (after a barrier) the g tiles hold the adjoint of
@@ -852,6 +859,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
     const float om = 1.0f - sig;
     const float onepe = 1.0f + d.eps;
     const bool smooth = d.smooth != 0;
+    const bool defer_smooth = smooth && hdr->any_clamped == 0;   // see reverse_finish
     float gm[PDE_MAX_CHANNELS] = {0.f, 0.f, 0.f, 0.f};
     float gw = 0.0f;
     const int sps = a.sps;
@@ -1073,7 +1081,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
                 }
                 if (ax == 0) reverse_core<N, P, 0>(gt, xt, t, vacc, r, iv, onepe, far, rebuild);
                 else reverse_core<N, P, 1>(gt, xt, t, vacc, r, iv, onepe, far, rebuild);
-                reverse_finish<N, P>(vacc, tbase + (ax ? 32u : 0u), tab_m + o, sw_scale, sw_t, smooth, sw_clamped);
+                reverse_finish<N, P>(vacc, tbase + (ax ? 32u : 0u), tab_m + o, sw_scale, sw_t, smooth && !defer_smooth, sw_clamped);
             }
             if (CHAN && d.chan_op == 1) {
                 // adjoint of the pre-step mix: needs g (rows) and the mix INPUT = state before this step
@@ -1106,6 +1114,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
         float av[16];
         tmem_ld16(tbase + kk * 16, av);
         tmem_wait_ld();
+        if (defer_smooth) smooth_adjoint<N, P>(av);
 #pragma unroll
         for (int o = 1; o < P; o <<= 1)
 #pragma unroll

@@ -7,3 +7,8 @@ class LearnableDiffusionLayer(_Enhanced):
     x half-sweep (cifar_2version.py:93,99)."""
 
     _lie = True
+
+
+from .classifiers import (CIFAR10HybridPDEModel, HamiltonianBlock, HybridPDEExtractor, NonConvSpatialAttention,  # noqa: E402,F401
+                          ParabolicBlock, SymmetricLayer)
+from .classifiers import HybridFC as PDEClassifier  # noqa: E402,F401  (cifar_2version.py:336-372)

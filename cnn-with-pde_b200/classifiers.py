@@ -10,6 +10,8 @@ attribute names so that a ``state_dict`` saved by a reference model loads here a
     SVHN.PDEClassifier                    SVHN.py:234-270
     emotion_recognition.DiffusionClassifier   emotion_recognition.py:170-195
     cifar10.SpatialAttention / MultiScaleExtractor / EnhancedFC / CIFAR10PDENoConv   cifar10.py:215-361
+    cifar_2version.SymmetricLayer / ParabolicBlock / HamiltonianBlock / HybridPDEExtractor /
+        NonConvSpatialAttention / PDEClassifier / CIFAR10HybridPDEModel            cifar_2version.py:189-408
 
 They are used by the data-parallel launcher (train.py); each is re-exported from the module
 named after its script.
@@ -229,3 +231,157 @@ class CIFAR10PDENoConv(nn.Module):
         f = self.feature_bn(combined)
         pooled = torch.cat([self.adaptive_pool(f), self.max_pool(f)], dim=1)
         return self.classifier(pooled.flatten(1))
+
+
+# ------------------------------------------------------------------ cifar_2version.py:189-408
+class SymmetricLayer(nn.Module):
+    """F_sym(Y) = -K^T act(BN(K Y)) on the flattened feature map (cifar_2version.py:190-222); stock
+    torch (two 3072 x 3072 GEMMs: cuBLAS)."""
+
+    def __init__(self, channels, spatial_size, activation="relu"):
+        super().__init__()
+        self.channels = channels
+        self.spatial_size = spatial_size
+        self.feature_dim = channels * spatial_size * spatial_size
+        self.K = nn.Linear(self.feature_dim, self.feature_dim, bias=False)
+        self.norm = nn.BatchNorm1d(self.feature_dim)
+        self.activation = nn.ReLU() if activation == "relu" else (nn.Tanh() if activation == "tanh" else nn.Identity())
+        nn.init.eye_(self.K.weight)
+        self.K.weight.data += torch.randn_like(self.K.weight) * 0.01
+
+    def forward(self, Y):
+        B, C, H, W = Y.shape
+        s = self.activation(self.norm(self.K(Y.reshape(B, -1))))
+        return (-torch.matmul(s, self.K.weight)).view(B, C, H, W)
+
+
+class ParabolicBlock(nn.Module):
+    """Y <- Y + dt F_sym(Y), num_steps times (cifar_2version.py:225-238)."""
+
+    def __init__(self, channels, spatial_size, num_steps=3, dt=1.0):
+        super().__init__()
+        self.num_steps = num_steps
+        self.dt = dt
+        self.symmetric_layer = SymmetricLayer(channels, spatial_size)
+
+    def forward(self, Y):
+        for _ in range(self.num_steps):
+            Y = Y + self.dt * self.symmetric_layer(Y)
+        return Y
+
+
+class HamiltonianBlock(nn.Module):
+    """Symplectic pair Y <- Y - dt F_Y(Z); Z <- Z - dt F_Z(Y), Z0 = 0 (cifar_2version.py:241-258)."""
+
+    def __init__(self, channels, spatial_size, num_steps=3, dt=1.0):
+        super().__init__()
+        self.num_steps = num_steps
+        self.dt = dt
+        self.F_Y = SymmetricLayer(channels, spatial_size)
+        self.F_Z = SymmetricLayer(channels, spatial_size)
+
+    def forward(self, Y):
+        Z = torch.zeros_like(Y)
+        for _ in range(self.num_steps):
+            Y = Y + self.dt * (-self.F_Y(Z))
+            Z = Z - self.dt * self.F_Z(Y)
+        return Y
+
+
+class HybridPDEExtractor(nn.Module):
+    """Two learnable diffusion layers (the B200 kernels) + parabolic + Hamiltonian blocks on the same
+    input, softmax-combined, BatchNorm2d (cifar_2version.py:261-307)."""
+
+    concurrent_branches = True
+
+    def __init__(self, input_size=32, channels=3):
+        super().__init__()
+        from .cifar_2version import LearnableDiffusionLayer
+        self.diffusion1 = LearnableDiffusionLayer(input_size, channels, dt=0.001, num_steps=8)
+        self.diffusion2 = LearnableDiffusionLayer(input_size, channels, dt=0.002, num_steps=5)
+        self.parabolic = ParabolicBlock(channels, input_size, num_steps=4, dt=0.5)
+        self.hamiltonian = HamiltonianBlock(channels, input_size, num_steps=3, dt=0.8)
+        self.combination_weights = nn.Parameter(torch.ones(4) / 4)
+        self.feature_norm = PlaneBatchNorm2d(channels)   # nn.BatchNorm2d in the reference (cifar_2version.py:276)
+
+    def forward(self, x):
+        if x.is_cuda and self.concurrent_branches and not os.environ.get("PDE_B200_SERIAL_BRANCHES"):
+            # the second diffusion layer on a side stream; the dense blocks keep the GPU busy on the main one
+            cur = torch.cuda.current_stream(x.device)
+            cache = self.__dict__.setdefault("_streams", {})
+            side = cache.setdefault(x.device, torch.cuda.Stream(device=x.device))
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                d2 = self.diffusion2(x)
+            d1 = self.diffusion1(x)
+            par = self.parabolic(x)
+            ham = self.hamiltonian(x)
+            cur.wait_stream(side)
+            d2.record_stream(cur)
+        else:
+            d1, d2 = self.diffusion1(x), self.diffusion2(x)
+            par, ham = self.parabolic(x), self.hamiltonian(x)
+        w = F.softmax(self.combination_weights, dim=0)
+        combined = self.feature_norm(w[0] * d1 + w[1] * d2 + w[2] * par + w[3] * ham)
+        return combined, d1, d2, par, ham
+
+
+class NonConvSpatialAttention(nn.Module):
+    """Per-pixel sigmoid gate from an MLP on (x + position embedding) (cifar_2version.py:310-333)."""
+
+    def __init__(self, channels, spatial_size):
+        super().__init__()
+        self.channels = channels
+        self.spatial_size = spatial_size
+        self.feature_dim = channels * spatial_size * spatial_size
+        self.pos_embed = nn.Parameter(torch.randn(1, channels, spatial_size, spatial_size) * 0.02)
+        fd = self.feature_dim
+        self.attention_net = nn.Sequential(nn.Linear(fd, fd // 4), nn.ReLU(), nn.Linear(fd // 4, fd // 8), nn.ReLU(),
+                                           nn.Linear(fd // 8, fd), nn.Sigmoid())
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        gate = self.attention_net((x + self.pos_embed).reshape(B, -1)).view(B, C, H, W)
+        return x * gate
+
+
+class HybridFC(nn.Module):
+    """cifar_2version.PDEClassifier (cifar_2version.py:336-372): 1024-512-256-128 with batch norm,
+    dropout p, p, p, p // 2 (sic), Kaiming-normal weights."""
+
+    def __init__(self, input_dim, num_classes=10, dropout_rate=0.4):
+        super().__init__()
+        mods, prev = [], input_dim
+        for width, p in ((1024, dropout_rate), (512, dropout_rate), (256, dropout_rate), (128, dropout_rate // 2)):
+            mods += [nn.Linear(prev, width), nn.BatchNorm1d(width), nn.ReLU(inplace=True), nn.Dropout(p)]
+            prev = width
+        mods.append(nn.Linear(prev, num_classes))
+        self.classifier = nn.Sequential(*mods)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        return self.classifier(x)
+
+
+class CIFAR10HybridPDEModel(nn.Module):
+    """HybridPDEExtractor -> NonConvSpatialAttention -> BatchNorm2d -> 8x8 avg + max pooling ->
+    PDEClassifier (cifar_2version.py:375-408)."""
+
+    def __init__(self, dropout_rate=0.4):
+        super().__init__()
+        self.feature_extractor = HybridPDEExtractor(input_size=32, channels=3)
+        self.attention = NonConvSpatialAttention(channels=3, spatial_size=32)
+        self.adaptive_avg_pool = nn.AdaptiveAvgPool2d((8, 8))
+        self.adaptive_max_pool = nn.AdaptiveMaxPool2d((8, 8))
+        self.feature_bn = PlaneBatchNorm2d(3)   # nn.BatchNorm2d(3) in the reference (cifar_2version.py:392)
+        self.classifier = HybridFC(input_dim=384, num_classes=10, dropout_rate=dropout_rate)
+
+    def forward(self, x):
+        combined = self.feature_extractor(x)[0]
+        f = self.feature_bn(self.attention(combined))
+        pooled = torch.cat([self.adaptive_avg_pool(f), self.adaptive_max_pool(f)], dim=1)
+        return self.classifier(pooled.reshape(pooled.size(0), -1))

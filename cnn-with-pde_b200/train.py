@@ -49,11 +49,17 @@ class Recipe:
     weight_decay: float
     label_smoothing: float
     split_groups: bool = False  # cifar10.py:423-434: alpha/beta parameters get their own group
+    group_keys: Tuple[str, ...] = ("alpha", "beta")   # substrings that put a parameter in the coefficient group
+    rest_lr_scale: float = 0.5                         # learning-rate factor of the other group
 
 
 def _recipes():
-    from . import SVHN, cifar10, emotion_recognition, fashion_mnist, mnist_test
+    from . import SVHN, cifar10, cifar_2version, emotion_recognition, fashion_mnist, mnist_test
     return {
+        # cifar_2version.py:487-499: coefficient group (alpha, beta, channel_mixing, combination_weights)
+        # lr 1e-3 / weight_decay 1e-6, the rest 0.8 x lr / 1e-4
+        "cifar2": Recipe(cifar_2version.CIFAR10HybridPDEModel, (3, 32, 32), 10, 64, 1e-3, 1e-4, 0.1, split_groups=True,
+                         group_keys=("alpha", "beta", "channel_mixing", "combination_weights"), rest_lr_scale=0.8),
         "mnist": Recipe(mnist_test.PDEClassifier, (1, 28, 28), 10, 128, 1e-3, 1e-4, 0.1),
         "fashion": Recipe(fashion_mnist.FashionPDEClassifier, (1, 28, 28), 10, 128, 2e-3, 5e-4, 0.1),
         "cifar10": Recipe(cifar10.CIFAR10PDENoConv, (3, 32, 32), 10, 64, 1e-3, 1e-4, 0.1, split_groups=True),
@@ -62,7 +68,7 @@ def _recipes():
     }
 
 
-MODELS = ("mnist", "fashion", "cifar10", "svhn", "emotion")
+MODELS = ("mnist", "fashion", "cifar10", "cifar2", "svhn", "emotion")
 
 
 class FlatGradSync:
@@ -93,10 +99,11 @@ def make_optimizer(model: nn.Module, r: Recipe, capturable: bool):
     on_cuda = all(p.is_cuda for p in model.parameters())
     extra = {"fused": True, "capturable": capturable} if on_cuda else {"capturable": capturable}
     if r.split_groups:
-        coef = [p for n, p in model.named_parameters() if "alpha" in n or "beta" in n]
-        rest = [p for n, p in model.named_parameters() if not ("alpha" in n or "beta" in n)]
+        in_coef = lambda n: any(k in n for k in r.group_keys)   # noqa: E731
+        coef = [p for n, p in model.named_parameters() if in_coef(n)]
+        rest = [p for n, p in model.named_parameters() if not in_coef(n)]
         groups = [{"params": coef, "lr": r.lr, "weight_decay": 1e-6},
-                  {"params": rest, "lr": r.lr * 0.5, "weight_decay": r.weight_decay}]
+                  {"params": rest, "lr": r.lr * r.rest_lr_scale, "weight_decay": r.weight_decay}]
         return torch.optim.AdamW(groups, **extra)
     return torch.optim.AdamW(model.parameters(), lr=r.lr, weight_decay=r.weight_decay, **extra)
 

@@ -19,10 +19,12 @@ OURS = {
     "mnist": ("mnist_test", "PDEClassifier"),
     "fashion": ("fashion_mnist", "FashionPDEClassifier"),
     "cifar10": ("cifar10", "CIFAR10PDENoConv"),
+    "cifar2": ("cifar_2version", "CIFAR10HybridPDEModel"),
     "svhn": ("SVHN", "PDEClassifier"),
     "emotion": ("emotion_recognition", "DiffusionClassifier"),
 }
 REF = dict(MODELS, svhn=("SVHN", "PDEClassifier", (3, 32, 32), 10, 2),
+           cifar2=("cifar_2version", "CIFAR10HybridPDEModel", (3, 32, 32), 10, 2),
            emotion=("emotion_recognition", "DiffusionClassifier", (1, 48, 48), 7, 3))
 
 
@@ -47,6 +49,48 @@ def test_state_dict_layout_matches_reference(name):
     ref.load_state_dict(mine.state_dict())
     for k in rsd:
         assert torch.equal(ref.state_dict()[k], mine.state_dict()[k]), k
+
+
+@pytest.mark.skipif(not refload.available(), reason="needs /root/reference (build container)")
+def test_cifar2_dense_blocks_match_reference():
+    """The non-PDE parts of the cifar_2version model (symmetric / parabolic / Hamiltonian blocks,
+    attention, classifier head) are stock torch mirrored from the reference: same construction
+    under the same seed, same outputs on CPU (small spatial size keeps it quick)."""
+    ref = refload.load("cifar_2version")
+    import cnn_with_pde_b200.cifar_2version as mine
+    x = torch.randn(4, 3, 8, 8, generator=torch.Generator().manual_seed(5))
+    for cls, args in (("SymmetricLayer", (3, 8)), ("ParabolicBlock", (3, 8, 2, 0.5)), ("HamiltonianBlock", (3, 8, 2, 0.8)),
+                      ("NonConvSpatialAttention", (3, 8))):
+        torch.manual_seed(9)
+        a = refload.quiet(getattr(ref, cls), *args)
+        torch.manual_seed(9)
+        b = getattr(mine, cls)(*args)
+        assert list(a.state_dict()) == list(b.state_dict())
+        for k, v in a.state_dict().items():
+            assert torch.equal(v, b.state_dict()[k]), (cls, k)
+        a.train(), b.train()
+        ya, yb = a(x), b(x)
+        assert torch.allclose(ya, yb, rtol=0, atol=1e-6), cls
+    torch.manual_seed(3)
+    a = refload.quiet(ref.PDEClassifier, 384)
+    torch.manual_seed(3)
+    b = mine.PDEClassifier(384)
+    a.eval(), b.eval()
+    z = torch.randn(5, 384)
+    assert torch.equal(a(z), b(z))
+
+
+def test_cifar2_optimizer_groups_follow_the_script():
+    from cnn_with_pde_b200 import train
+    r = train._recipes()["cifar2"]
+    model = r.build()
+    opt = train.make_optimizer(model, r, capturable=False)
+    coef, rest = opt.param_groups
+    keys = ("alpha", "beta", "channel_mixing", "combination_weights")
+    n_coef = sum(p.numel() for n, p in model.named_parameters() if any(k in n for k in keys))
+    assert sum(p.numel() for p in coef["params"]) == n_coef == 2 * (4 * 3 * 32 * 32 + 9) + 4
+    assert coef["lr"] == 1e-3 and coef["weight_decay"] == 1e-6
+    assert abs(rest["lr"] - 8e-4) < 1e-12 and rest["weight_decay"] == 1e-4
 
 
 def test_cifar10_optimizer_groups_follow_the_script():
@@ -104,3 +148,31 @@ def test_launcher_trains_one_gpu(graph):
     from cnn_with_pde_b200 import train
     out = train.run("fashion", 32, 4, 2, graph=graph, quiet=True)
     assert out["img_per_s"] > 0 and np.isfinite(out["loss"]) and out["cuda_graph"] == graph
+
+
+@pytest.mark.gpu
+def test_cifar2_hybrid_model_trains_and_branch_order_does_not_matter(monkeypatch):
+    """cifar_2version's hybrid model on the B200 diffusion layers: serial and concurrent branches
+    give the same logits and PDE gradients; the launcher trains it under a CUDA graph."""
+    from cnn_with_pde_b200 import train
+    from cnn_with_pde_b200.cifar_2version import CIFAR10HybridPDEModel
+    torch.manual_seed(0)
+    model = CIFAR10HybridPDEModel().cuda().eval()
+    x = torch.randn(6, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 10, (6,), device="cuda")
+    outs = []
+    for serial in ("1", ""):
+        if serial:
+            monkeypatch.setenv("PDE_B200_SERIAL_BRANCHES", "1")
+        else:
+            monkeypatch.delenv("PDE_B200_SERIAL_BRANCHES", raising=False)
+        model.zero_grad(set_to_none=True)
+        logits = model(x)
+        torch.nn.functional.cross_entropy(logits, y).backward()
+        torch.cuda.synchronize()
+        outs.append((logits.detach().clone(), model.feature_extractor.diffusion2.alpha_base.grad.clone(),
+                     model.feature_extractor.diffusion1.channel_mixing.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.isfinite(a).all() and torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+    out = train.run("cifar2", 32, 3, 2, graph=True, quiet=True)
+    assert out["img_per_s"] > 0 and np.isfinite(out["loss"])

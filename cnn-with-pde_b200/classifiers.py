@@ -10,6 +10,7 @@ attribute names so that a ``state_dict`` saved by a reference model loads here a
     SVHN.PDEClassifier                    SVHN.py:234-270
     emotion_recognition.DiffusionClassifier   emotion_recognition.py:170-195
     cifar10.SpatialAttention / MultiScaleExtractor / EnhancedFC / CIFAR10PDENoConv   cifar10.py:215-361
+    tiny_imagenet.BasicBlock / ImprovedTinyImageNetClassifier                       tiny_imagenet.py:237-327
     cifar_2version.SymmetricLayer / ParabolicBlock / HamiltonianBlock / HybridPDEExtractor /
         NonConvSpatialAttention / PDEClassifier / CIFAR10HybridPDEModel            cifar_2version.py:189-408
 
@@ -385,3 +386,68 @@ class CIFAR10HybridPDEModel(nn.Module):
         f = self.feature_bn(self.attention(combined))
         pooled = torch.cat([self.adaptive_avg_pool(f), self.adaptive_max_pool(f)], dim=1)
         return self.classifier(pooled.reshape(pooled.size(0), -1))
+
+
+# ------------------------------------------------------------------ tiny_imagenet.py:237-327
+class BasicBlock(nn.Module):
+    """ResNet basic block (tiny_imagenet.py:306-327); stock torch (cuDNN convolutions)."""
+
+    def __init__(self, in_planes, planes, stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.shortcut = nn.Sequential()
+        if stride != 1 or in_planes != planes:
+            self.shortcut = nn.Sequential(nn.Conv2d(in_planes, planes, kernel_size=1, stride=stride, bias=False),
+                                          nn.BatchNorm2d(planes))
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        out = out + self.shortcut(x)
+        return F.relu(out)
+
+
+class ImprovedTinyImageNetClassifier(nn.Module):
+    """diff (the B200 explicit layer, 3 x 64 x 64) -> ResNet-18-style backbone -> 200 classes
+    (tiny_imagenet.py:237-303)."""
+
+    def __init__(self, num_classes=200, use_pde=True, dropout_rate=0.3):
+        super().__init__()
+        self.use_pde = use_pde
+        if use_pde:
+            from .tiny_imagenet import ImprovedDiffusionLayer
+            self.diff = ImprovedDiffusionLayer(size=64, channels=3, num_steps=1, use_implicit=False)
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = self._make_layer(64, 64, 2, stride=1)
+        self.layer2 = self._make_layer(64, 128, 2, stride=2)
+        self.layer3 = self._make_layer(128, 256, 2, stride=2)
+        self.layer4 = self._make_layer(256, 512, 2, stride=2)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.dropout = nn.Dropout(dropout_rate)
+        self.fc = nn.Linear(512, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, 0, 0.01)
+                nn.init.constant_(m.bias, 0)
+
+    @staticmethod
+    def _make_layer(in_planes, planes, num_blocks, stride):
+        return nn.Sequential(BasicBlock(in_planes, planes, stride), *[BasicBlock(planes, planes, 1) for _ in range(1, num_blocks)])
+
+    def forward(self, x):
+        if self.use_pde:
+            x = self.diff(x)
+        x = self.maxpool(F.relu(self.bn1(self.conv1(x))))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        x = torch.flatten(self.avgpool(x), 1)
+        return self.fc(self.dropout(x))

@@ -28,3 +28,6 @@ class ImprovedDiffusionLayer(nn.Module):
             raise ValueError(f"ImprovedDiffusionLayer: expected (B, {self.channels}, H, W), got {tuple(u.shape)}")
         cfg = TinyConfig(steps=self.num_steps, dt=self.dt, cmin=self.stability_eps, cmax=self.max_coeff)
         return tiny_layer(u, self.alpha_base, self.channel_scaling, cfg)
+
+
+from .classifiers import BasicBlock, ImprovedTinyImageNetClassifier  # noqa: E402,F401  (tiny_imagenet.py:237-327)

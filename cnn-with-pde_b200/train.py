@@ -54,8 +54,17 @@ class Recipe:
 
 
 def _recipes():
-    from . import SVHN, cifar10, cifar_2version, emotion_recognition, fashion_mnist, mnist_test
+    from . import SVHN, cifar10, cifar_2version, emotion_recognition, fashion_mnist, mnist_test, tiny_imagenet
+
+    def tiny():
+        # diff.beta_base takes no part in the forward pass (tiny_imagenet.py:21,26): its .grad stays None in
+        # the reference, so AdamW never touches it; with one flat gradient buffer that means "frozen"
+        m = tiny_imagenet.ImprovedTinyImageNetClassifier()
+        m.diff.beta_base.requires_grad_(False)
+        return m
+
     return {
+        "tiny": Recipe(tiny, (3, 64, 64), 200, 32, 1e-3, 1e-4, 0.1),   # tiny_imagenet.py:543-556
         # cifar_2version.py:487-499: coefficient group (alpha, beta, channel_mixing, combination_weights)
         # lr 1e-3 / weight_decay 1e-6, the rest 0.8 x lr / 1e-4
         "cifar2": Recipe(cifar_2version.CIFAR10HybridPDEModel, (3, 32, 32), 10, 64, 1e-3, 1e-4, 0.1, split_groups=True,
@@ -68,7 +77,7 @@ def _recipes():
     }
 
 
-MODELS = ("mnist", "fashion", "cifar10", "cifar2", "svhn", "emotion")
+MODELS = ("mnist", "fashion", "cifar10", "cifar2", "svhn", "emotion", "tiny")
 
 
 class FlatGradSync:

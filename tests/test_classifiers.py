@@ -22,9 +22,11 @@ OURS = {
     "cifar2": ("cifar_2version", "CIFAR10HybridPDEModel"),
     "svhn": ("SVHN", "PDEClassifier"),
     "emotion": ("emotion_recognition", "DiffusionClassifier"),
+    "tiny": ("tiny_imagenet", "ImprovedTinyImageNetClassifier"),
 }
 REF = dict(MODELS, svhn=("SVHN", "PDEClassifier", (3, 32, 32), 10, 2),
            cifar2=("cifar_2version", "CIFAR10HybridPDEModel", (3, 32, 32), 10, 2),
+           tiny=("tiny_imagenet", "ImprovedTinyImageNetClassifier", (3, 64, 64), 200, 2),
            emotion=("emotion_recognition", "DiffusionClassifier", (1, 48, 48), 7, 3))
 
 
@@ -175,4 +177,6 @@ def test_cifar2_hybrid_model_trains_and_branch_order_does_not_matter(monkeypatch
     for a, b in zip(*outs):
         assert torch.isfinite(a).all() and torch.allclose(a, b, rtol=1e-5, atol=1e-7)
     out = train.run("cifar2", 32, 3, 2, graph=True, quiet=True)
+    assert out["img_per_s"] > 0 and np.isfinite(out["loss"])
+    out = train.run("tiny", 16, 3, 2, graph=True, quiet=True)     # tiny_imagenet's ResNet behind the explicit layer
     assert out["img_per_s"] > 0 and np.isfinite(out["loss"])

@@ -226,3 +226,39 @@ def test_cuda_split_shapes_and_tails(monkeypatch):
             if not need_gin:
                 assert got["gin"] is None
             _assert_close(got, want, TOL, f"{c.name} P={forced or 'default'}")
+
+
+def test_cuda_layers_under_autocast():
+    """The CIFAR scripts wrap the model in autocast (cifar10.py:459, cifar_2version.py:521): the
+    layers cast their inputs to fp32 (custom_fwd) and give the fp32 result; a half-precision input is
+    accepted and its gradient comes back in its own dtype."""
+    import torch
+    for c in (K.case("amp_cifar10", "cifar10", B=3, **K.SCRIPT_INSTANCES["cifar10_pde3"]), K.case("amp_emotion", "emotion", B=2),
+              K.case("amp_tiny", "tiny", B=2, **K.SCRIPT_INSTANCES["tiny"])):
+        layer = runners.make_cuda_layer(c)
+        u, g = K.make_io(c)
+        x = torch.from_numpy(u).cuda().requires_grad_(True)
+        y_ref = layer(x)
+        y_ref.backward(torch.from_numpy(g).cuda())
+        ref_grads = [p.grad.clone() for p in layer.parameters() if p.grad is not None]
+        gin_ref = x.grad.clone()
+        for p in layer.parameters():
+            p.grad = None
+        xh = torch.from_numpy(u).cuda().half().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            y = layer(xh)
+        assert y.dtype == torch.float32
+        y.backward(torch.from_numpy(g).cuda())
+        assert xh.grad.dtype == torch.float16
+        # the only difference is the rounding of the input to fp16 (2^-11 relative)
+        assert runners.rel_l2(y.detach().cpu().numpy(), y_ref.detach().cpu().numpy()) <= 2e-3
+        assert runners.rel_l2(xh.grad.float().cpu().numpy(), gin_ref.cpu().numpy()) <= 2e-3
+        got = [p.grad for p in layer.parameters() if p.grad is not None]
+        assert len(got) == len(ref_grads) and all(torch.isfinite(a).all() for a in got)
+        # fp32 input under autocast: bit-identical to the plain call
+        for p in layer.parameters():
+            p.grad = None
+        x2 = torch.from_numpy(u).cuda().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y2 = layer(x2)
+        assert torch.equal(y2, y_ref)

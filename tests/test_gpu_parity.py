@@ -262,3 +262,38 @@ def test_cuda_layers_under_autocast():
         with torch.autocast("cuda", dtype=torch.bfloat16):
             y2 = layer(x2)
         assert torch.equal(y2, y_ref)
+
+
+def test_cuda_split_few_steps_and_single_channel_ops(monkeypatch):
+    """Half-line kernels at the ends of the schedule: one and two steps (the checkpoint stream runs
+    one step ahead, across items), Lie splitting, channel ops with a single channel, batches of
+    several items per block."""
+    monkeypatch.setenv("PDE_B200_ADI_SPLIT", "1")
+    todo = [
+        K.case("split_fashion_1step", "fashion", B=37, num_steps=1),
+        K.case("split_mnist_2steps", "mnist", B=41, num_steps=2),
+        K.case("split_cifar2_1step", "cifar2", B=9, size=32, channels=3, dt=0.002, num_steps=1),
+        K.case("split_svhn_c1", "svhn", B=6, size=32, channels=1, num_steps=2),
+        K.case("split_cifar10_c1", "cifar10", B=6, size=28, channels=1, dt=0.002, num_steps=2, dx=1.0, dy=1.0),
+    ]
+    for c in todo:
+        params, io = K.make_params(c), K.make_io(c)
+        want = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+        got = runners.run_cuda(c, params=params, io=io)
+        _assert_close(got, want, TOL, c.name)
+    # many items per block: 3000 samples on a persistent grid, first / last samples against the oracle
+    import torch
+    c = K.case("split_many_items", "cifar10", B=3000, **K.SCRIPT_INSTANCES["cifar10_pde3"])
+    params = K.make_params(c)
+    layer = runners.make_cuda_layer(c, params)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    u = torch.randn(c.B, *c.shape, device="cuda", generator=gen)
+    g = torch.randn(c.B, *c.shape, device="cuda", generator=gen)
+    x = u.clone().requires_grad_(True)
+    y = layer(x)
+    y.backward(g)
+    for sl in (slice(0, 3), slice(c.B - 3, c.B)):
+        c3 = K.case("split_many_items_3", "cifar10", B=3, **K.SCRIPT_INSTANCES["cifar10_pde3"])
+        want = runners.run_oracle(c3, params=params, io=(u[sl].cpu().numpy(), g[sl].cpu().numpy()), dtype=np.float32)
+        assert runners.rel_l2(y[sl].detach().cpu().numpy(), want["y"]) <= TOL
+        assert runners.rel_l2(x.grad[sl].cpu().numpy(), want["gin"]) <= TOL

@@ -297,3 +297,30 @@ def test_cuda_split_few_steps_and_single_channel_ops(monkeypatch):
         want = runners.run_oracle(c3, params=params, io=(u[sl].cpu().numpy(), g[sl].cpu().numpy()), dtype=np.float32)
         assert runners.rel_l2(y[sl].detach().cpu().numpy(), want["y"]) <= TOL
         assert runners.rel_l2(x.grad[sl].cpu().numpy(), want["gin"]) <= TOL
+
+
+def test_cuda_split_results_are_bitwise_reproducible(monkeypatch):
+    """The half-line kernels synchronise warps of a block through barriers, mbarriers (TMA) and
+    cp.async groups, and sum gradients in a fixed order: repeated calls must agree bit for bit
+    (a missing barrier shows up as run-to-run differences long before it shows up in a tolerance)."""
+    import torch
+    monkeypatch.setenv("PDE_B200_ADI_SPLIT", "1")
+    for c in (K.case("rep_fashion", "fashion", B=1201), K.case("rep_svhn", "svhn", B=301, **K.SCRIPT_INSTANCES["svhn"]),
+              K.case("rep_cifar10", "cifar10", B=610, **K.SCRIPT_INSTANCES["cifar10_pde2"])):
+        layer = runners.make_cuda_layer(c)
+        gen = torch.Generator(device="cuda").manual_seed(17)
+        u = torch.randn(c.B, *c.shape, device="cuda", generator=gen)
+        g = torch.randn(c.B, *c.shape, device="cuda", generator=gen)
+        first = None
+        for _ in range(6):
+            for p in layer.parameters():
+                p.grad = None
+            x = u.clone().requires_grad_(True)
+            y = layer(x)
+            y.backward(g)
+            now = [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in layer.parameters() if p.grad is not None]
+            if first is None:
+                first = now
+            else:
+                for a, b in zip(first, now):
+                    assert torch.equal(a, b), c.name

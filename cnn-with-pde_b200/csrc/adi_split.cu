@@ -555,7 +555,10 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
         int s = 0;
         while (s < S) {
             const int k = s % sps, step = s / sps, ax = sweep_axis(k);
-            if (k == 0 && d.chan_op == 1) mix_phase();
+            // the pre-step mix (cifar) runs inside the step's first sweep phase: mixed rows go from the
+            // tiles of all channels into registers, through the sweep and only then back to the tile
+            const bool mix_first = P < 4 && k == 0 && d.chan_op == 1;   // (four pairs per group: single channel, no channel op)
+            if (P >= 4 && k == 0 && d.chan_op == 1) mix_phase();        // never taken; keeps that instantiation's schedule
             // the next sweep has the same orientation and (Strang: same time, time step, spacing) the same tables
             const bool fuse = sps == 3 && k == 2 && s + 1 < S && d.chan_op == 0 && h_slot[s] == h_slot[s + 1];
             const int s_next = s + (fuse ? 2 : 1);
@@ -580,6 +583,22 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
                 }
             }
             cb ^= 1;
+            if (P < 4 && mix_first) {
+                f2 xm[Q][H];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) mix_rows<N, P>(set + q * TILE, Q * TILE, C, a.chan + t.c * C, 1, t, xm[q]);
+                __syncthreads();   // every channel has read every tile of the item
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    f2 x[1][H];
+#pragma unroll
+                    for (int kk = 0; kk < H; ++kk) x[0][kk] = xm[q][kk];
+                    solve<N, P, 1>(x, iv, e, far);
+                    if (t.active) st_half<N, P, 0>(my + q * TILE, t, x[0]);
+                }
+                s = s_next;
+                continue;
+            }
 #pragma unroll 1
             for (int q = 0; q < Q; ++q) {
                 float *tile = my + q * TILE;

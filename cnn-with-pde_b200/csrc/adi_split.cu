@@ -482,7 +482,9 @@ __device__ __forceinline__ void planes_to_tile_async(const float *__restrict__ g
     }
 }
 
-template <int N, int P, int Q>
+// MIX1: instantiation for layers with a pre-step channel mix (chan_op == 1), which runs inside the
+// first sweep phase of a step; the others keep the plain schedule (and their register allocation).
+template <int N, int P, int Q, bool MIX1>
 __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kernel(const Args a) {
     using G = SG<N, P>;
     constexpr int H = G::H, TILE = G::TILE, HQ4 = 4 * G::HQ;
@@ -557,8 +559,8 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
             const int k = s % sps, step = s / sps, ax = sweep_axis(k);
             // the pre-step mix (cifar) runs inside the step's first sweep phase: mixed rows go from the
             // tiles of all channels into registers, through the sweep and only then back to the tile
-            const bool mix_first = P < 4 && k == 0 && d.chan_op == 1;   // (four pairs per group: single channel, no channel op)
-            if (P >= 4 && k == 0 && d.chan_op == 1) mix_phase();        // never taken; keeps that instantiation's schedule
+            const bool mix_first = MIX1 && k == 0 && d.chan_op == 1;
+            if (!MIX1 && k == 0 && d.chan_op == 1) mix_phase();
             // the next sweep has the same orientation and (Strang: same time, time step, spacing) the same tables
             const bool fuse = sps == 3 && k == 2 && s + 1 < S && d.chan_op == 0 && h_slot[s] == h_slot[s + 1];
             const int s_next = s + (fuse ? 2 : 1);
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
                 }
             }
             cb ^= 1;
-            if (P < 4 && mix_first) {
+            if (MIX1 && mix_first) {
                 f2 xm[Q][H];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) mix_rows<N, P>(set + q * TILE, Q * TILE, C, a.chan + t.c * C, 1, t, xm[q]);
@@ -1245,16 +1247,20 @@ static const void *bwd_kernel_for(int N, int P, bool chan) {
     return nullptr;
 }
 template <int N>
-static const void *fwd_kernel_n(int P, int Q) {
+static const void *fwd_kernel_n(int P, int Q, bool mix1) {
     if (P == 4)
-        return Q == 4 ? reinterpret_cast<const void *>(sfwd_kernel<N, 4, 4>)
-                      : (Q == 2 ? reinterpret_cast<const void *>(sfwd_kernel<N, 4, 2>)
-                                : reinterpret_cast<const void *>(sfwd_kernel<N, 4, 1>));
-    return Q == 2 ? reinterpret_cast<const void *>(sfwd_kernel<N, 2, 2>) : reinterpret_cast<const void *>(sfwd_kernel<N, 2, 1>);
+        return Q == 4 ? reinterpret_cast<const void *>(sfwd_kernel<N, 4, 4, false>)
+                      : (Q == 2 ? reinterpret_cast<const void *>(sfwd_kernel<N, 4, 2, false>)
+                                : reinterpret_cast<const void *>(sfwd_kernel<N, 4, 1, false>));
+    if (mix1)
+        return Q == 2 ? reinterpret_cast<const void *>(sfwd_kernel<N, 2, 2, true>)
+                      : reinterpret_cast<const void *>(sfwd_kernel<N, 2, 1, true>);
+    return Q == 2 ? reinterpret_cast<const void *>(sfwd_kernel<N, 2, 2, false>)
+                  : reinterpret_cast<const void *>(sfwd_kernel<N, 2, 1, false>);
 }
-static const void *fwd_kernel_for(int N, int P, int Q) {
-    if (N == 28) return fwd_kernel_n<28>(P, Q);
-    if (N == 32) return fwd_kernel_n<32>(P, Q);
+static const void *fwd_kernel_for(int N, int P, int Q, bool mix1) {
+    if (N == 28) return fwd_kernel_n<28>(P, Q, mix1);
+    if (N == 32) return fwd_kernel_n<32>(P, Q, mix1);
     return nullptr;
 }
 
@@ -1351,7 +1357,7 @@ int forward(const pde_adi_desc &d, const char *tables, const float *u, const flo
     DeviceProps props;
     rc = query_props(&props);
     if (rc) return rc;
-    const void *kern = fwd_kernel_for(d.N, p.P, p.Qf);
+    const void *kern = fwd_kernel_for(d.N, p.P, p.Qf, d.chan_op == 1);
     if (!kern) return PDE_ERR_UNSUPPORTED;
     // Qf groups of tiles, two coefficient stages of two tables
     const size_t smem = (size_t)d.C * p.Qf * p.tile_bytes + (size_t)4 * d.C * ((d.N / 2 + 3) / 4) * d.N * 2 * 16;

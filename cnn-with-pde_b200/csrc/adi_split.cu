@@ -1,7 +1,8 @@
 // Implicit ADI layers, second implementation: HALF a line per thread, twisted factorisation.
 //
 // Same mathematics as adi.cu (reference: mnist_test.py:33-198, fashion_mnist.py:40-196,
-// SVHN.py:38-230, cifar10.py:53-211, cifar_2version.py:52-187); different mapping onto the SM:
+// SVHN.py:38-230, cifar10.py:53-211, cifar_2version.py:52-187); different mapping onto the SM
+// (DESIGN.md section 4.0 has the measurements behind every choice):
 //
 //   * A tridiagonal system can be eliminated from BOTH ends towards the middle ("twisted"
 //     factorisation): two independent recurrences of half the length and one exchange where they
@@ -11,14 +12,16 @@
 //   * Everything is addressed in MIRRORED coordinates: a half line is indexed from the plane edge
 //     (k = 0) to the junction (k = H-1) in both halves, so both threads of a line run the same
 //     instruction stream; rows and columns of the tile are stored in that order too.
-//   * A block advances P sample pairs of every channel: the P threads that own the same half line
-//     read the same coefficient address (one L1 wavefront serves P pairs and 32/P half lines), and
-//     every lane of a warp is busy for any plane edge that is a multiple of 32 / (2 P).
-//   * The transposition between x and y sweeps goes through a shared-memory tile as in adi.cu, but
-//     across the warps of the block: one __syncthreads() per change of orientation.
-//   * The forward kernel optionally writes the state at the end of every step (the "checkpoints",
-//     HBM is idle in these kernels); the backward kernel starts from them instead of recomputing
-//     the forward trajectory.
+//   * A block advances groups of P sample pairs of every channel; every lane of a warp is busy for
+//     any plane edge that is a multiple of 32 / (2 P).  The transposition between x and y sweeps goes
+//     through a shared-memory tile as in adi.cu, but across the warps of the block: one
+//     __syncthreads() per change of orientation.
+//   * Forward: every sweep is a phase in which a thread applies its coefficients (staged in shared
+//     memory by TMA one phase ahead) to its half line of Q groups in turn; it optionally writes the
+//     state at the end of every step as a tile image (the "checkpoints": HBM is idle in these kernels).
+//   * Backward: starts from those checkpoints instead of recomputing the trajectory; checkpoint
+//     tiles arrive by TMA bulk copies one step ahead, the next item's gout planes by LDGSTS, the
+//     coefficients by TMA one sweep ahead; gradient accumulators live in tensor memory.
 #include "adi_common.cuh"
 
 namespace pde {

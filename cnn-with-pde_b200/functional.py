@@ -1,7 +1,9 @@
 """torch.autograd.Function wrappers over the C ABI (the only callers of _cabi).
 
-Each Function saves nothing but its inputs (and, for the implicit family, the factorised
-coefficient tables of the call): the backward kernels rebuild the forward states on-chip.
+Each Function saves its inputs and, for the implicit family, the factorised coefficient tables of
+the call plus -- when the half-line kernels serve it -- the state at the end of every step
+(`pde_adi_forward_train`); everything else of the forward trajectory is rebuilt on-chip by the
+backward kernels.
 """
 from __future__ import annotations
 

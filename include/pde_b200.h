@@ -89,12 +89,16 @@ int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sched,
 int pde_adi_forward(const pde_adi_desc *d, const void *tables, const float *u,
                     const float *chan, const float *skip_weight, float *out, void *stream);
 
-/* Training variants of pde_adi_forward / pde_adi_backward.  autograd keeps what forward computed for backward; here
- * that is the state at the end of every step ("checkpoints", pde_adi_checkpoint_bytes(d) bytes,
+/* Training variants of pde_adi_forward / pde_adi_backward.  Replace what autograd keeps between
+ * the reference's forward and backward (mnist_test.py:44-65 and the graph recorded under it): here
+ * that is the state at the end of every step ("checkpoints": pde_adi_checkpoint_bytes(d) bytes,
  * 256-byte aligned, opaque layout), so that the backward kernel does not recompute the forward
  * trajectory.  pde_adi_checkpoint_bytes returns 0 when the configuration is served by kernels
- * that rebuild the trajectory on-chip; ckpt may then be NULL.  pde_adi_backward (no ckpt) makes
- * the checkpoints itself inside its (then batch-sized) workspace. */
+ * that rebuild the trajectory on-chip (small batches, plane edges other than 28 / 32); ckpt may
+ * then be NULL.  pde_adi_backward (no ckpt) stays valid for every configuration: it makes the
+ * checkpoints itself inside its (then batch-sized) workspace.  pde_adi_backward_saved needs
+ * pde_adi_backward_saved_workspace_bytes(d) bytes of workspace when ckpt != NULL and
+ * pde_adi_backward_workspace_bytes(d) when ckpt == NULL. */
 size_t pde_adi_checkpoint_bytes(const pde_adi_desc *d);
 size_t pde_adi_backward_saved_workspace_bytes(const pde_adi_desc *d);
 int pde_adi_forward_train(const pde_adi_desc *d, const void *tables, const float *u,

@@ -359,7 +359,11 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "backward (adjoint + coefficient-gradient reduction)",
                          "achieved": round(bwd_gbs, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": round(bwd_gbs / peak, 4), "traffic": _profile_traffic(args.layer),
-                         "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": round(bwd_ms, 4)},
+                         "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": round(bwd_ms, 4),
+                         "traffic_note": ("ncu dram bytes of the backward kernel; for the implicit layers they include the step "
+                                          "checkpoints (num_steps x 4 B/cell) the training forward wrote on purpose: HBM is the "
+                                          "idle resource of these kernels, shared memory the busy one (DESIGN.md 4.0)")
+                         if kind not in ("emotion", "tiny") else None},
             "roofline_fwd": {"bound": "hbm", "achieved": round(fwd_gbs, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(fwd_gbs / peak, 4), "algorithmic_bytes_per_launch": fwd_bytes,
                              "ms_per_launch": round(fwd_ms, 4)},

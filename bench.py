@@ -11,6 +11,13 @@ latency; the config-batch latency is reported beside it.  Unit: cell-updates = B
 per step.  Under torchrun every rank runs its own batch (weak scaling; the only exchange is the
 all-reduce of the coefficient gradients) and rank 0 prints ONE JSON line.
 
+Every one of the K timed "steps" is INNER back-to-back passes (config.inner_repeats, sized so that the
+timed region lasts about a second: clock samples and event resolution mean something); ms_per_step
+is the time of ONE pass.  Beside the default-init weights the same batch is timed with perturbed
+weights that put cells outside both clamp edges (`clamped`: the masked / in-sweep smoothing-adjoint
+path), and at N = 1 the CPU leg doubles as a parity self-check: the oracle runs on the very batch the
+GPU was timed on and `parity_rel_err` holds the worst relative error per output.
+
 --impl reference times the CPU restatement (oracle/, C + OpenMP on all host cores; the
 reference itself is pure Python and does not travel to the GPU box) on a bounded sample.
 """
@@ -61,13 +68,51 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _profile_traffic(layer):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def _csrc_sha():
+    """Hash of the kernel sources: ties the ncu-derived counters to the build being timed."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "cnn-with-pde_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
+def _profile_counters(layer):
+    """Per-launch ncu counters of the layer's backward / forward kernels at the bench batch
+    (profiles/kernel_counters.json, written by tools/ncu_counters.py from the round's `ncu --set full`
+    capture): dram bytes and executed warp instructions.  `csrc_sha` says which sources they were
+    captured from."""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(layer)
+        with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as f:
+            allc = json.load(f)
+        c = dict(allc.get(layer) or {})
+        c["csrc_sha"] = allc.get("_csrc_sha")
+        return c
     except Exception:
-        return None
+        return {}
+
+
+def _bind_to_gpu_numa(index):
+    """Restrict this process to the CPUs NVML reports as local to GPU `index` (first-touch policy then
+    places the pinned staging buffer on that NUMA node).  Best effort: returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = [i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [i for i in cpus if i in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} of {len(allowed)} CPUs local to GPU {index}"
+        return "no narrower CPU set reported for this GPU"
+    except Exception as ex:   # NVML or affinity not available: keep going unbound
+        return f"unbound ({type(ex).__name__})"
 
 
 class ClockSampler:
@@ -156,6 +201,9 @@ def run_b200(args):
     layer = runners.make_cuda_layer(c, device=dev)
     params = [p for p in layer.parameters()]
     nparam = sum(p.numel() for p in params if p.requires_grad)
+    # same layer, weights perturbed so that cells sit outside both clamp edges (tests/cases.make_params)
+    c_pert = K.case("bench_clamped_" + args.layer, kind, B=B, perturb=True, **ctor)
+    layer_c = runners.make_cuda_layer(c_pert, device=dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     u = torch.randn(B, C, H, W, device=dev, generator=gen)
     g = torch.randn(B, C, H, W, device=dev, generator=gen)
@@ -186,11 +234,21 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step(x)
     sync_all()
-    if sampler:
-        sampler.begin()
+    # passes per timed "step": enough for a timed region of about a second (same on every rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    step(x)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    inner = args.inner or max(1, min(256, int(-(-args.min_seconds * 1e3 // (args.steps * max(float(t.item()), 1e-3))))))
+    sync_all()
+    if sampler:
+        sampler.begin()
+    e0.record()
+    for _ in range(args.steps * inner):
         step(x)
     e1.record()
     sync_all()
@@ -200,7 +258,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
+    ms_per_step = ms_total / (args.steps * inner)
     value = world * cells * nsteps / (ms_per_step * 1e-3) / 1e9
 
     # ----------------------------------------- per-kernel timing through the C ABI (roofline)
@@ -215,7 +273,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n
 
-    n_k = max(5, min(args.steps, 20))
+    n_k = max(20, min(args.steps * inner, 100))
     with torch.no_grad():
         fwd_eval_ms = time_phase(lambda: layer(u), n_k)      # inference forward (no checkpoints)
     fwd_ms = time_phase(lambda: layer(x), n_k)               # training forward: also writes the step checkpoints
@@ -226,6 +284,12 @@ def run_b200(args):
     yn = layer(xn)
     bwd_nogin_ms = time_phase(lambda: torch.autograd.grad(yn, [p for p in params if p.requires_grad], g,
                                                           retain_graph=True, allow_unused=True), n_k)
+    # the clamped-cell variant of the same batch (masks read, smoothing adjoint inside every sweep)
+    pc = [p for p in layer_c.parameters() if p.requires_grad]
+    fwd_c_ms = time_phase(lambda: layer_c(x), n_k)
+    yc = layer_c(x)
+    bwd_c_ms = time_phase(lambda: torch.autograd.grad(yc, [x] + pc, g, retain_graph=True, allow_unused=True), n_k)
+    del yc
     peak, peak_src = _peaks()
     bwd_bytes = 12 * cells + 4 * nparam       # read u, read g_out, write g_in, write coefficient grads
     fwd_bytes = 8 * cells + 4 * nparam        # read u, write out, read coefficient maps
@@ -238,6 +302,9 @@ def run_b200(args):
     # g_out stays on the device: in training it is produced there by the classifier's backward.
     nchunk = 8 if B >= 8 * 1024 else 1
     cb = (B + nchunk - 1) // nchunk
+    # the staging buffer is first touched by this process: bind it to the CPUs next to this rank's GPU so
+    # that with several ranks the pinned pages do not all land on NUMA node 0
+    numa = _bind_to_gpu_numa(local) if world > 1 else None
     host_u = torch.empty((B, C, H, W), dtype=torch.float32).pin_memory()
     host_u.copy_(u)
     host_g = torch.empty(nparam, dtype=torch.float32).pin_memory()
@@ -284,6 +351,33 @@ def run_b200(args):
     e2e_ms = float(t.item()) / k_e2e
     e2e_value = world * cells * nsteps / (e2e_ms * 1e-3) / 1e9
 
+    # ------------------------------- N > 1: sharded gradients + all-reduce against one GPU, on hardware
+    # Every rank runs its shard and the coefficient gradients are all-reduced; rank 0 then runs the
+    # concatenated global batch alone.  The two must agree to fp32 reduction-order noise.
+    dp_parity = None
+    if world > 1:
+        bc = min(B, 4096)
+        uc, gc = u[:bc].contiguous(), g[:bc].contiguous()
+        for p in params:
+            p.grad = None
+        layer(uc.clone().requires_grad_(True)).backward(gc)
+        allreduce_coefficient_grads(params)
+        sharded = [p.grad.clone() for p in params if p.grad is not None]
+        U = [torch.empty_like(uc) for _ in range(world)]
+        G = [torch.empty_like(gc) for _ in range(world)]
+        dist.all_gather(U, uc)
+        dist.all_gather(G, gc)
+        if rank == 0:
+            for p in params:
+                p.grad = None
+            layer(torch.cat(U).requires_grad_(True)).backward(torch.cat(G))
+            single = [p.grad for p in params if p.grad is not None]
+            errs = [max(runners.rel_l2(a.cpu().numpy(), b.cpu().numpy()), runners.rel_max(a.cpu().numpy(), b.cpu().numpy()))
+                    for a, b in zip(sharded, single)]
+            dp_parity = {"worst": float(f"{max(errs):.3e}"), "global_batch": bc * world, "ranks": world, "tolerance": 1e-5,
+                         "what": "all-reduced coefficient gradients of the sharded batch vs a single-GPU run of the same global batch"}
+        del U, G
+
     # ------------------------------------------------------- latency at the script's own batch
     cs = K.case("bench_small", kind, B=script_b, perturb=False, **ctor)
     us = torch.randn(script_b, C, H, W, device=dev, generator=gen)
@@ -321,7 +415,12 @@ def run_b200(args):
     out = None
     if rank == 0:
         # the CPU leg runs on rank 0 at N = 1 only (the other ranks would idle at the barrier)
-        cpu = cpu_baseline(args.layer, budget_s=args.cpu_seconds) if world == 1 else None
+        cpu, parity, parity_c = None, None, None
+        if world == 1:
+            x = y = yn = xn = None
+            torch.cuda.empty_cache()
+            cpu, parity = cpu_baseline_and_parity(args.layer, c, layer, u, g, args.cpu_seconds)
+            _, parity_c = cpu_baseline_and_parity(args.layer, c_pert, layer_c, u, g, args.cpu_seconds)
         if train is not None and "error" not in train and world == 1:
             try:
                 train["cpu_baseline"] = cpu_train_baseline(args.train_model)
@@ -337,11 +436,27 @@ def run_b200(args):
                         others[name] = _quick_layer(name, dev, peak)
                     except Exception as ex:  # keep the headline line even if a side measurement fails
                         others[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        ctr = _profile_counters(args.layer)
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        sweeps = nsteps * (3 if kind in ("fashion", "mnist", "svhn", "cifar10") else (2 if kind == "cifar2" else 1))
+
+        def issue(inst, ms):
+            """warp instructions / (SMs x 4 schedulers x f x t): share of the issue slots a launch used"""
+            if not inst:
+                return None
+            return round(inst / (info["sm_count"] * 4 * sm_mhz * 1e6 * ms * 1e-3), 4)
+
+        def per_cell_sweep(inst):
+            return round(inst * 32 / (cells * sweeps), 2) if inst else None
+
         out = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "timed_region_s": round(ms_total * 1e-3, 3),
             "config": {
+                "inner_repeats": inner,
+                "timing": f"{args.steps} steps x {inner} back-to-back passes inside one CUDA-event bracket; ms_per_step = one pass",
                 "workload": f"{args.layer} PDE layer forward+backward (grad_input + coefficient grads), "
                             f"{C}x{H}x{W}, num_steps={nsteps}, batch {B} per GPU "
                             f"(script batch {script_b} scaled so every tensor ({cells * 4 / 1e6:.0f} MB) exceeds L2)",
@@ -352,22 +467,43 @@ def run_b200(args):
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": cells * 4,
                     "d2h_bytes_per_step": nparam * 4, "ms_per_step": round(e2e_ms, 4), "chunks": nchunk,
                     "note": "pinned host input -> H2D -> nn.Module forward+backward -> D2H coefficient grads; PCIe bound"},
-            "gpu_launches": ((6 if kind not in ("emotion", "tiny") else 3) * args.steps),
-            "gpu_launches_per_step": {"tables_kernel": 1, "header_kernel": 1, "stables_kernel": 1, "sfwd_kernel": 1,
-                                      "sbwd_kernel": 1, "finish_kernel": 1} if kind not in ("emotion", "tiny") else
+            "gpu_launches": ((5 if kind not in ("emotion", "tiny") else 3) * args.steps * inner),
+            "gpu_launches_per_step": {"prepare_kernel": 1, "flags_kernel": 1, "sfwd_kernel": 1, "sbwd_kernel": 1,
+                                      "finish_kernel": 1} if kind not in ("emotion", "tiny") else
                                      {"fwd_kernel": 1, "bwd_kernel": 1, "finish_kernel": 1},
             "roofline": {"bound": "hbm", "kernel": "backward (adjoint + coefficient-gradient reduction)",
                          "achieved": round(bwd_gbs, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": round(bwd_gbs / peak, 4), "traffic": _profile_traffic(args.layer),
+                         "frac": round(bwd_gbs / peak, 4), "traffic": ctr.get("bwd_dram_bytes"),
                          "algorithmic_bytes_per_launch": bwd_bytes, "ms_per_launch": round(bwd_ms, 4),
+                         # the binding roof of the implicit kernels is instruction issue, not HBM:
+                         # executed warp instructions per launch (ncu smsp__inst_executed.sum of the capture in
+                         # profiles/, sources `counters_csrc_sha`) over the issue slots of the live-timed launch
+                         "issue_frac": issue(ctr.get("bwd_inst_executed"), bwd_ms),
+                         "inst_executed_per_launch": ctr.get("bwd_inst_executed"),
+                         "thread_inst_per_cell_sweep": per_cell_sweep(ctr.get("bwd_inst_executed")),
+                         "issue_clock_mhz": sm_mhz,
+                         "counters_csrc_sha": ctr.get("csrc_sha"), "csrc_sha": _csrc_sha(),
+                         "counters_match_build": ctr.get("csrc_sha") == _csrc_sha(),
                          "traffic_note": ("ncu dram bytes of the backward kernel; for the implicit layers they include the step "
                                           "checkpoints (num_steps x 4 B/cell) the training forward wrote on purpose: HBM is the "
                                           "idle resource of these kernels, shared memory the busy one (DESIGN.md 4.0)")
                          if kind not in ("emotion", "tiny") else None},
             "roofline_fwd": {"bound": "hbm", "achieved": round(fwd_gbs, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(fwd_gbs / peak, 4), "algorithmic_bytes_per_launch": fwd_bytes,
-                             "ms_per_launch": round(fwd_ms, 4)},
-            "fwd_bwd_hbm_frac": round((fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak, 4),
+                             "ms_per_launch": round(fwd_ms, 4), "traffic": ctr.get("fwd_dram_bytes"),
+                             "issue_frac": issue(ctr.get("fwd_inst_executed"), fwd_ms),
+                             "thread_inst_per_cell_sweep": per_cell_sweep(ctr.get("fwd_inst_executed"))},
+            # forward + backward against the HBM roof, on the step the driver's clock sees (ms_per_step)
+            "fwd_bwd_hbm_frac": round((fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+            "clamped": {"note": "same batch, weights perturbed so that cells sit outside both clamp edges and the time "
+                                "coefficients cross a clamp inside [0, T] (masked path, smoothing adjoint inside every sweep)",
+                        "fwd_ms": round(fwd_c_ms, 4), "bwd_ms": round(bwd_c_ms, 4),
+                        "fwd_bwd_gcell_updates_per_s": round(cells * nsteps / ((fwd_c_ms + bwd_c_ms) * 1e-3) / 1e9, 2),
+                        "bwd_hbm_frac": round(bwd_bytes / (bwd_c_ms * 1e-3) / 1e9 / peak, 4)},
+            "dp_parity_rel_err": dp_parity,
+            "numa_binding": numa,
+            "parity_rel_err": parity,
+            "parity_rel_err_clamped": parity_c,
             "fwd_inference_ms": round(fwd_eval_ms, 4),
             "bwd_no_grad_input_ms": round(bwd_nogin_ms, 4),
             "script_batch_latency_us": round(small_ms * 1e3, 1),
@@ -468,6 +604,51 @@ def cpu_baseline(layer, budget_s=12.0, fixed_batch=None, reps=1):
     return {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"oracle/pde_oracle.c (fp32, OpenMP x{cores}) forward+backward of {layer}, batch {b2}, "
                       f"{dt2:.2f} s", "batch": b2, "seconds": round(dt2, 3)}
+
+
+def cpu_baseline_and_parity(layer_name, c, layer, u, g, budget_s):
+    """The CPU leg at N = 1, doubling as a parity self-check of what was just timed: the oracle (all
+    host cores) runs forward + backward on the benched batch itself -- or, if that would take more
+    than ~3x the budget, on its first samples -- and the GPU results for exactly those samples are
+    compared with it (worst of rel-L2 and max-abs / max-ref per output, tests/runners.compare)."""
+    import numpy as np
+    import torch
+    from tests import cases as K
+    from tests import runners
+    kind, ctor, _, _ = LAYERS[layer_name]
+    cores = os.cpu_count() or 1
+    nsteps = _steps_of(kind, ctor)
+    C, H, W = c.shape
+    probe = cpu_baseline(layer_name, budget_s=1.0)
+    full_s = c.B * C * H * W * nsteps / 1e9 / max(probe["value"], 1e-9)
+    b2 = c.B if full_s <= 3.0 * budget_s else max(cores * 8, int(c.B * budget_s / full_s))
+    c2 = K.case(c.name + "_cpu", kind, B=b2, perturb=c.perturb, **ctor)
+    params = K.make_params(c2)
+    for p in layer.parameters():
+        p.grad = None
+    xs = u[:b2].clone().requires_grad_(True)
+    ys = layer(xs)
+    ys.backward(g[:b2])
+    torch.cuda.synchronize()
+    got = {"y": ys.detach().cpu().numpy(), "gin": xs.grad.cpu().numpy()}
+    for k, p in layer.named_parameters():
+        if p.grad is not None:
+            got["g_" + k] = p.grad.detach().cpu().numpy()
+    io = (u[:b2].cpu().numpy(), g[:b2].cpu().numpy())
+    del xs, ys
+    t0 = time.perf_counter()
+    want = runners.run_oracle(c2, params=params, io=io, dtype=np.float32, nthreads=cores)
+    dt = time.perf_counter() - t0
+    errs = runners.compare(got, want)
+    val = b2 * C * H * W * nsteps / dt / 1e9
+    cpu = {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"oracle/pde_oracle.c (fp32, OpenMP x{cores}) forward+backward of {layer_name} on "
+                     f"{'the benched batch' if b2 == c.B else 'the first samples of the benched batch'} ({b2} samples), {dt:.2f} s",
+           "batch": b2, "seconds": round(dt, 3)}
+    parity = {"worst": float(f"{max(errs.values()):.3e}"), "batch": b2, "tolerance": 1e-5,
+              "per_output": {k: float(f"{v:.3e}") for k, v in errs.items()},
+              "against": "oracle fp32 on the same inputs and weights" + ("" if not c.perturb else " (perturbed, clamped cells)")}
+    return cpu, parity
 
 
 def cpu_train_baseline(model_name="cifar10", batch=64, steps=2):
@@ -583,6 +764,8 @@ def main():
     ap.add_argument("--layer", default="fashion", choices=sorted(LAYERS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: roofline-size batch of the layer)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--inner", type=int, default=0, help="passes per timed step (default: sized for --min-seconds)")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="target length of the timed region")
     ap.add_argument("--all-layers", type=int, default=1, help="also time the other layers (N=1 only)")
     ap.add_argument("--train", type=int, default=1, help="also time a whole-model training step (img/s)")
     ap.add_argument("--train-model", default="cifar10")

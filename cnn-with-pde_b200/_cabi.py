@@ -15,6 +15,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PDE_B200_LIB") or os.path.join(_HERE, "libpde_b200.so")
 MAX_SWEEPS = 192
 MAX_CHANNELS = 4
+ABI_VERSION = 3
+
+# pde_adi_desc.tuning / pde_emo_desc.tuning (include/pde_b200.h)
+TUNE_IMPL_HALF_LINE = 1
+TUNE_IMPL_WHOLE_LINE = 2
+EMO_TUNE_GENERIC = 1
+
+
+def adi_tuning(impl: int = 0, pairs: int = 0, qf: int = 0, np_: int = 0) -> int:
+    return (impl & 3) | ((pairs & 7) << 2) | ((qf & 7) << 5) | ((np_ & 3) << 8)
 
 EXPORTS = (
     "pde_b200_abi_version", "pde_b200_error_string", "pde_b200_device_info",
@@ -29,7 +39,7 @@ EXPORTS = (
 
 class AdiDesc(Structure):
     _fields_ = [(n, c_int32) for n in ("B", "C", "N", "steps", "lie", "smooth", "has_max", "chan_op", "skip")] + \
-               [(n, c_float) for n in ("cmin", "cmax", "eps")]
+               [(n, c_float) for n in ("cmin", "cmax", "eps")] + [("tuning", c_int32)]
 
 
 class AdiSchedule(Structure):
@@ -37,7 +47,8 @@ class AdiSchedule(Structure):
 
 
 class EmoDesc(Structure):
-    _fields_ = [(n, c_int32) for n in ("B", "N", "Nt")] + [(n, c_float) for n in ("half_dt", "dt", "dx2", "dy2")]
+    _fields_ = [(n, c_int32) for n in ("B", "N", "Nt")] + [(n, c_float) for n in ("half_dt", "dt", "dx2", "dy2")] + \
+               [("tuning", c_int32)]
 
 
 class TinyDesc(Structure):
@@ -99,7 +110,7 @@ def lib():
     L.pde_tiny_forward.argtypes = [POINTER(TinyDesc), fp, fp, fp, fp, vp]
     L.pde_tiny_backward.restype = c_int
     L.pde_tiny_backward.argtypes = [POINTER(TinyDesc), fp, fp, fp, fp, fp, fp, fp, vp, c_size_t, vp]
-    if L.pde_b200_abi_version() != 2:
+    if L.pde_b200_abi_version() != ABI_VERSION:
         raise PdeB200Error("libpde_b200.so ABI version mismatch; rebuild it")
     _lib = L
     return L

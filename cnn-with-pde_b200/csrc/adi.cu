@@ -38,17 +38,29 @@ struct Geo {
 };
 
 // ------------------------------------------------------------------------------------------
-// prepare: coefficient map -> clamp -> smoothing -> r -> pivots.  One thread per (sweep,
-// channel, line); op-for-op the fp32 arithmetic of the reference (no FMA contraction).
-// Table layout: [s][c][i/4][line][i%4] so a warp reads one float4 per lane, fully coalesced.
+// prepare: coefficient map -> clamp -> smoothing -> r -> pivots, ONE launch per call.  A block
+// owns a sweep, a thread one (channel, line) of it; op-for-op the fp32 arithmetic of the reference
+// (no FMA contraction).  The thread writes its line into the tables of both implementations:
+//   whole-line (adi.cu):        [s][c][i/4][line][i%4], one-sided Thomas pivots (the reference's);
+//   half-line  (adi_split.cu):  [s][c][k/4][mirrored line][half][k%4], twisted pivots: top-down
+//                               for cells 0 .. H-1 (the same values), bottom-up for N-1 .. H+1,
+//                               and cell H closes both; written only when the call can be served
+//                               by those kernels.
+// The block reduces the sweep's largest r and "some cell clamped" and writes its header entries;
+// nothing crosses blocks: flags_kernel (one warp, next in the stream) folds them into the call-wide
+// flags the backward kernels read.
 // ------------------------------------------------------------------------------------------
-__global__ void tables_kernel(pde_adi_desc d, pde_adi_schedule sch, const float *__restrict__ ab,
-                              const float *__restrict__ bb, const float *__restrict__ atc,
-                              const float *__restrict__ btc, char *tables) {
-    const int sps = sweeps_per_step(d), S = d.steps * sps, N = d.N, C = d.C;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= S * C * N) return;
-    const int line = idx % N, c = (idx / N) % C, s = idx / (N * C);
+template <int N>
+__global__ void __launch_bounds__(128) prepare_kernel(pde_adi_desc d, pde_adi_schedule sch, SlotMap sm,
+                                                      const float *__restrict__ ab, const float *__restrict__ bb,
+                                                      const float *__restrict__ atc, const float *__restrict__ btc,
+                                                      char *tables, int want_split) {
+    constexpr int H = N / 2, HQ = (H + 3) / 4;
+    const int sps = sweeps_per_step(d), C = d.C;
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int line = tid % N, c = tid / N;
+    const bool live = c < C;
     const int axis = sweep_axis(s % sps);
     const float *base = axis ? bb : ab, *tc = axis ? btc : atc;
     const float tt = sch.t[s], dts = sch.dts[s], h2 = sch.h2[s];
@@ -56,84 +68,133 @@ __global__ void tables_kernel(pde_adi_desc d, pde_adi_schedule sch, const float 
     Header *hdr = reinterpret_cast<Header *>(tables);
     float *f = reinterpret_cast<float *>(tables + kHeaderBytes);
     const size_t T = table_elems(d);
-    float *tr = f, *tinv = f + T, *te = f + 2 * T, *tm = f + 3 * T;
 
-    float kap[32], msk[32];
-    for (int i = 0; i < N; ++i) {
-        const size_t q = axis == 0 ? ((size_t)c * N + line) * N + i : ((size_t)c * N + i) * N + line;
-        const float raw = __fadd_rn(base[q], __fmul_rn(tc[q], tt));
-        bool m = raw >= d.cmin;
-        float k = raw < d.cmin ? d.cmin : raw;
-        if (d.has_max) {
-            m = m && raw <= d.cmax;
-            k = k > d.cmax ? d.cmax : k;
+    float rmax = 0.0f;
+    int any_clamped = 0;
+    if (live) {
+        float kap[N], r[N], den[N];
+        unsigned inside = 0u;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const size_t q = axis == 0 ? ((size_t)c * N + line) * N + i : ((size_t)c * N + i) * N + line;
+            const float raw = __fadd_rn(__ldg(base + q), __fmul_rn(__ldg(tc + q), tt));
+            bool m = raw >= d.cmin;
+            float k = raw < d.cmin ? d.cmin : raw;
+            if (d.has_max) {
+                m = m && raw <= d.cmax;
+                k = k > d.cmax ? d.cmax : k;
+            }
+            kap[i] = k;
+            if (m) inside |= 1u << i;
         }
-        kap[i] = k;
-        msk[i] = m ? 1.0f : 0.0f;
-    }
-    float cst_prev = 0.0f, rmax = 0.0f;
-    for (int i = 0; i < N; ++i) {
-        float ks = kap[i];
-        if (d.smooth) {
-            const float a0 = __fmul_rn(kap[i > 0 ? i - 1 : 0], third);
-            const float a1 = __fmul_rn(kap[i], third);
-            const float a2 = __fmul_rn(kap[i < N - 1 ? i + 1 : N - 1], third);
-            ks = __fadd_rn(__fadd_rn(a0, a1), a2);
+        any_clamped = inside != (N == 32 ? 0xffffffffu : ((1u << (N & 31)) - 1u));
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            float ks = kap[i];
+            if (d.smooth) {
+                const float a0 = __fmul_rn(kap[i > 0 ? i - 1 : 0], third);
+                const float a1 = __fmul_rn(kap[i], third);
+                const float a2 = __fmul_rn(kap[i < N - 1 ? i + 1 : N - 1], third);
+                ks = __fadd_rn(__fadd_rn(a0, a1), a2);
+            }
+            r[i] = __fdiv_rn(__fmul_rn(ks, dts), h2);
+            rmax = fmaxf(rmax, fabsf(r[i]));
         }
-        const float r = __fdiv_rn(__fmul_rn(ks, dts), h2);
-        const float b = (i == 0 || i == N - 1) ? __fadd_rn(1.0f, r) : __fadd_rn(1.0f, __fmul_rn(2.0f, r));
-        float den;
-        if (i == 0)
-            den = __fadd_rn(b, d.eps);
-        else
-            den = __fadd_rn(__fsub_rn(b, __fmul_rn(-r, cst_prev)), d.eps);
-        cst_prev = __fdiv_rn(-r, den);
-        const size_t o = (((size_t)s * C + c) * (N / 4) + i / 4) * N * 4 + (size_t)line * 4 + (i & 3);
-        tr[o] = r;
-        tinv[o] = __fdiv_rn(1.0f, den);
-        te[o] = -cst_prev;
-        tm[o] = msk[i];
-        rmax = fmaxf(rmax, fabsf(r));
-    }
-    atomicMax(&hdr->rmax_bits[s], __float_as_uint(rmax));
-    bool any_clamped = false;
-    for (int i = 0; i < N; ++i) any_clamped = any_clamped || msk[i] == 0.0f;
-    if (any_clamped) atomicOr(&hdr->clamped[s], 1);
-}
-
-__global__ void header_kernel(pde_adi_desc d, pde_adi_schedule sch, char *tables) {
-    Header *hdr = reinterpret_cast<Header *>(tables);
-    const int sps = sweeps_per_step(d), S = d.steps * sps;
-    float amp = 1.0f;
-    for (int step = 0; step < d.steps; ++step) {
-        float a = 1.0f;
-        // the first sweep of a step is never rebuilt (its input is a checkpoint)
-        for (int k = 1; k < sps; ++k) a *= 1.0f + 4.0f * __uint_as_float(hdr->rmax_bits[step * sps + k]);
-        amp = fmaxf(amp, a);
-    }
-    for (int s = 0; s < S; ++s) {
-        hdr->scale[s] = __fdiv_rn(sch.dts[s], sch.h2[s]);
-        hdr->t[s] = sch.t[s];
-    }
-    hdr->amp_bound = amp;
-    hdr->mode_exact = (amp > kAmpLimit || !(amp == amp)) ? 1 : 0;
-    int any = 0;
-    for (int s = 0; s < S; ++s) any |= hdr->clamped[s];
-    hdr->any_clamped = any;
-    int nslots = 0;
-    for (int s = 0; s < S; ++s) {
-        int u = -1;
-        for (int q = 0; q < s && u < 0; ++q)
-            if (sweep_axis(q % sps) == sweep_axis(s % sps) && sch.t[q] == sch.t[s] && sch.dts[q] == sch.dts[s] &&
-                sch.h2[q] == sch.h2[s])
-                u = hdr->slot[q];
-        if (u < 0) {
-            u = nslots++;
-            hdr->rep[u] = (short)s;
+        auto diag = [&](int i) {
+            return (i == 0 || i == N - 1) ? __fadd_rn(1.0f, r[i]) : __fadd_rn(1.0f, __fmul_rn(2.0f, r[i]));
+        };
+        // one-sided elimination, top-down (mnist_test.py:165-185): c*_i = -r_i / den_i
+        float cst = 0.0f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            den[i] = i == 0 ? __fadd_rn(diag(i), d.eps) : __fadd_rn(__fsub_rn(diag(i), __fmul_rn(-r[i], cst)), d.eps);
+            cst = __fdiv_rn(-r[i], den[i]);
         }
-        hdr->slot[s] = (short)u;
+        {
+            float *tr = f, *tinv = f + T, *te = f + 2 * T, *tm = f + 3 * T;
+#pragma unroll
+            for (int q = 0; q < N / 4; ++q) {
+                const size_t o = (((size_t)s * C + c) * (N / 4) + q) * N * 4 + (size_t)line * 4;
+                float4 vr, vi, ve, vm;
+                float *pr = &vr.x, *pi = &vi.x, *pe = &ve.x, *pm = &vm.x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = 4 * q + k;
+                    pr[k] = r[i];
+                    pi[k] = __fdiv_rn(1.0f, den[i]);
+                    pe[k] = __fdiv_rn(r[i], den[i]);
+                    pm[k] = (inside >> i) & 1u ? 1.0f : 0.0f;
+                }
+                *reinterpret_cast<float4 *>(tr + o) = vr;
+                *reinterpret_cast<float4 *>(tinv + o) = vi;
+                *reinterpret_cast<float4 *>(te + o) = ve;
+                *reinterpret_cast<float4 *>(tm + o) = vm;
+            }
+        }
+        if (want_split) {
+            // twisted pivots: cells 0 .. H-1 keep the top-down values, cells N-1 .. H+1 are eliminated
+            // bottom-up, cell H closes both
+            float ast = 0.0f;
+#pragma unroll
+            for (int i = N - 1; i > H; --i) {
+                den[i] = i == N - 1 ? __fadd_rn(diag(i), d.eps) : __fadd_rn(__fsub_rn(diag(i), __fmul_rn(-r[i], ast)), d.eps);
+                ast = __fdiv_rn(-r[i], den[i]);
+            }
+            const float cst_h = __fdiv_rn(-r[H - 1], den[H - 1]);
+            den[H] = __fadd_rn(__fsub_rn(__fsub_rn(diag(H), __fmul_rn(-r[H], cst_h)), __fmul_rn(-r[H], ast)), d.eps);
+            const size_t TS = split::stab_floats_per_table(d);
+            float *stab = f + 4 * T;
+            float *tr = stab, *tinv = stab + TS, *te = stab + 2 * TS, *tm = stab + 3 * TS;
+            const int R = split::mirror(line, N);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int q = 0; q < HQ; ++q) {
+                    const size_t o = ((((size_t)s * C + c) * HQ + q) * N + R) * 8 + h * 4;
+                    float4 vr, vi, ve, vm;
+                    float *pr = &vr.x, *pi = &vi.x, *pe = &ve.x, *pm = &vm.x;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int k = 4 * q + kk;
+                        if (k < H) {
+                            const int i = h ? N - 1 - k : k;
+                            pr[kk] = r[i];
+                            pi[kk] = __fdiv_rn(1.0f, den[i]);
+                            pe[kk] = __fdiv_rn(r[i], den[i]);
+                            pm[kk] = (inside >> i) & 1u ? 1.0f : 0.0f;
+                        } else {
+                            pr[kk] = 0.0f; pi[kk] = 0.0f; pe[kk] = 0.0f; pm[kk] = 0.0f;
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(tr + o) = vr;
+                    *reinterpret_cast<float4 *>(tinv + o) = vi;
+                    *reinterpret_cast<float4 *>(te + o) = ve;
+                    *reinterpret_cast<float4 *>(tm + o) = vm;
+                }
+        }
     }
-    hdr->nslots = nslots;
+    // the sweep's header entries
+    __shared__ float s_rmax[4];
+    const int any = __syncthreads_or(any_clamped);
+    rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, 16));
+    rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, 8));
+    rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, 4));
+    rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, 2));
+    rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, 1));
+    if ((tid & 31) == 0) s_rmax[tid >> 5] = rmax;
+    __syncthreads();
+    if (tid == 0) {
+        float m = 0.0f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_rmax[w]);
+        hdr->rmax_bits[s] = __float_as_uint(m);
+        hdr->clamped[s] = any ? 1 : 0;
+        hdr->scale[s] = __fdiv_rn(dts, h2);
+        hdr->t[s] = tt;
+        hdr->slot[s] = sm.slot[s];
+        if (s == 0) hdr->nslots = sm.nslots;
+    }
+    if (s == 0)
+        for (int u = tid; u < sm.nslots; u += blockDim.x) hdr->rep[u] = sm.rep[u];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1029,15 +1090,15 @@ static int plan_bwd(const pde_adi_desc *d, BwdPlan *p) {
     if (p->smem > (size_t)props.max_smem_optin || p->warps > 16) return PDE_ERR_UNSUPPORTED;
     const void *kern = bwd_kernel_for(d->N, d->chan_op != 0);
     if (!kern) return PDE_ERR_UNSUPPORTED;
-    PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     // Residency from first principles: the occupancy calculator answers 1 block / SM for kernels
     // that allocate tensor memory, whatever their footprint.
-    cudaFuncAttributes fa;
-    PDE_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+    KernelInfo fa;
+    rc = kernel_info(kern, p->smem, &fa);
+    if (rc) return rc;
     const int threads = p->warps * 32;
-    const int regs_per_warp = ((fa.numRegs + 7) / 8) * 8 * 32;
+    const int regs_per_warp = ((fa.regs + 7) / 8) * 8 * 32;
     const int by_regs = 65536 / (regs_per_warp * p->warps);
-    const int by_smem = (int)((size_t)(228 * 1024) / (p->smem + fa.sharedSizeBytes + 1024));
+    const int by_smem = (int)((size_t)(228 * 1024) / (p->smem + fa.static_smem + 1024));
     const int by_threads = 2048 / threads;
     const int by_tmem = 512 / p->tmem_cols;
     int occ = by_regs;
@@ -1045,9 +1106,9 @@ static int plan_bwd(const pde_adi_desc *d, BwdPlan *p) {
     if (by_threads < occ) occ = by_threads;
     if (by_tmem < occ) occ = by_tmem;
     p->blocks_per_sm = occ;
-    if (env_int("PDE_B200_DEBUG", 0))
+    if (debug_enabled())
         fprintf(stderr, "[pde_b200] bwd plan: N=%d C=%d warps=%d smem=%zu regs=%d by_regs=%d by_smem=%d by_tmem=%d\n",
-                d->N, d->C, p->warps, p->smem, fa.numRegs, by_regs, by_smem, by_tmem);
+                d->N, d->C, p->warps, p->smem, fa.regs, by_regs, by_smem, by_tmem);
     if (p->blocks_per_sm < 1) p->blocks_per_sm = 1;
     p->nitems = (d->B + 1) / 2;
     int want = (p->nitems + p->G - 1) / p->G;
@@ -1066,11 +1127,10 @@ static int plan_bwd(const pde_adi_desc *d, BwdPlan *p) {
 template <int N>
 static int launch_fwd(const Args &a, int NP, int sm_count, int threads, size_t smem, cudaStream_t st) {
     auto go = [&](auto kern) -> int {
-        PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // persistent grid: exactly the blocks that are resident at once (registers included)
         int per_sm = 1;
-        PDE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-        if (per_sm < 1) per_sm = 1;
+        int rc = cached_occupancy(reinterpret_cast<const void *>(kern), threads, smem, &per_sm);
+        if (rc) return rc;
         const int want = (a.nitems + a.G - 1) / a.G, cap = sm_count * per_sm;
         kern<<<want < cap ? want : cap, threads, smem, st>>>(a);
         return cuda_last_error();
@@ -1140,6 +1200,46 @@ extern "C" size_t pde_adi_backward_workspace_bytes(const pde_adi_desc *d) {
     return legacy_workspace_bytes(d);
 }
 
+// sweeps with the same axis, time, time step and spacing share their tables
+static void make_slot_map(const pde_adi_desc &d, const pde_adi_schedule &sch, SlotMap *m) {
+    const int sps = sweeps_per_step(d), S = d.steps * sps;
+    int nslots = 0;
+    for (int s = 0; s < S; ++s) {
+        int u = -1;
+        for (int q = 0; q < s && u < 0; ++q)
+            if (sweep_axis(q % sps) == sweep_axis(s % sps) && sch.t[q] == sch.t[s] && sch.dts[q] == sch.dts[s] &&
+                sch.h2[q] == sch.h2[s])
+                u = m->slot[q];
+        if (u < 0) {
+            u = nslots++;
+            m->rep[u] = (short)s;
+        }
+        m->slot[s] = (short)u;
+    }
+    m->nslots = nslots;
+}
+
+__global__ void flags_kernel(char *tables, int steps, int sps) {
+    Header *hdr = reinterpret_cast<Header *>(tables);
+    bool exact, any_clamped;
+    header_flags(hdr, steps, sps, &exact, &any_clamped);
+    if (threadIdx.x == 0) {
+        hdr->mode_exact = exact ? 1 : 0;
+        hdr->any_clamped = any_clamped ? 1 : 0;
+    }
+}
+
+template <int N>
+static int launch_prepare(const pde_adi_desc &d, const pde_adi_schedule &sch, const SlotMap &sm, const float *ab,
+                          const float *bb, const float *atc, const float *btc, char *tables, int want_split,
+                          cudaStream_t st) {
+    const int S = d.steps * sweeps_per_step(d);
+    const int threads = ((d.C * N + 31) / 32) * 32;
+    prepare_kernel<N><<<S, threads, 0, st>>>(d, sch, sm, ab, bb, atc, btc, tables, want_split);
+    flags_kernel<<<1, 32, 0, st>>>(tables, d.steps, sweeps_per_step(d));
+    return cuda_last_error();
+}
+
 extern "C" int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sched, const float *ab,
                                const float *bb, const float *atc, const float *btc, void *tables,
                                void *stream) {
@@ -1148,18 +1248,23 @@ extern "C" int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sc
     if (!sched || !ab || !bb || !atc || !btc || !tables) return PDE_ERR_INVALID;
     if (reinterpret_cast<uintptr_t>(tables) & 255u) return PDE_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PDE_CUDA_TRY(cudaMemsetAsync(tables, 0, kHeaderBytes, st));
     const int S = d->steps * sweeps_per_step(*d);
-    const int n = S * d->C * d->N;
-    if (n > 0) {
-        tables_kernel<<<(n + 127) / 128, 128, 0, st>>>(*d, *sched, ab, bb, atc, btc, static_cast<char *>(tables));
-        rc = cuda_last_error();
-        if (rc) return rc;
+    if (S == 0) {   // zero steps: identity; the backward kernel still reads the flags
+        flags_kernel<<<1, 32, 0, st>>>(static_cast<char *>(tables), 0, sweeps_per_step(*d));
+        return cuda_last_error();
     }
-    header_kernel<<<1, 1, 0, st>>>(*d, *sched, static_cast<char *>(tables));
-    rc = cuda_last_error();
-    if (rc) return rc;
-    if (split::supported(*d)) rc = split::prepare(*d, *sched, ab, bb, atc, btc, static_cast<char *>(tables), st);
+    SlotMap sm;
+    make_slot_map(*d, *sched, &sm);
+    const int want_split = split::supported(*d) ? 1 : 0;
+    char *tb = static_cast<char *>(tables);
+    switch (d->N) {
+        case 8: rc = launch_prepare<8>(*d, *sched, sm, ab, bb, atc, btc, tb, 0, st); break;
+        case 12: rc = launch_prepare<12>(*d, *sched, sm, ab, bb, atc, btc, tb, 0, st); break;
+        case 16: rc = launch_prepare<16>(*d, *sched, sm, ab, bb, atc, btc, tb, 0, st); break;
+        case 28: rc = launch_prepare<28>(*d, *sched, sm, ab, bb, atc, btc, tb, want_split, st); break;
+        case 32: rc = launch_prepare<32>(*d, *sched, sm, ab, bb, atc, btc, tb, want_split, st); break;
+        default: rc = PDE_ERR_UNSUPPORTED;
+    }
     return rc;
 }
 
@@ -1167,11 +1272,11 @@ extern "C" int pde_adi_forward_train(const pde_adi_desc *d, const void *tables, 
                                      const float *skipw, float *out, void *ckpt, void *stream) {
     int rc = validate(d);
     if (rc) return rc;
+    if (d->B == 0) return PDE_OK;   // an empty batch (a rank with no samples) is a no-op: its pointers may be NULL
     if (!tables || !u || !out) return PDE_ERR_INVALID;
     if (d->chan_op && !chan) return PDE_ERR_INVALID;
     if (d->skip && !skipw) return PDE_ERR_INVALID;
     if (!aligned16(u) || !aligned16(out)) return PDE_ERR_INVALID;
-    if (d->B == 0) return PDE_OK;
     // with checkpoints to write: the half-line kernel (its backward twin needs them); plain
     // inference: the whole-line kernel below, which is the faster forward
     if (ckpt && split::supported(*d))
@@ -1189,8 +1294,9 @@ extern "C" int pde_adi_forward_train(const pde_adi_desc *d, const void *tables, 
     // a warp advances NP sample pairs; small batches spread over more warps instead
     // measured: two pairs per warp win for the single-channel 28 x 28 layers (coefficient rows shared
     // by four samples), one pair for the three-channel 32 x 32 ones (254 registers cost residency)
-    int NP = env_int("PDE_B200_FWD_NP", d->C == 1 ? 2 : 1) == 1 ? 1 : 2;
+    int NP = d->C == 1 ? 2 : 1;
     if (NP == 2 && (d->B + 3) / 4 < props.sm_count * 4 * a.G) NP = 1;
+    if (tune_np(*d) == 1 || tune_np(*d) == 2) NP = tune_np(*d);
     a.nitems = (d->B + 2 * NP - 1) / (2 * NP);
     a.tables = static_cast<const char *>(tables);
     a.u = u; a.chan = chan; a.skipw = skipw; a.out = out;
@@ -1226,11 +1332,25 @@ extern "C" int pde_adi_backward_saved(const pde_adi_desc *d, const void *tables,
                                       float *g_skip, void *workspace, size_t workspace_bytes, void *stream) {
     int rc = validate(d);
     if (rc) return rc;
-    if (!tables || !u || !gout || !g_ab || !g_bb || !g_atc || !g_btc) return PDE_ERR_INVALID;
-    if (d->chan_op && (!chan || !g_chan)) return PDE_ERR_INVALID;
-    if (d->skip && (!skipw || !g_skip)) return PDE_ERR_INVALID;
-    if (!aligned16(u) || !aligned16(gout) || (gin && !aligned16(gin))) return PDE_ERR_INVALID;
+    if (!g_ab || !g_bb || !g_atc || !g_btc) return PDE_ERR_INVALID;
+    if (d->chan_op && !g_chan) return PDE_ERR_INVALID;
+    if (d->skip && !g_skip) return PDE_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->B == 0) {
+        // empty batch (a rank without samples): every gradient is exactly zero; u / gout / gin may be NULL
+        const size_t mapb = (size_t)d->C * d->N * d->N * sizeof(float);
+        PDE_CUDA_TRY(cudaMemsetAsync(g_ab, 0, mapb, st));
+        PDE_CUDA_TRY(cudaMemsetAsync(g_bb, 0, mapb, st));
+        PDE_CUDA_TRY(cudaMemsetAsync(g_atc, 0, mapb, st));
+        PDE_CUDA_TRY(cudaMemsetAsync(g_btc, 0, mapb, st));
+        if (g_chan) PDE_CUDA_TRY(cudaMemsetAsync(g_chan, 0, (size_t)d->C * d->C * sizeof(float), st));
+        if (g_skip) PDE_CUDA_TRY(cudaMemsetAsync(g_skip, 0, sizeof(float), st));
+        return PDE_OK;
+    }
+    if (!tables || !u || !gout) return PDE_ERR_INVALID;
+    if (d->chan_op && !chan) return PDE_ERR_INVALID;
+    if (d->skip && !skipw) return PDE_ERR_INVALID;
+    if (!aligned16(u) || !aligned16(gout) || (gin && !aligned16(gin))) return PDE_ERR_INVALID;
     if (d->B > 0 && split::supported(*d)) {
         const char *tb = static_cast<const char *>(tables);
         if (ckpt)
@@ -1266,17 +1386,6 @@ extern "C" int pde_adi_backward_saved(const pde_adi_desc *d, const void *tables,
     a.part_chan = a.part_maps + p.maps_floats;
     a.part_skip = a.part_chan + p.chan_floats;
     const int nw = p.grid * p.warps;
-    if (d->B == 0) {
-        // empty batch: every gradient is exactly zero
-        const size_t mapb = (size_t)d->C * d->N * d->N * sizeof(float);
-        PDE_CUDA_TRY(cudaMemsetAsync(g_ab, 0, mapb, st));
-        PDE_CUDA_TRY(cudaMemsetAsync(g_bb, 0, mapb, st));
-        PDE_CUDA_TRY(cudaMemsetAsync(g_atc, 0, mapb, st));
-        PDE_CUDA_TRY(cudaMemsetAsync(g_btc, 0, mapb, st));
-        if (g_chan) PDE_CUDA_TRY(cudaMemsetAsync(g_chan, 0, (size_t)d->C * d->C * sizeof(float), st));
-        if (g_skip) PDE_CUDA_TRY(cudaMemsetAsync(g_skip, 0, sizeof(float), st));
-        return PDE_OK;
-    }
     rc = launch_bwd(a, p, st);
     if (rc) return rc;
     launch_finish(*d, nw, nw, a.part_maps, a.part_chan, a.part_skip, skipw, g_ab, g_atc, g_bb, g_btc, g_chan, g_skip, st);

@@ -5,7 +5,6 @@
 //                 coefficient loads.
 #pragma once
 #include <cstdio>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -16,17 +15,18 @@ constexpr int kHeaderBytes = 4096;
 constexpr float kAmpLimit = 256.0f;  // see DESIGN.md "reverse reconstruction"
 
 struct Header {
-    int mode_exact;
-    float amp_bound;
+    // call-wide flags, folded from the per-sweep entries by flags_kernel (header_flags)
+    int mode_exact;    // rebuilding sweep inputs would amplify rounding noise: per-sweep checkpoints
     int any_clamped;   // 1 if any cell of any sweep sits outside the clamp interval
-    int pad;
+    int pad[2];
+    // written per sweep by prepare_kernel (one block per sweep, no cross-block step)
     float scale[PDE_MAX_SWEEPS];
     float t[PDE_MAX_SWEEPS];
     unsigned rmax_bits[PDE_MAX_SWEEPS];
     int clamped[PDE_MAX_SWEEPS];   // 1 if any cell of sweep s sits outside the clamp interval
     // sweeps with the same axis, time, time step and spacing have the same tables (Strang: the
     // closing half sweep of a step and the opening one of the next): slot[s] numbers the distinct
-    // ones in order of first appearance, rep[u] is the first sweep of slot u
+    // ones in order of first appearance, rep[u] is the first sweep of slot u (host computed)
     int nslots;
     short slot[PDE_MAX_SWEEPS];
     short rep[PDE_MAX_SWEEPS];
@@ -77,10 +77,45 @@ struct Args {
     float *ckpt;
 };
 
-inline int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    if (!v || !*v) return dflt;
-    return atoi(v);
+// pde_adi_desc.tuning (include/pde_b200.h)
+__host__ __device__ inline int tune_impl(const pde_adi_desc &d) { return d.tuning & 3; }
+__host__ __device__ inline int tune_p(const pde_adi_desc &d) { return (d.tuning >> 2) & 7; }
+__host__ __device__ inline int tune_qf(const pde_adi_desc &d) { return (d.tuning >> 5) & 7; }
+__host__ __device__ inline int tune_np(const pde_adi_desc &d) { return (d.tuning >> 8) & 3; }
+
+// The sweep -> distinct-table map, computed on the host from the schedule (kernel parameter).
+struct SlotMap {
+    int nslots;
+    short slot[PDE_MAX_SWEEPS];
+    short rep[PDE_MAX_SWEEPS];
+};
+
+// Call-wide flags from the per-sweep header entries, computed by one warp (a few loads per lane).  exact: rebuilding a sweep's input from its output would amplify rounding noise
+// by more than kAmpLimit inside some step (DESIGN.md "reverse reconstruction") -> per-sweep
+// checkpoints.  any_clamped: some cell of some sweep sits outside the clamp interval.
+__device__ __forceinline__ void header_flags(const Header *hdr, int steps, int sps, bool *exact, bool *any_clamped) {
+    const int lane = threadIdx.x & 31;
+    float amp = 1.0f;
+    int cl = 0;
+    for (int step = lane; step < steps; step += 32) {
+        float a = 1.0f;
+        cl |= hdr->clamped[step * sps];
+        // the first sweep of a step is never rebuilt (its input is a checkpoint)
+        for (int k = 1; k < sps; ++k) {
+            a *= 1.0f + 4.0f * __uint_as_float(hdr->rmax_bits[step * sps + k]);
+            cl |= hdr->clamped[step * sps + k];
+        }
+        amp = fmaxf(amp, a);
+        if (!(a == a)) amp = __int_as_float(0x7fc00000);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float other = __shfl_xor_sync(kFullMask, amp, o);
+        amp = (amp == amp && other == other) ? fmaxf(amp, other) : __int_as_float(0x7fc00000);
+        cl |= __shfl_xor_sync(kFullMask, cl, o);
+    }
+    *exact = amp > kAmpLimit || !(amp == amp);
+    *any_clamped = cl != 0;
 }
 
 // adi.cu: sums the per-set gradient partials (double, fixed order).  Map partials: nsets_maps sets
@@ -91,12 +126,21 @@ void launch_finish(const pde_adi_desc &d, int nsets_maps, int nsets_small, const
 
 // adi_split.cu
 namespace split {
+// mirrored index of a row / column / line: 0 .. H-1 from the near edge, H .. N-1 from the far edge
+// inwards (an involution)
+__host__ __device__ __forceinline__ int mirror(int i, int N) {
+    const int H = N / 2;
+    return i < H ? i : H + (N - 1 - i);
+}
+// floats per table in the half-line layout [s][c][k/4][line][half][k%4] (k = mirrored cell)
+__host__ __device__ inline size_t stab_floats_per_table(const pde_adi_desc &d) {
+    const int H = d.N / 2, HQ = (H + 3) / 4;
+    return (size_t)d.steps * sweeps_per_step(d) * d.C * HQ * d.N * 2 * 4;
+}
 bool supported(const pde_adi_desc &d);
 size_t table_floats(const pde_adi_desc &d);             // 4 tables in the split layout
 size_t checkpoint_bytes(const pde_adi_desc &d);
 size_t workspace_bytes(const pde_adi_desc &d);          // partials (+ exact-mode scratch), no checkpoints
-int prepare(const pde_adi_desc &d, const pde_adi_schedule &sch, const float *ab, const float *bb,
-            const float *atc, const float *btc, char *tables, cudaStream_t st);
 int forward(const pde_adi_desc &d, const char *tables, const float *u, const float *chan, const float *skipw,
             float *out, float *ckpt, cudaStream_t st);
 int backward(const pde_adi_desc &d, const char *tables, const float *u, const float *gout, const float *chan,

@@ -53,91 +53,6 @@ __device__ __forceinline__ int row_off(int R) {
     return R * SG<N, P>::RS + (R >= SG<N, P>::H ? SG<N, P>::HPAD : 0);
 }
 
-// mirrored index of a row / column / line: 0 .. H-1 from the near edge, H .. N-1 from the far edge
-// inwards (an involution)
-__host__ __device__ __forceinline__ int mirror(int i, int N) {
-    const int H = N / 2;
-    return i < H ? i : H + (N - 1 - i);
-}
-
-__host__ __device__ inline size_t stab_floats_per_table(const pde_adi_desc &d) {
-    const int H = d.N / 2, HQ = (H + 3) / 4;
-    return (size_t)d.steps * sweeps_per_step(d) * d.C * HQ * d.N * 2 * 4;
-}
-
-// ------------------------------------------------------------------------------------------
-// tables.  One thread per (sweep, channel, line): clamp -> smoothing -> r, then the twisted
-// pivots: top-down for cells 0 .. H-1 (op for op the reference's elimination), bottom-up for cells
-// N-1 .. H+1, and cell H closes both.  Layout [s][c][k/4][line][half][k%4] (k = mirrored cell).
-// ------------------------------------------------------------------------------------------
-__global__ void stables_kernel(pde_adi_desc d, pde_adi_schedule sch, const float *__restrict__ ab,
-                               const float *__restrict__ bb, const float *__restrict__ atc,
-                               const float *__restrict__ btc, float *stab) {
-    const int sps = sweeps_per_step(d), S = d.steps * sps, N = d.N, C = d.C, H = N / 2, HQ = (H + 3) / 4;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= S * C * N) return;
-    const int line = idx % N, c = (idx / N) % C, s = idx / (N * C);
-    const int axis = sweep_axis(s % sps);
-    const float *base = axis ? bb : ab, *tc = axis ? btc : atc;
-    const float tt = sch.t[s], dts = sch.dts[s], h2 = sch.h2[s];
-    const float third = __fdiv_rn(1.0f, 3.0f);
-    const size_t T = stab_floats_per_table(d);
-    float *tr = stab, *tinv = stab + T, *te = stab + 2 * T, *tm = stab + 3 * T;
-
-    float kap[32], msk[32], r[32], den[32];
-    for (int i = 0; i < N; ++i) {
-        const size_t q = axis == 0 ? ((size_t)c * N + line) * N + i : ((size_t)c * N + i) * N + line;
-        const float raw = __fadd_rn(base[q], __fmul_rn(tc[q], tt));
-        bool m = raw >= d.cmin;
-        float k = raw < d.cmin ? d.cmin : raw;
-        if (d.has_max) {
-            m = m && raw <= d.cmax;
-            k = k > d.cmax ? d.cmax : k;
-        }
-        kap[i] = k;
-        msk[i] = m ? 1.0f : 0.0f;
-    }
-    for (int i = 0; i < N; ++i) {
-        float ks = kap[i];
-        if (d.smooth) {
-            const float a0 = __fmul_rn(kap[i > 0 ? i - 1 : 0], third);
-            const float a1 = __fmul_rn(kap[i], third);
-            const float a2 = __fmul_rn(kap[i < N - 1 ? i + 1 : N - 1], third);
-            ks = __fadd_rn(__fadd_rn(a0, a1), a2);
-        }
-        r[i] = __fdiv_rn(__fmul_rn(ks, dts), h2);
-    }
-    auto diag = [&](int i) {
-        return (i == 0 || i == N - 1) ? __fadd_rn(1.0f, r[i]) : __fadd_rn(1.0f, __fmul_rn(2.0f, r[i]));
-    };
-    float cst = 0.0f;   // c*_{i-1} = -r_{i-1} / den_{i-1}
-    for (int i = 0; i < H; ++i) {
-        den[i] = i == 0 ? __fadd_rn(diag(i), d.eps) : __fadd_rn(__fsub_rn(diag(i), __fmul_rn(-r[i], cst)), d.eps);
-        cst = __fdiv_rn(-r[i], den[i]);
-    }
-    float ast = 0.0f;   // mirror image from the far end
-    for (int i = N - 1; i > H; --i) {
-        den[i] = i == N - 1 ? __fadd_rn(diag(i), d.eps) : __fadd_rn(__fsub_rn(diag(i), __fmul_rn(-r[i], ast)), d.eps);
-        ast = __fdiv_rn(-r[i], den[i]);
-    }
-    den[H] = __fadd_rn(__fsub_rn(__fsub_rn(diag(H), __fmul_rn(-r[H], cst)), __fmul_rn(-r[H], ast)), d.eps);
-
-    const int R = mirror(line, N);
-    for (int h = 0; h < 2; ++h)
-        for (int k = 0; k < 4 * HQ; ++k) {
-            const size_t o = ((((size_t)s * C + c) * HQ + k / 4) * N + R) * 8 + h * 4 + (k & 3);
-            if (k < H) {
-                const int i = h ? N - 1 - k : k;
-                tr[o] = r[i];
-                tinv[o] = __fdiv_rn(1.0f, den[i]);
-                te[o] = __fdiv_rn(r[i], den[i]);
-                tm[o] = msk[i];
-            } else {
-                tr[o] = 0.0f; tinv[o] = 0.0f; te[o] = 0.0f; tm[o] = 0.0f;
-            }
-        }
-}
-
 // ------------------------------------------------------------------------------------------
 // tile: N rows (mirrored order) x NC chunks x P pairs x {cell 2m, cell 2m+1} x {sample a, b}
 // ------------------------------------------------------------------------------------------
@@ -1169,13 +1084,14 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
 // host side
 // ------------------------------------------------------------------------------------------
 bool supported(const pde_adi_desc &d) {
-    if (env_int("PDE_B200_ADI_LEGACY", 0)) return false;
+    const int impl = tune_impl(d);
+    if (impl == PDE_ADI_TUNE_IMPL_WHOLE_LINE) return false;
     if (d.steps < 1 || d.B < 1 || d.C > 3) return false;
     if (d.N != 28 && d.N != 32) return false;
     // Below two groups of two sample pairs per SM the call is latency bound either way: stay with
-    // the whole-line kernels (one pair per warp spreads a small batch over more SMs, one launch
-    // less).  PDE_B200_ADI_SPLIT=1 / PDE_B200_SPLIT_P force the half-line kernels (tests).
-    if (env_int("PDE_B200_ADI_SPLIT", 0) || env_int("PDE_B200_SPLIT_P", 0)) return true;
+    // the whole-line kernels (one pair per warp spreads a small batch over more SMs).  The tuning
+    // field forces the half-line kernels (tests).
+    if (impl == PDE_ADI_TUNE_IMPL_HALF_LINE || tune_p(d) != 0) return true;
     DeviceProps props;
     if (query_props(&props) != PDE_OK) return false;
     return (d.B + 3) / 4 >= 2 * props.sm_count;
@@ -1207,7 +1123,7 @@ static int make_plan(const pde_adi_desc &d, Plan *p) {
     // pairs per group: 4 for the single-channel layers once the batch fills the GPU with such groups
     p->P = 2;
     if (d.C == 1 && d.chan_op == 0) {
-        const int forced = env_int("PDE_B200_SPLIT_P", 0);
+        const int forced = tune_p(d);
         if (forced == 4 || (forced != 2 && (d.B + 7) / 8 >= 2 * sm)) p->P = 4;
     }
     if (d.N == 28) { if (p->P == 4) fill_geo<28, 4>(d, p); else fill_geo<28, 2>(d, p); }
@@ -1215,14 +1131,13 @@ static int make_plan(const pde_adi_desc &d, Plan *p) {
     else return PDE_ERR_UNSUPPORTED;
     p->ngroups = (d.B + 2 * p->P - 1) / (2 * p->P);
     // groups per block: as many as still leave two blocks of work per SM (and fit shared memory)
-    auto pick = [&](int qmax, size_t tiles_per_group, const char *env) {
+    auto pick = [&](int qmax, size_t tiles_per_group, int forced) {
         int q = qmax;
         while (q > 1 && ((p->ngroups + q - 1) / q < 2 * sm || (size_t)q * tiles_per_group * p->tile_bytes > 101 * 1024)) q >>= 1;
-        const int forced = env_int(env, 0);
         if (forced == 1 || forced == 2 || (forced == 4 && qmax == 4)) q = forced;
         return q;
     };
-    p->Qf = pick(p->P == 4 ? 4 : 2, (size_t)d.C, "PDE_B200_SPLIT_QF");
+    p->Qf = pick(p->P == 4 ? 4 : 2, (size_t)d.C, tune_qf(d));
     p->Qb = 1;   // measured: the backward kernel gains nothing from sharing coefficient loads
     const int warps = p->threads / 32;
     const int blocks4 = (warps + 3) / 4;
@@ -1281,29 +1196,27 @@ static int plan_bwd_grid(const pde_adi_desc &d, const Plan &p, BwdLaunch *b) {
     // x tile sets double buffered, g sets too for P == 4, two coefficient stages of two tables
     b->smem = (size_t)(p.P >= 4 ? 4 : 3) * d.C * p.tile_bytes + (size_t)4 * d.C * ((d.N / 2 + 3) / 4) * d.N * 2 * 16;
     if (b->smem > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
-    PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
     // residency from first principles (the occupancy calculator answers 1 block / SM for kernels
     // that allocate tensor memory)
-    cudaFuncAttributes fa;
-    PDE_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+    KernelInfo fa;
+    rc = kernel_info(kern, b->smem, &fa);
+    if (rc) return rc;
     // registers: 16 K per scheduler, a block's warps dealt round-robin over the four schedulers
     const int warps = p.threads / 32;
-    const int regs_per_warp = ((fa.numRegs + 7) / 8) * 8 * 32;
+    const int regs_per_warp = ((fa.regs + 7) / 8) * 8 * 32;
     int occ = 16384 / (regs_per_warp * ((warps + 3) / 4));
-    const int by_smem = (int)((size_t)(228 * 1024) / (b->smem + fa.sharedSizeBytes + 1024));
+    const int by_smem = (int)((size_t)(228 * 1024) / (b->smem + fa.static_smem + 1024));
     const int by_threads = 2048 / p.threads;
     const int by_tmem = 512 / p.tmem_cols;
     if (by_smem < occ) occ = by_smem;
     if (by_threads < occ) occ = by_threads;
     if (by_tmem < occ) occ = by_tmem;
-    const int cap_env = env_int("PDE_B200_SPLIT_BWD_OCC", 0);
-    if (cap_env > 0 && cap_env < occ) occ = cap_env;
     if (occ < 1) occ = 1;
     b->occ = occ;
     b->nitems = p.ngroups;
-    if (env_int("PDE_B200_DEBUG", 0))
+    if (debug_enabled())
         fprintf(stderr, "[pde_b200] split bwd plan: N=%d C=%d P=%d threads=%d smem=%zu regs=%d occ=%d tmem=%d\n", d.N,
-                d.C, p.P, p.threads, b->smem, fa.numRegs, occ, p.tmem_cols);
+                d.C, p.P, p.threads, b->smem, fa.regs, occ, p.tmem_cols);
     const int cap = props.sm_count * occ;
     b->grid = b->nitems < cap ? b->nitems : cap;
     if (b->grid < 1) b->grid = 1;
@@ -1334,15 +1247,6 @@ size_t workspace_bytes(const pde_adi_desc &d) {
     return (w.scratch_floats + w.maps_floats + w.chan_floats + w.skip_floats) * sizeof(float) + 512;
 }
 
-int prepare(const pde_adi_desc &d, const pde_adi_schedule &sch, const float *ab, const float *bb, const float *atc,
-            const float *btc, char *tables, cudaStream_t st) {
-    const int S = d.steps * sweeps_per_step(d);
-    const int n = S * d.C * d.N;
-    float *stab = reinterpret_cast<float *>(tables + kHeaderBytes) + 4 * table_elems(d);
-    if (n > 0) stables_kernel<<<(n + 127) / 128, 128, 0, st>>>(d, sch, ab, bb, atc, btc, stab);
-    return cuda_last_error();
-}
-
 static void fill_args(const pde_adi_desc &d, const char *tables, Args *a) {
     a->d = d;
     a->sps = sweeps_per_step(d);
@@ -1365,12 +1269,9 @@ int forward(const pde_adi_desc &d, const char *tables, const float *u, const flo
     // Qf groups of tiles, two coefficient stages of two tables
     const size_t smem = (size_t)d.C * p.Qf * p.tile_bytes + (size_t)4 * d.C * ((d.N / 2 + 3) / 4) * d.N * 2 * 16;
     if (smem > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
-    PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    PDE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, p.threads, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int cap_env = env_int("PDE_B200_SPLIT_FWD_OCC", 0);
-    if (cap_env > 0 && cap_env < per_sm) per_sm = cap_env;
+    rc = cached_occupancy(kern, p.threads, smem, &per_sm);
+    if (rc) return rc;
     Args a{};
     fill_args(d, tables, &a);
     a.nitems = (p.ngroups + p.Qf - 1) / p.Qf;
@@ -1378,7 +1279,7 @@ int forward(const pde_adi_desc &d, const char *tables, const float *u, const flo
     a.ckpt = ckpt ? reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ckpt) + 255u) & ~(uintptr_t)255u) : nullptr;
     const int cap = props.sm_count * per_sm;
     const int grid = a.nitems < cap ? a.nitems : cap;
-    if (env_int("PDE_B200_DEBUG", 0))
+    if (debug_enabled())
         fprintf(stderr, "[pde_b200] split fwd plan: N=%d C=%d P=%d Q=%d threads=%d smem=%zu occ=%d grid=%d\n", d.N, d.C, p.P,
                 p.Qf, p.threads, smem, per_sm, grid);
     void *params[] = {&a};

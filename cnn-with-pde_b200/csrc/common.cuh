@@ -4,6 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
 #include "pde_b200.h"
 
 #define PDE_CUDA_TRY(expr)                          \
@@ -43,14 +47,118 @@ struct DeviceProps {
     int max_smem_optin;
 };
 
-// cudaGetDeviceProperties is slow; the two attributes we need are cheap to query per call
-// and keep the library free of global mutable state.
+// ------------------------------------------------------------------------------------------
+// Launch-attribute cache.  Device properties, a kernel's register count / static shared memory,
+// "dynamic shared-memory limit raised" and occupancy answers never change for a (device, kernel)
+// pair; asking the runtime on every call costs more host time than the small-batch kernels run.
+// Read-mostly, filled on first use under a mutex; it holds nothing a caller can observe.
+// ------------------------------------------------------------------------------------------
+struct KernelInfo {
+    int regs;
+    size_t static_smem;
+};
+
+namespace detail {
+struct KernelKey {
+    int dev;
+    const void *kern;
+    int threads;     // 0 for the attribute entry
+    size_t smem;     // 0 for the attribute entry
+    bool operator<(const KernelKey &o) const {
+        if (dev != o.dev) return dev < o.dev;
+        if (kern != o.kern) return kern < o.kern;
+        if (threads != o.threads) return threads < o.threads;
+        return smem < o.smem;
+    }
+};
+struct KernelEntry {
+    KernelInfo info;
+    size_t smem_limit;   // largest dynamic shared-memory size the kernel has been opted in to
+    int occ;
+};
+inline std::mutex &cache_mutex() {
+    static std::mutex m;
+    return m;
+}
+inline std::map<KernelKey, KernelEntry> &kernel_cache() {
+    static std::map<KernelKey, KernelEntry> c;
+    return c;
+}
+inline std::map<int, DeviceProps> &props_cache() {
+    static std::map<int, DeviceProps> c;
+    return c;
+}
+}  // namespace detail
+
 inline int query_props(DeviceProps *p) {
     int dev = 0;
     PDE_CUDA_TRY(cudaGetDevice(&dev));
-    PDE_CUDA_TRY(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev));
-    PDE_CUDA_TRY(cudaDeviceGetAttribute(&p->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    std::lock_guard<std::mutex> lock(detail::cache_mutex());
+    auto &c = detail::props_cache();
+    auto it = c.find(dev);
+    if (it == c.end()) {
+        DeviceProps q;
+        PDE_CUDA_TRY(cudaDeviceGetAttribute(&q.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        PDE_CUDA_TRY(cudaDeviceGetAttribute(&q.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        it = c.emplace(dev, q).first;
+    }
+    *p = it->second;
     return PDE_OK;
+}
+
+// Registers and static shared memory of `kern`; makes sure it may be launched with `smem` bytes of
+// dynamic shared memory.
+inline int kernel_info(const void *kern, size_t smem, KernelInfo *out) {
+    int dev = 0;
+    PDE_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(detail::cache_mutex());
+    auto &c = detail::kernel_cache();
+    const detail::KernelKey key{dev, kern, 0, 0};
+    auto it = c.find(key);
+    if (it == c.end()) {
+        cudaFuncAttributes fa;
+        PDE_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+        detail::KernelEntry e{};
+        e.info.regs = fa.numRegs;
+        e.info.static_smem = fa.sharedSizeBytes;
+        e.smem_limit = 48 * 1024;
+        it = c.emplace(key, e).first;
+    }
+    if (smem > it->second.smem_limit) {
+        PDE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        it->second.smem_limit = smem;
+    }
+    if (out) *out = it->second.info;
+    return PDE_OK;
+}
+
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor, remembered (also opts the kernel in to `smem`)
+inline int cached_occupancy(const void *kern, int threads, size_t smem, int *per_sm) {
+    int rc = kernel_info(kern, smem, nullptr);
+    if (rc) return rc;
+    int dev = 0;
+    PDE_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(detail::cache_mutex());
+    auto &c = detail::kernel_cache();
+    const detail::KernelKey key{dev, kern, threads, smem + 1};
+    auto it = c.find(key);
+    if (it == c.end()) {
+        detail::KernelEntry e{};
+        PDE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e.occ, kern, threads, smem));
+        if (e.occ < 1) e.occ = 1;
+        it = c.emplace(key, e).first;
+    }
+    *per_sm = it->second.occ;
+    return PDE_OK;
+}
+
+// PDE_B200_DEBUG=1 prints the launch plans; read once per process (it changes no result)
+inline bool debug_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("PDE_B200_DEBUG");
+        return v && *v && *v != '0';
+    }();
+    return on;
 }
 
 }  // namespace pde

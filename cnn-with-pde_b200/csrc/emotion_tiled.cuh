@@ -388,13 +388,10 @@ __global__ void emo_finish_tiled(pde_emo_desc d, int nwarps, const double *__res
 }
 
 // ------------------------------------------------------------------------------------------ host
-static bool emo_tiled_ok(const pde_emo_desc *d) { return d->N == 16 || d->N == 32 || d->N == 48; }
-
 // warps in flight per SM during the backward pass: each owns Nt * N * N * 4 bytes of history
 // (92 KB for the reference model); 8 per SM keep the whole history (109 MB) inside the 126 MB L2
 static int emo_tiled_bwd_grid(const pde_emo_desc *d, int sm_count) {
-    int per_sm = env_flag("PDE_B200_EMO_BWD_BLOCKS", 2);
-    if (per_sm < 1 || per_sm > 4) per_sm = 2;
+    const int per_sm = 2;
     int grid = sm_count * per_sm;
     const int want = (d->B + kTileWarps - 1) / kTileWarps;
     if (grid > want) grid = want;
@@ -413,8 +410,8 @@ static size_t emo_tiled_workspace_bytes(const pde_emo_desc *d, int sm_count) {
 template <int N>
 static int emo_tiled_forward_n(const EmoArgs &a, int sm_count, cudaStream_t st) {
     int per_sm = 1;   // persistent grid: the blocks resident at once (register bound)
-    PDE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emo_fwd_tiled<N>, kTileWarps * 32, 0));
-    if (per_sm < 1) per_sm = 1;
+    int rc = cached_occupancy(reinterpret_cast<const void *>(emo_fwd_tiled<N>), kTileWarps * 32, 0, &per_sm);
+    if (rc) return rc;
     const int want = (a.d.B + kTileWarps - 1) / kTileWarps;
     int grid = sm_count * per_sm;
     if (grid > want) grid = want;

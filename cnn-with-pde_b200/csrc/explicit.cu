@@ -565,9 +565,9 @@ static int emo_bwd_grid(const pde_emo_desc *d, const DeviceProps &props, size_t 
     return (int)(grid < 1 ? 1 : grid);
 }
 
-static int env_flag(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
+// the register-tiled kernels serve plane edges 16 / 32 / 48 unless the descriptor asks for the generic ones
+static bool emo_use_tiled(const pde_emo_desc *d) {
+    return (d->N == 16 || d->N == 32 || d->N == 48) && !(d->tuning & PDE_EMO_TUNE_GENERIC);
 }
 
 }  // namespace expl
@@ -591,9 +591,9 @@ extern "C" int pde_tiny_forward(const pde_tiny_desc *d, const float *u, const fl
                                 const float *channel_scaling, float *out, void *stream) {
     int rc = tiny_validate(d);
     if (rc) return rc;
+    if (d->B == 0) return PDE_OK;   // empty batch: a no-op, its tensor pointers may be NULL
     if (!u || !alpha_base || !channel_scaling || !out) return PDE_ERR_INVALID;
     if (!aligned16(u) || !aligned16(out)) return PDE_ERR_INVALID;
-    if (d->B == 0) return PDE_OK;
     DeviceProps props;
     rc = query_props(&props);
     if (rc) return rc;
@@ -604,7 +604,8 @@ extern "C" int pde_tiny_forward(const pde_tiny_desc *d, const float *u, const fl
     rc = tiny_plan(d, false, props.max_smem_optin, &a.stages, &smem);
     if (rc) return rc;
     const int grid = tiny_grid(d, props, smem, false);
-    PDE_CUDA_TRY(cudaFuncSetAttribute(tiny_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rc = kernel_info(reinterpret_cast<const void *>(tiny_fwd_kernel), smem, nullptr);
+    if (rc) return rc;
     tiny_fwd_kernel<<<grid, kTinyThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     return cuda_last_error();
 }
@@ -615,14 +616,15 @@ extern "C" int pde_tiny_backward(const pde_tiny_desc *d, const float *u, const f
                                  size_t workspace_bytes, void *stream) {
     int rc = tiny_validate(d);
     if (rc) return rc;
-    if (!u || !gout || !alpha_base || !channel_scaling || !g_alpha_base || !g_channel_scaling) return PDE_ERR_INVALID;
-    if (!aligned16(u) || !aligned16(gout) || (gin && !aligned16(gin))) return PDE_ERR_INVALID;
+    if (!g_alpha_base || !g_channel_scaling) return PDE_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (d->B == 0) {
+    if (d->B == 0) {   // empty batch: zero gradients; u / gout / gin may be NULL
         PDE_CUDA_TRY(cudaMemsetAsync(g_alpha_base, 0, d->C * sizeof(float), st));
         PDE_CUDA_TRY(cudaMemsetAsync(g_channel_scaling, 0, d->C * sizeof(float), st));
         return PDE_OK;
     }
+    if (!u || !gout || !alpha_base || !channel_scaling) return PDE_ERR_INVALID;
+    if (!aligned16(u) || !aligned16(gout) || (gin && !aligned16(gin))) return PDE_ERR_INVALID;
     DeviceProps props;
     rc = query_props(&props);
     if (rc) return rc;
@@ -637,7 +639,8 @@ extern "C" int pde_tiny_backward(const pde_tiny_desc *d, const float *u, const f
     const size_t need = (size_t)grid * 2 * sizeof(float) + 256;
     if (!workspace || workspace_bytes < need) return PDE_ERR_WORKSPACE;
     a.part = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255u) & ~(uintptr_t)255u);
-    PDE_CUDA_TRY(cudaFuncSetAttribute(tiny_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rc = kernel_info(reinterpret_cast<const void *>(tiny_bwd_kernel), smem, nullptr);
+    if (rc) return rc;
     tiny_bwd_kernel<<<grid, kTinyThreads, smem, st>>>(a);
     rc = cuda_last_error();
     if (rc) return rc;
@@ -651,7 +654,7 @@ extern "C" size_t pde_emotion_backward_workspace_bytes(const pde_emo_desc *d) {
     DeviceProps props;
     if (query_props(&props) != PDE_OK) return 0;
     const size_t generic = (size_t)props.sm_count * 4 * 2 * kEmoMaxN * sizeof(float) + 256;
-    if (emo_tiled_ok(d) && env_flag("PDE_B200_EMO_TILED", 1)) {
+    if (emo_use_tiled(d)) {
         const size_t tiled = emo_tiled_workspace_bytes(d, props.sm_count);
         return tiled > generic ? tiled : generic;
     }
@@ -662,20 +665,21 @@ extern "C" int pde_emotion_forward(const pde_emo_desc *d, const float *u0, const
                                    const float *ys, float *out, void *stream) {
     int rc = emo_validate(d);
     if (rc) return rc;
+    if (d->B == 0) return PDE_OK;   // empty batch: a no-op, its tensor pointers may be NULL
     if (!u0 || !w6 || !xs || !ys || !out) return PDE_ERR_INVALID;
-    if (d->B == 0) return PDE_OK;
     DeviceProps props;
     rc = query_props(&props);
     if (rc) return rc;
     EmoArgs a{};
     a.d = *d; a.u0 = u0; a.w6 = w6; a.xs = xs; a.ys = ys; a.out = out;
-    if (emo_tiled_ok(d) && env_flag("PDE_B200_EMO_TILED", 1))
+    if (emo_use_tiled(d))
         return emo_tiled_forward(a, props.sm_count, static_cast<cudaStream_t>(stream));
     const size_t smem = emo_fwd_smem(d);
     const int threads = emo_threads(d->N);
     long grid = (long)props.sm_count * 6;
     if (grid > d->B) grid = d->B;
-    PDE_CUDA_TRY(cudaFuncSetAttribute(emo_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rc = kernel_info(reinterpret_cast<const void *>(emo_fwd_kernel), smem, nullptr);
+    if (rc) return rc;
     emo_fwd_kernel<<<(int)grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     return cuda_last_error();
 }
@@ -685,16 +689,17 @@ extern "C" int pde_emotion_backward(const pde_emo_desc *d, const float *u0, cons
                                     size_t workspace_bytes, void *stream) {
     int rc = emo_validate(d);
     if (rc) return rc;
-    if (!u0 || !gout || !w6 || !xs || !ys || !g_w6) return PDE_ERR_INVALID;
+    if (!g_w6) return PDE_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (d->B == 0) {
+    if (d->B == 0) {   // empty batch: zero gradients; u0 / gout / gin may be NULL
         PDE_CUDA_TRY(cudaMemsetAsync(g_w6, 0, 6 * sizeof(float), st));
         return PDE_OK;
     }
+    if (!u0 || !gout || !w6 || !xs || !ys) return PDE_ERR_INVALID;
     DeviceProps props;
     rc = query_props(&props);
     if (rc) return rc;
-    if (emo_tiled_ok(d) && env_flag("PDE_B200_EMO_TILED", 1)) {
+    if (emo_use_tiled(d)) {
         if (!workspace || workspace_bytes < emo_tiled_workspace_bytes(d, props.sm_count)) return PDE_ERR_WORKSPACE;
         EmoArgs t{};
         t.d = *d; t.u0 = u0; t.gout = gout; t.w6 = w6; t.xs = xs; t.ys = ys; t.gin = gin;
@@ -710,7 +715,8 @@ extern "C" int pde_emotion_backward(const pde_emo_desc *d, const float *u0, cons
     a.d = *d; a.u0 = u0; a.gout = gout; a.w6 = w6; a.xs = xs; a.ys = ys; a.gin = gin;
     a.need_gin = gin != nullptr;
     a.part = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255u) & ~(uintptr_t)255u);
-    PDE_CUDA_TRY(cudaFuncSetAttribute(emo_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rc = kernel_info(reinterpret_cast<const void *>(emo_bwd_kernel), smem, nullptr);
+    if (rc) return rc;
     emo_bwd_kernel<<<grid, emo_threads(d->N), smem, st>>>(a);
     rc = cuda_last_error();
     if (rc) return rc;

@@ -4,15 +4,24 @@ Each Function saves its inputs and, for the implicit family, the factorised coef
 the call plus -- when the half-line kernels serve it -- the state at the end of every step
 (`pde_adi_forward_train`); everything else of the forward trajectory is rebuilt on-chip by the
 backward kernels.
+
+Host-side cost matters at the reference's own batch sizes (a call is a few tens of microseconds of
+GPU time): everything that depends only on (configuration, batch, device) -- descriptor, sweep
+schedule, buffer sizes -- is computed once and cached (`_adi_plan`), the gradient outputs share one
+allocation, and under `torch.no_grad()` the coefficient tables are reused while the parameters'
+version counters have not moved.
 """
 from __future__ import annotations
 
+import contextlib
+import functools
 import os
 
 from ctypes import byref
 from dataclasses import dataclass
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _cabi
 from .schedule import adi_schedule
@@ -35,9 +44,38 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _guard(device):
+    """Device guard only when the tensor does not live on the current device."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return contextlib.nullcontext()
+    return torch.cuda.device(device)
+
+
 def _bytes(n: int, device) -> torch.Tensor:
     # caching-allocator blocks are 512-byte aligned, which covers the 256-byte requirement
     return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
+
+
+def _contig(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def env_tuning() -> int:
+    """The kernel-variant switches of the test suite and of A/B timing runs, as a
+    `pde_adi_desc.tuning` value.  This is the only place they are read: the value travels inside the
+    descriptor, is saved with the autograd context, and so cannot differ between forward and backward.
+
+        PDE_B200_ADI_LEGACY=1   whole-line kernels (adi.cu) everywhere
+        PDE_B200_ADI_SPLIT=1    half-line kernels (adi_split.cu) also for small batches
+        PDE_B200_SPLIT_P=2|4    sample pairs per half-line group
+        PDE_B200_SPLIT_QF=1|2|4 groups per half-line forward block
+        PDE_B200_FWD_NP=1|2     sample pairs per whole-line forward warp
+    """
+    env = os.environ
+    impl = _cabi.TUNE_IMPL_WHOLE_LINE if env.get("PDE_B200_ADI_LEGACY") else (
+        _cabi.TUNE_IMPL_HALF_LINE if env.get("PDE_B200_ADI_SPLIT") else 0)
+    num = lambda k: int(env.get(k) or 0)   # noqa: E731
+    return _cabi.adi_tuning(impl, num("PDE_B200_SPLIT_P"), num("PDE_B200_SPLIT_QF"), num("PDE_B200_FWD_NP"))
 
 
 # ------------------------------------------------------------------------------ implicit ADI
@@ -58,9 +96,54 @@ class AdiConfig:
     cmax: float = 10.0
     eps: float = 1e-6
 
-    def desc(self, B: int) -> "_cabi.AdiDesc":
+    def desc(self, B: int, tuning: int = 0) -> "_cabi.AdiDesc":
         return _cabi.AdiDesc(B, self.C, self.N, self.steps, int(self.lie), int(self.smooth), int(self.has_max),
-                             self.chan_op, int(self.skip), self.cmin, self.cmax, self.eps)
+                             self.chan_op, int(self.skip), self.cmin, self.cmax, self.eps, tuning)
+
+
+class _AdiPlan:
+    """Everything about a call that depends only on (configuration, batch, tuning, device)."""
+    __slots__ = ("cfg", "B", "desc", "dref", "sched", "sref", "tables_bytes", "ckpt_bytes", "ws_saved_bytes", "ws_bytes",
+                 "grad_numel")
+
+    def __init__(self, cfg: AdiConfig, B: int, tuning: int):
+        L = _cabi.lib()
+        self.cfg, self.B = cfg, B
+        self.desc = cfg.desc(B, tuning)
+        self.dref = byref(self.desc)
+        self.tables_bytes = L.pde_adi_tables_bytes(self.dref)
+        if self.tables_bytes == 0:
+            raise _cabi.PdeB200Error(
+                f"unsupported implicit-layer configuration (size={cfg.N}, channels={cfg.C}, steps={cfg.steps}); "
+                "supported: size in {8,12,16,28,32}, channels <= 4")
+        self.sched = adi_schedule(cfg.steps, cfg.dt, cfg.hx, cfg.hy, cfg.lie)
+        self.sref = byref(self.sched)
+        self.ckpt_bytes = L.pde_adi_checkpoint_bytes(self.dref)
+        self.ws_saved_bytes = L.pde_adi_backward_saved_workspace_bytes(self.dref)
+        self.ws_bytes = L.pde_adi_backward_workspace_bytes(self.dref)
+        self.grad_numel = 4 * cfg.C * cfg.N * cfg.N
+
+
+@functools.lru_cache(maxsize=256)
+def _adi_plan(cfg: AdiConfig, B: int, tuning: int, device_index: int) -> _AdiPlan:
+    return _AdiPlan(cfg, B, tuning)
+
+
+# coefficient tables of inference calls, reused while the parameters have not changed:
+# (plan, data_ptr and version of the four maps) -> tables.  Never consulted under autograd or
+# during CUDA-graph capture (a captured graph must contain its own prepare launch).
+_TABLE_CACHE_SLOTS = 8
+_table_cache: "dict" = {}
+
+
+def _cached_tables(key):
+    return _table_cache.get(key)
+
+
+def _remember_tables(key, tables):
+    if len(_table_cache) >= _TABLE_CACHE_SLOTS:
+        _table_cache.pop(next(iter(_table_cache)))
+    _table_cache[key] = tables
 
 
 class _AdiFunction(torch.autograd.Function):
@@ -69,37 +152,39 @@ class _AdiFunction(torch.autograd.Function):
     def forward(ctx, u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg: AdiConfig, grad_mode: bool = True):
         _require_cuda(u, "PDE layer input")
         L = _cabi.lib()
-        u = u.contiguous()
-        B = u.shape[0]
-        maps = [p.detach().contiguous() for p in (alpha_base, beta_base, alpha_tc, beta_tc)]
+        u = _contig(u)
+        maps = [_contig(p) for p in (alpha_base, beta_base, alpha_tc, beta_tc)]
         for p in maps:
             _require_cuda(p, "PDE layer parameter")
-        chan_c = None if chan is None else chan.detach().contiguous()
-        skip_c = None if skipw is None else skipw.detach().contiguous()
-        d = cfg.desc(B)
-        with torch.cuda.device(u.device):
-            tables = _bytes(L.pde_adi_tables_bytes(byref(d)), u.device)
-            if tables.numel() <= 1:
-                raise _cabi.PdeB200Error(
-                    f"unsupported implicit-layer configuration (size={cfg.N}, channels={cfg.C}, steps={cfg.steps}); "
-                    "supported: size in {8,12,16,28,32}, channels <= 4")
-            sched = adi_schedule(cfg.steps, cfg.dt, cfg.hx, cfg.hy, cfg.lie)
-            _cabi.check(L.pde_adi_prepare(byref(d), byref(sched), *[_ptr(p) for p in maps], _ptr(tables), _stream()),
-                        "pde_adi_prepare")
+        chan_c = None if chan is None else _contig(chan.detach())
+        skip_c = None if skipw is None else _contig(skipw.detach())
+        dev = u.device
+        plan = _adi_plan(cfg, u.shape[0], env_tuning(), dev.index if dev.index is not None else torch.cuda.current_device())
+        # needs_input_grad ignores torch.no_grad() and grad mode is always off inside forward(): the
+        # caller passes the mode it saw
+        training = grad_mode and any(ctx.needs_input_grad)
+        with _guard(dev):
+            st = _stream()
+            tables, key = None, None
+            if not training and not torch.cuda.is_current_stream_capturing():
+                key = (plan, tuple((p.data_ptr(), p._version) for p in (alpha_base, beta_base, alpha_tc, beta_tc)))
+                tables = _cached_tables(key)
+            if tables is None:
+                tables = _bytes(plan.tables_bytes, dev)
+                _cabi.check(L.pde_adi_prepare(plan.dref, plan.sref, *[p.data_ptr() for p in maps], tables.data_ptr(), st),
+                            "pde_adi_prepare")
+                if key is not None:
+                    _remember_tables(key, tables)
             out = torch.empty_like(u)
             # under autograd the forward kernel also writes the state at the end of every step for
             # the backward kernel (0 bytes when the configuration is served by the kernels that
-            # rebuild the trajectory on-chip)
-            # PDE_B200_NO_CKPT=1 trades them for a recomputation inside pde_adi_backward (saves
-            # num_steps x the input in memory between forward and backward)
-            # (needs_input_grad ignores torch.no_grad() and grad mode is always off inside forward():
-            # the caller passes the mode it saw)
-            want_ck = grad_mode and any(ctx.needs_input_grad) and not os.environ.get("PDE_B200_NO_CKPT")
-            ck_bytes = L.pde_adi_checkpoint_bytes(byref(d)) if want_ck else 0
-            ckpt = _bytes(ck_bytes, u.device) if ck_bytes else None
-            _cabi.check(L.pde_adi_forward_train(byref(d), _ptr(tables), _ptr(u), _ptr(chan_c), _ptr(skip_c), _ptr(out),
-                                                _ptr(ckpt), _stream()), "pde_adi_forward_train")
-        ctx.cfg = cfg
+            # rebuild the trajectory on-chip).  PDE_B200_NO_CKPT=1 trades them for a recomputation
+            # inside pde_adi_backward (saves num_steps x the input in memory between the passes)
+            ck_bytes = plan.ckpt_bytes if training and not os.environ.get("PDE_B200_NO_CKPT") else 0
+            ckpt = _bytes(ck_bytes, dev) if ck_bytes else None
+            _cabi.check(L.pde_adi_forward_train(plan.dref, tables.data_ptr(), _ptr(u), _ptr(chan_c), _ptr(skip_c), _ptr(out),
+                                                _ptr(ckpt), st), "pde_adi_forward_train")
+        ctx.plan = plan   # the descriptor (tuning included) the backward pass must use as well
         ctx.has_chan = chan is not None
         ctx.has_skip = skipw is not None
         ctx.has_ckpt = ckpt is not None
@@ -109,31 +194,39 @@ class _AdiFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
     def backward(ctx, gout):
         L = _cabi.lib()
-        cfg = ctx.cfg
+        plan = ctx.plan
+        cfg = plan.cfg
         saved = list(ctx.saved_tensors)
         u, tables = saved[0], saved[1]
         rest = saved[2:]
         chan = rest.pop(0) if ctx.has_chan else None
         skipw = rest.pop(0) if ctx.has_skip else None
         ckpt = rest.pop(0) if ctx.has_ckpt else None
-        gout = gout.contiguous().float()
-        B = u.shape[0]
-        d = cfg.desc(B)
-        with torch.cuda.device(u.device):
-            ws_bytes = (L.pde_adi_backward_saved_workspace_bytes if ckpt is not None
-                        else L.pde_adi_backward_workspace_bytes)(byref(d))
-            ws = _bytes(ws_bytes, u.device)
+        gout = _contig(gout)
+        if gout.dtype != torch.float32:
+            gout = gout.float()
+        dev = u.device
+        with _guard(dev):
+            ws_bytes = plan.ws_saved_bytes if ckpt is not None else plan.ws_bytes
+            ws = _bytes(ws_bytes, dev)
             gin = torch.empty_like(u) if ctx.needs_input_grad[0] else None
-            gmaps = [torch.empty((cfg.C, cfg.N, cfg.N), dtype=torch.float32, device=u.device) for _ in range(4)]
-            gchan = torch.empty((cfg.C, cfg.C), dtype=torch.float32, device=u.device) if chan is not None else None
-            gskip = torch.empty((), dtype=torch.float32, device=u.device) if skipw is not None else None
-            _cabi.check(L.pde_adi_backward_saved(byref(d), _ptr(tables), _ptr(u), _ptr(gout), _ptr(chan), _ptr(skipw),
-                                                 _ptr(ckpt), _ptr(gin), _ptr(gmaps[0]), _ptr(gmaps[1]), _ptr(gmaps[2]),
-                                                 _ptr(gmaps[3]), _ptr(gchan), _ptr(gskip), _ptr(ws), ws_bytes,
-                                                 _stream()), "pde_adi_backward_saved")
-        gmaps = [g.reshape(s) for g, s in zip(gmaps, ctx.param_shapes)]
+            # one allocation for every gradient output: four maps, the channel matrix, the skip weight
+            C, N = cfg.C, cfg.N
+            plane = C * N * N
+            flat = torch.empty(plan.grad_numel + C * C + 1, dtype=torch.float32, device=dev)
+            base = flat.data_ptr()
+            gp = [base + 4 * k * plane for k in range(4)]
+            gchan_p = base + 4 * plan.grad_numel if chan is not None else None
+            gskip_p = base + 4 * (plan.grad_numel + C * C) if skipw is not None else None
+            _cabi.check(L.pde_adi_backward_saved(plan.dref, tables.data_ptr(), _ptr(u), _ptr(gout), _ptr(chan), _ptr(skipw),
+                                                 _ptr(ckpt), _ptr(gin), gp[0], gp[1], gp[2], gp[3], gchan_p, gskip_p,
+                                                 ws.data_ptr(), ws_bytes, _stream()), "pde_adi_backward_saved")
+        gmaps = [flat[k * plane:(k + 1) * plane].view(s) for k, s in enumerate(ctx.param_shapes)]
+        gchan = flat[plan.grad_numel:plan.grad_numel + C * C].view(C, C) if chan is not None else None
+        gskip = flat[plan.grad_numel + C * C].view(()) if skipw is not None else None
         return (gin, gmaps[0], gmaps[1], gmaps[2], gmaps[3], gchan, gskip, None, None)
 
 
@@ -153,7 +246,8 @@ class EmoConfig:
     def desc(self, B: int) -> "_cabi.EmoDesc":
         import numpy as np
         f = lambda v: float(np.float32(v))
-        return _cabi.EmoDesc(B, self.N, self.Nt, f(0.5 * self.dt), f(self.dt), f(self.dx ** 2), f(self.dy ** 2))
+        tuning = _cabi.EMO_TUNE_GENERIC if os.environ.get("PDE_B200_EMO_TILED") == "0" else 0
+        return _cabi.EmoDesc(B, self.N, self.Nt, f(0.5 * self.dt), f(self.dt), f(self.dx ** 2), f(self.dy ** 2), tuning)
 
 
 class _EmotionFunction(torch.autograd.Function):
@@ -169,17 +263,18 @@ class _EmotionFunction(torch.autograd.Function):
             out = torch.empty_like(u0)
             _cabi.check(L.pde_emotion_forward(byref(d), _ptr(u0), _ptr(w6c), _ptr(xs), _ptr(ys), _ptr(out), _stream()),
                         "pde_emotion_forward")
-        ctx.cfg = cfg
+        ctx.desc = d   # the backward pass uses the same descriptor (tuning included)
         ctx.save_for_backward(u0, w6c, xs, ys)
         return out
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
     def backward(ctx, gout):
         L = _cabi.lib()
         u0, w6, xs, ys = ctx.saved_tensors
         gout = gout.contiguous().float()
-        d = ctx.cfg.desc(u0.shape[0])
+        d = ctx.desc
         with torch.cuda.device(u0.device):
             ws_bytes = L.pde_emotion_backward_workspace_bytes(byref(d))
             ws = _bytes(ws_bytes, u0.device)
@@ -224,6 +319,7 @@ class _TinyFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
+    @once_differentiable
     def backward(ctx, gout):
         L = _cabi.lib()
         u, al, sc = ctx.saved_tensors

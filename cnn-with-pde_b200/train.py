@@ -21,9 +21,15 @@ every loop clips the gradient norm at 1.0.  Weak scaling: --batch is the per-GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
         --master-port 29511 train.py --model cifar10 --batch 512 --steps 50
 
-With --graph the step is captured in CUDA graphs (one graph on a single GPU; forward + backward and
-clipping + AdamW around an eager NCCL all-reduce on several): after the PDE kernels a step is a few
-dozen tiny dense kernels and launch bound.
+With --graph the step is captured in CUDA graphs: after the PDE kernels a step is a few dozen tiny
+dense kernels and launch bound.  On several GPUs the NCCL all-reduce is captured INSIDE the graph
+(one launch per step; capture runs in thread-local error mode after a warm-up collective on the
+capture stream, so that ProcessGroupNCCL's watchdog thread cannot invalidate it); --nccl-eager keeps
+it as an eager call between two graphs (forward + backward | clipping + AdamW) instead.
+
+--amp reproduces the CIFAR scripts' mixed-precision recipe (cifar10.py:440,458-467): autocast,
+GradScaler.scale(loss).backward(), unscale_, clip_grad_norm_, scaler.step, scaler.update -- the PDE
+layers themselves stay fp32 (custom_fwd(cast_inputs=float32)).
 """
 from __future__ import annotations
 
@@ -125,7 +131,7 @@ def _dist_env():
 
 
 def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = False, amp: bool = False,
-        seed: int = 1234, pool: int = 4, quiet: bool = False, sync: str = "flat"):
+        seed: int = 1234, pool: int = 4, quiet: bool = False, sync: str = "flat", nccl_in_graph: bool = True):
     """Train `steps` timed steps (after `warmup`) of `model_name` at per-GPU batch `batch` on the
     current rank's GPU; returns a dict with whole-job img/s (max-over-ranks device time)."""
     world, rank, local = _dist_env()
@@ -159,7 +165,10 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
     x_in, y_in = xs[0].clone(), ys[0].clone()
     loss_out = torch.zeros((), device=dev)
 
-    state = {}
+    # cifar10.py:440: GradScaler on CUDA; a disabled scaler is the identity (scale = 1, plain step).
+    # With the flat all-reduce the ranks exchange SCALED gradients; unscale_ runs after the exchange,
+    # so an overflow on one rank is seen by all and the scalers stay in step.
+    scaler = torch.amp.GradScaler("cuda", enabled=amp)
 
     def fwd_bwd():
         if flat is not None:
@@ -168,12 +177,14 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
             opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", enabled=amp):
             loss = criterion(net(x_in), y_in)
-        loss.backward()
+        scaler.scale(loss).backward()
         loss_out.copy_(loss.detach())
 
     def update():
+        scaler.unscale_(opt)
         nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
-        opt.step()
+        scaler.step(opt)      # fused AdamW takes grad_scale / found_inf on the device: no host sync
+        scaler.update()
 
     def step_body():
         fwd_bwd()
@@ -181,9 +192,11 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
             flat.all_reduce()
         update()
 
-    # CUDA graphs: one graph for the whole step on one GPU; with several ranks the all-reduce stays
-    # an eager NCCL call between two graphs (forward + backward | clipping + AdamW), so a step is
-    # three launches and NCCL never runs under capture.
+    # CUDA graphs: one graph for the whole step.  With several ranks the flat all-reduce is captured
+    # inside it (thread-local capture mode: the NCCL watchdog thread polls events concurrently, which
+    # a global-mode capture would treat as a violation; the warm-up steps below run the collective on
+    # the capture stream first so that no communicator is created under capture).  nccl_in_graph=False
+    # keeps the all-reduce eager between two graphs (forward + backward | clipping + AdamW).
     graphs = []
     if graph:
         if use_ddp:
@@ -192,11 +205,11 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
             for _ in range(3):
                 step_body()
             side.synchronize()
-            parts = [step_body] if world == 1 else [fwd_bwd, update]
+            parts = [step_body] if (world == 1 or nccl_in_graph) else [fwd_bwd, update]
             pool_id = None
             for fn in parts:
                 cg = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(cg, stream=side, pool=pool_id):
+                with torch.cuda.graph(cg, stream=side, pool=pool_id, capture_error_mode="thread_local"):
                     fn()
                 pool_id = cg.pool()
                 graphs.append(cg)
@@ -238,7 +251,9 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
         "steps": steps, "warmup": warmup, "ms_per_step": ms / max(steps, 1),
         "img_per_s": batch * world * steps / (ms * 1e-3) if ms > 0 else 0.0,
         "loss": float(loss_out.item()), "cuda_graph": bool(graphs), "autocast": amp,
-        "grad_sync": "none" if world == 1 else ("ddp" if use_ddp else "flat all-reduce"),
+        "grad_sync": "none" if world == 1 else ("ddp" if use_ddp else (
+            "flat all-reduce inside the CUDA graph" if len(graphs) == 1 else "flat all-reduce")),
+        "grad_scaler": bool(amp),
         "params": sum(p.numel() for p in model.parameters()), "data": "synthetic, device resident",
         "scaling": "weak",
     }
@@ -258,11 +273,13 @@ def main(argv=None):
     ap.add_argument("--graph", action="store_true", help="capture the whole step in a CUDA graph")
     ap.add_argument("--amp", action="store_true", help="autocast as in cifar10.py:459 (the PDE layer stays fp32)")
     ap.add_argument("--sync", choices=("flat", "ddp"), default="flat", help="gradient sync for N > 1")
+    ap.add_argument("--nccl-eager", action="store_true", help="keep the all-reduce out of the CUDA graph")
     ap.add_argument("--seed", type=int, default=1234)
     a = ap.parse_args(argv)
     batch = a.batch or _recipes()[a.model].batch
     t0 = time.time()
-    out = run(a.model, batch, a.steps, a.warmup, graph=a.graph, amp=a.amp, seed=a.seed, sync=a.sync)
+    out = run(a.model, batch, a.steps, a.warmup, graph=a.graph, amp=a.amp, seed=a.seed, sync=a.sync,
+              nccl_in_graph=not a.nccl_eager)
     if int(os.environ.get("RANK", "0")) == 0:
         print(f"# {out['img_per_s']:.0f} img/s on {out['n_gpus']} GPU(s), {out['ms_per_step']:.3f} ms/step, "
               f"wall {time.time() - t0:.1f} s", flush=True)

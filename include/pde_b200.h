@@ -16,7 +16,11 @@
  *     synchronises the device;
  *   - return value: 0 on success, a negative PDE_ERR_* for argument errors, a positive
  *     cudaError_t if the CUDA runtime reported one.  No exceptions cross the boundary;
- *   - no global mutable state: re-entrant across host threads and streams;
+ *   - re-entrant across host threads and streams; no setting lives outside the descriptors: which
+ *     kernel variant serves a call is a pure function of the descriptor (its `tuning` field
+ *     included) and of the device, so forward and backward of one descriptor always agree.  The
+ *     only process-level state is a read-mostly cache of per-kernel launch attributes (registers,
+ *     occupancy, "shared-memory limit raised"), filled on first use under a mutex;
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef PDE_B200_H
@@ -29,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PDE_B200_ABI_VERSION 2
+#define PDE_B200_ABI_VERSION 3
 
 #define PDE_OK 0
 #define PDE_ERR_INVALID (-1)      /* NULL pointer, negative size, inconsistent descriptor   */
@@ -60,7 +64,19 @@ typedef struct pde_adi_desc {
     int32_t chan_op;          /* 0 none, 1 pre-step u<-M u (cifar), 2 post-step u<-K u (SVHN) */
     int32_t skip;             /* out = sigmoid(w) u0 + (1-sigmoid(w)) u   (SVHN.py:74)        */
     float cmin, cmax, eps;    /* clamp bounds, stability_eps added to every Thomas pivot      */
+    int32_t tuning;           /* 0 = automatic.  PDE_ADI_TUNE_* bits force a kernel variant
+                                 (tests, A/B timing); results are the same for every value     */
 } pde_adi_desc;
+
+/* pde_adi_desc.tuning: implementation (bits 0-1), sample pairs per half-line group (bits 2-4),
+ * groups per half-line forward block (bits 5-7), sample pairs per whole-line forward warp
+ * (bits 8-9).  Invalid combinations fall back to the automatic choice. */
+#define PDE_ADI_TUNE_IMPL_AUTO 0
+#define PDE_ADI_TUNE_IMPL_HALF_LINE 1   /* adi_split.cu even for small batches                   */
+#define PDE_ADI_TUNE_IMPL_WHOLE_LINE 2  /* adi.cu even where the half-line kernels would serve   */
+#define PDE_ADI_TUNE_P(p) (((p) & 7) << 2)    /* 0 auto, 2 or 4                                  */
+#define PDE_ADI_TUNE_QF(q) (((q) & 7) << 5)   /* 0 auto, 1, 2 or 4                               */
+#define PDE_ADI_TUNE_NP(n) (((n) & 3) << 8)   /* 0 auto, 1 or 2                                  */
 
 /* Per-sweep schedule, built by the host exactly as the reference accumulates it in Python
  * double (current_time += dt/2) and rounded to fp32 the way ATen rounds a Python scalar:
@@ -130,7 +146,10 @@ typedef struct pde_emo_desc {
     float half_dt;            /* fp32(0.5*dt)      (scalar in alpha())                       */
     float dt;                 /* fp32(dt)          (scalar in beta())                        */
     float dx2, dy2;           /* fp32(dx**2), fp32(dy**2)                                    */
+    int32_t tuning;           /* 0 = automatic; PDE_EMO_TUNE_GENERIC forces the shared-memory
+                                 kernels where the register-tiled ones would serve            */
 } pde_emo_desc;
+#define PDE_EMO_TUNE_GENERIC 1
 
 size_t pde_emotion_backward_workspace_bytes(const pde_emo_desc *d);
 /* w6 = {alpha_w1, alpha_w2, alpha_w3, beta_w1, beta_w2, beta_w3}; xs, ys: the registered

@@ -22,7 +22,7 @@ def test_cabi_library_exports_every_declared_symbol():
     lib = P._cabi.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pde_b200_abi_version() == 2
+    assert lib.pde_b200_abi_version() == 3
     assert b"unsupported" in lib.pde_b200_error_string(-2).lower() or b"not supported" in lib.pde_b200_error_string(-2)
 
 
@@ -44,9 +44,9 @@ def test_cabi_host_only_queries():
     bad = P.AdiConfig(N=30, C=1, steps=4, dt=0.3, hx=1.0, hy=1.0).desc(1)     # size not built
     assert lib.pde_adi_tables_bytes(ctypes.byref(bad)) == 0
     # struct layouts must match the header
-    assert ctypes.sizeof(P._cabi.AdiDesc) == 9 * 4 + 3 * 4
+    assert ctypes.sizeof(P._cabi.AdiDesc) == 9 * 4 + 3 * 4 + 4      # ... + tuning
     assert ctypes.sizeof(P._cabi.AdiSchedule) == 3 * 192 * 4
-    assert ctypes.sizeof(P._cabi.EmoDesc) == 3 * 4 + 4 * 4
+    assert ctypes.sizeof(P._cabi.EmoDesc) == 3 * 4 + 4 * 4 + 4     # ... + tuning
     assert ctypes.sizeof(P._cabi.TinyDesc) == 5 * 4 + 4 * 4
 
 

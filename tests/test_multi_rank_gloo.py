@@ -39,8 +39,15 @@ def _worker(rank, world, port, tmpdir):
             p = torch.nn.Parameter(torch.from_numpy(np.asarray(params[n], np.float64)))
             p.grad = torch.from_numpy(np.asarray(r["g_" + n], np.float64).copy())
             plist.append(p)
-        unused = torch.nn.Parameter(torch.zeros(3))      # no .grad: must be skipped, not crash
-        allreduce_coefficient_grads(plist + [unused])
+        unused = torch.nn.Parameter(torch.zeros(3, dtype=torch.float64))   # no .grad on any rank: stays None
+        # a gradient on rank 0 only (an empty shard / a skipped branch on the other rank): the flat
+        # buffers must still line up and both ranks must end with the sum
+        lopsided = torch.nn.Parameter(torch.zeros(4, dtype=torch.float64))
+        if rank == 0:
+            lopsided.grad = torch.arange(4, dtype=torch.float64)
+        allreduce_coefficient_grads([unused] + plist[:2] + [lopsided] + plist[2:])
+        assert unused.grad is None
+        assert lopsided.grad is not None and torch.equal(lopsided.grad, torch.arange(4, dtype=torch.float64))
         if rank == 0:
             np.savez(os.path.join(tmpdir, "reduced.npz"), **{n: p.grad.numpy() for n, p in zip(names, plist)})
     finally:

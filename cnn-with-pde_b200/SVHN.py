@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from ._base import check_input, smooth_coefficients as _smooth
+from ._base import cached_config, check_input, smooth_coefficients as _smooth
 from .functional import AdiConfig, adi_layer
 
 
@@ -27,8 +27,9 @@ class DiffusionLayer(nn.Module):
         self.skip_weight = nn.Parameter(torch.tensor(0.9))
 
     def _config(self) -> AdiConfig:
-        return AdiConfig(N=self.size, C=self.channels, steps=self.num_steps, dt=self.dt, hx=self.dx, hy=self.dx,
-                         smooth=True, chan_op=2, skip=True, cmin=self.stability_eps, eps=self.stability_eps)
+        return cached_config(self, (self.size, self.channels, self.num_steps, self.dt, self.dx, self.stability_eps), lambda: AdiConfig(
+            N=self.size, C=self.channels, steps=self.num_steps, dt=self.dt, hx=self.dx, hy=self.dx, smooth=True,
+            chan_op=2, skip=True, cmin=self.stability_eps, eps=self.stability_eps))
 
     def get_alpha_beta_at_time(self, t):
         alpha_t = torch.clamp(self.alpha_base + self.alpha_time_coeff * t, min=self.stability_eps)

@@ -15,6 +15,16 @@ def check_input(u: torch.Tensor, channels: int, size_h: int, size_w: int, who: s
         raise ValueError(f"{who}: expected {size_h}x{size_w} planes, got {H}x{W}")
 
 
+def cached_config(module, key, build):
+    """The layer's kernel configuration, rebuilt only when one of the plain attributes it is made of
+    (`key`) has changed since the last call (they are ordinary, assignable attributes in the reference)."""
+    hit = module.__dict__.get("_pde_cfg")
+    if hit is None or hit[0] != key:
+        hit = (key, build())
+        module.__dict__["_pde_cfg"] = hit
+    return hit[1]
+
+
 def smooth_coefficients(coeffs: torch.Tensor, dim: int = 1, kernel_size: int = 3) -> torch.Tensor:
     """3-tap moving average with replicate padding along dim 1 of a (lines, N) tensor
     (what mnist_test.py:135-149 computes); kept as a helper, the kernels fuse it."""

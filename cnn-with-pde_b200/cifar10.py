@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from ._base import check_input
+from ._base import cached_config, check_input
 from .functional import AdiConfig, adi_layer
 
 
@@ -29,9 +29,9 @@ class EnhancedDiffusionLayer(nn.Module):
         self.stability_eps = 1e-6
 
     def _config(self) -> AdiConfig:
-        return AdiConfig(N=self.size, C=self.channels, steps=self.num_steps, dt=self.dt, hx=self.dx, hy=self.dy,
-                         lie=self._lie, has_max=True, chan_op=1, cmin=self.stability_eps, cmax=10.0,
-                         eps=self.stability_eps)
+        return cached_config(self, (self.size, self.channels, self.num_steps, self.dt, self.dx, self.dy, self.stability_eps), lambda: AdiConfig(
+            N=self.size, C=self.channels, steps=self.num_steps, dt=self.dt, hx=self.dx, hy=self.dy, lie=self._lie,
+            has_max=True, chan_op=1, cmin=self.stability_eps, cmax=10.0, eps=self.stability_eps))
 
     def get_alpha_beta_at_time(self, t):
         alpha_t = torch.clamp(self.alpha_base + self.alpha_time_coeff * t, min=self.stability_eps, max=10.0)

@@ -72,104 +72,83 @@ __global__ void __launch_bounds__(128) prepare_kernel(pde_adi_desc d, pde_adi_sc
     float rmax = 0.0f;
     int any_clamped = 0;
     if (live) {
-        float kap[N], r[N], den[N];
-        unsigned inside = 0u;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const size_t q = axis == 0 ? ((size_t)c * N + line) * N + i : ((size_t)c * N + i) * N + line;
-            const float raw = __fadd_rn(__ldg(base + q), __fmul_rn(__ldg(tc + q), tt));
+        // the line walks the map with stride 1 (x sweeps: a row of alpha) or N (y sweeps: a column of beta)
+        const size_t q0 = axis == 0 ? ((size_t)c * N + line) * N : (size_t)c * N * N + line;
+        const int qs = axis == 0 ? 1 : N;
+        // clamped coefficient of cell i (replicate padding beyond the ends) and "inside the clamp interval"
+        auto coef = [&](int i, bool *inside) {
+            i = i < 0 ? 0 : (i > N - 1 ? N - 1 : i);
+            const float raw = __fadd_rn(__ldg(base + q0 + (size_t)i * qs), __fmul_rn(__ldg(tc + q0 + (size_t)i * qs), tt));
             bool m = raw >= d.cmin;
             float k = raw < d.cmin ? d.cmin : raw;
             if (d.has_max) {
                 m = m && raw <= d.cmax;
                 k = k > d.cmax ? d.cmax : k;
             }
-            kap[i] = k;
-            if (m) inside |= 1u << i;
-        }
-        any_clamped = inside != (N == 32 ? 0xffffffffu : ((1u << (N & 31)) - 1u));
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            float ks = kap[i];
-            if (d.smooth) {
-                const float a0 = __fmul_rn(kap[i > 0 ? i - 1 : 0], third);
-                const float a1 = __fmul_rn(kap[i], third);
-                const float a2 = __fmul_rn(kap[i < N - 1 ? i + 1 : N - 1], third);
-                ks = __fadd_rn(__fadd_rn(a0, a1), a2);
-            }
-            r[i] = __fdiv_rn(__fmul_rn(ks, dts), h2);
-            rmax = fmaxf(rmax, fabsf(r[i]));
-        }
-        auto diag = [&](int i) {
-            return (i == 0 || i == N - 1) ? __fadd_rn(1.0f, r[i]) : __fadd_rn(1.0f, __fmul_rn(2.0f, r[i]));
+            *inside = m;
+            return k;
         };
-        // one-sided elimination, top-down (mnist_test.py:165-185): c*_i = -r_i / den_i
-        float cst = 0.0f;
-#pragma unroll
+        // r_i from the (smoothed) coefficient: (k dt) / h^2, op for op mnist_test.py:83,135-149
+        auto rate = [&](float km, float k0, float kp) {
+            float ks = k0;
+            if (d.smooth) ks = __fadd_rn(__fadd_rn(__fmul_rn(km, third), __fmul_rn(k0, third)), __fmul_rn(kp, third));
+            return __fdiv_rn(__fmul_rn(ks, dts), h2);
+        };
+        auto diag = [&](int i, float r) {
+            return (i == 0 || i == N - 1) ? __fadd_rn(1.0f, r) : __fadd_rn(1.0f, __fmul_rn(2.0f, r));
+        };
+        float *tr = f, *tinv = f + T, *te = f + 2 * T, *tm = f + 3 * T;
+        const size_t TS = split::stab_floats_per_table(d);
+        float *sr = f + 4 * T, *sinv = sr + TS, *se = sr + 2 * TS, *smk = sr + 3 * TS;
+        const int R = split::mirror(line, N);
+        const size_t so = (((size_t)s * C + c) * HQ * N + R) * 8;   // + (k / 4) * N * 8 + half * 4 + k % 4
+
+        // ---- top-down elimination (mnist_test.py:165-185): c*_i = -r_i / den_i.  Serves the whole-line
+        // tables and the near half of the twisted ones (cells 0 .. H-1: the same values).
+        bool in_m, in_0, in_p;
+        float km = coef(-1, &in_m), k0 = coef(0, &in_0), kp;
+        float cst = 0.0f, cst_h = 0.0f;
+#pragma unroll 4
         for (int i = 0; i < N; ++i) {
-            den[i] = i == 0 ? __fadd_rn(diag(i), d.eps) : __fadd_rn(__fsub_rn(diag(i), __fmul_rn(-r[i], cst)), d.eps);
-            cst = __fdiv_rn(-r[i], den[i]);
-        }
-        {
-            float *tr = f, *tinv = f + T, *te = f + 2 * T, *tm = f + 3 * T;
-#pragma unroll
-            for (int q = 0; q < N / 4; ++q) {
-                const size_t o = (((size_t)s * C + c) * (N / 4) + q) * N * 4 + (size_t)line * 4;
-                float4 vr, vi, ve, vm;
-                float *pr = &vr.x, *pi = &vi.x, *pe = &ve.x, *pm = &vm.x;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = 4 * q + k;
-                    pr[k] = r[i];
-                    pi[k] = __fdiv_rn(1.0f, den[i]);
-                    pe[k] = __fdiv_rn(r[i], den[i]);
-                    pm[k] = (inside >> i) & 1u ? 1.0f : 0.0f;
-                }
-                *reinterpret_cast<float4 *>(tr + o) = vr;
-                *reinterpret_cast<float4 *>(tinv + o) = vi;
-                *reinterpret_cast<float4 *>(te + o) = ve;
-                *reinterpret_cast<float4 *>(tm + o) = vm;
+            kp = coef(i + 1, &in_p);
+            const float r = rate(km, k0, kp);
+            rmax = fmaxf(rmax, fabsf(r));
+            any_clamped |= in_0 ? 0 : 1;
+            const float den = i == 0 ? __fadd_rn(diag(i, r), d.eps) : __fadd_rn(__fsub_rn(diag(i, r), __fmul_rn(-r, cst)), d.eps);
+            cst = __fdiv_rn(-r, den);
+            if (i == H - 1) cst_h = cst;
+            const float inv = __fdiv_rn(1.0f, den), e = __fdiv_rn(r, den), mk = in_0 ? 1.0f : 0.0f;
+            const size_t o = (((size_t)s * C + c) * (N / 4) + (i >> 2)) * N * 4 + (size_t)line * 4 + (i & 3);
+            tr[o] = r; tinv[o] = inv; te[o] = e; tm[o] = mk;
+            if (want_split && i < H) {
+                const size_t o2 = so + (size_t)(i >> 2) * N * 8 + (i & 3);
+                sr[o2] = r; sinv[o2] = inv; se[o2] = e; smk[o2] = mk;
             }
+            km = k0; k0 = kp; in_0 = in_p;
         }
         if (want_split) {
-            // twisted pivots: cells 0 .. H-1 keep the top-down values, cells N-1 .. H+1 are eliminated
-            // bottom-up, cell H closes both
+            // ---- twisted pivots: cells N-1 .. H+1 are eliminated bottom-up, cell H closes both
+            float kq = coef(N, &in_m);           // the window now slides downwards: kq = cell i + 1
+            k0 = coef(N - 1, &in_0);
             float ast = 0.0f;
-#pragma unroll
-            for (int i = N - 1; i > H; --i) {
-                den[i] = i == N - 1 ? __fadd_rn(diag(i), d.eps) : __fadd_rn(__fsub_rn(diag(i), __fmul_rn(-r[i], ast)), d.eps);
-                ast = __fdiv_rn(-r[i], den[i]);
+#pragma unroll 4
+            for (int i = N - 1; i >= H; --i) {
+                km = coef(i - 1, &in_m);
+                const float r = rate(km, k0, kq);
+                float den;
+                if (i == N - 1) den = __fadd_rn(diag(i, r), d.eps);
+                else if (i > H) den = __fadd_rn(__fsub_rn(diag(i, r), __fmul_rn(-r, ast)), d.eps);
+                else den = __fadd_rn(__fsub_rn(__fsub_rn(diag(i, r), __fmul_rn(-r, cst_h)), __fmul_rn(-r, ast)), d.eps);
+                ast = __fdiv_rn(-r, den);
+                const int k = N - 1 - i;
+                const size_t o2 = so + (size_t)(k >> 2) * N * 8 + 4 + (k & 3);
+                sr[o2] = r; sinv[o2] = __fdiv_rn(1.0f, den); se[o2] = __fdiv_rn(r, den); smk[o2] = in_0 ? 1.0f : 0.0f;
+                kq = k0; k0 = km; in_0 = in_m;
             }
-            const float cst_h = __fdiv_rn(-r[H - 1], den[H - 1]);
-            den[H] = __fadd_rn(__fsub_rn(__fsub_rn(diag(H), __fmul_rn(-r[H], cst_h)), __fmul_rn(-r[H], ast)), d.eps);
-            const size_t TS = split::stab_floats_per_table(d);
-            float *stab = f + 4 * T;
-            float *tr = stab, *tinv = stab + TS, *te = stab + 2 * TS, *tm = stab + 3 * TS;
-            const int R = split::mirror(line, N);
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int q = 0; q < HQ; ++q) {
-                    const size_t o = ((((size_t)s * C + c) * HQ + q) * N + R) * 8 + h * 4;
-                    float4 vr, vi, ve, vm;
-                    float *pr = &vr.x, *pi = &vi.x, *pe = &ve.x, *pm = &vm.x;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const int k = 4 * q + kk;
-                        if (k < H) {
-                            const int i = h ? N - 1 - k : k;
-                            pr[kk] = r[i];
-                            pi[kk] = __fdiv_rn(1.0f, den[i]);
-                            pe[kk] = __fdiv_rn(r[i], den[i]);
-                            pm[kk] = (inside >> i) & 1u ? 1.0f : 0.0f;
-                        } else {
-                            pr[kk] = 0.0f; pi[kk] = 0.0f; pe[kk] = 0.0f; pm[kk] = 0.0f;
-                        }
-                    }
-                    *reinterpret_cast<float4 *>(tr + o) = vr;
-                    *reinterpret_cast<float4 *>(tinv + o) = vi;
-                    *reinterpret_cast<float4 *>(te + o) = ve;
-                    *reinterpret_cast<float4 *>(tm + o) = vm;
+            for (int k = H; k < 4 * HQ; ++k)     // padding of the last float4 of both halves
+                for (int h = 0; h < 2; ++h) {
+                    const size_t o2 = so + (size_t)(k >> 2) * N * 8 + h * 4 + (k & 3);
+                    sr[o2] = 0.0f; sinv[o2] = 0.0f; se[o2] = 0.0f; smk[o2] = 0.0f;
                 }
         }
     }

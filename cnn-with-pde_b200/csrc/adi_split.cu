@@ -1084,17 +1084,15 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
 // host side
 // ------------------------------------------------------------------------------------------
 bool supported(const pde_adi_desc &d) {
-    const int impl = tune_impl(d);
-    if (impl == PDE_ADI_TUNE_IMPL_WHOLE_LINE) return false;
+    if (tune_impl(d) == PDE_ADI_TUNE_IMPL_WHOLE_LINE) return false;
     if (d.steps < 1 || d.B < 1 || d.C > 3) return false;
     if (d.N != 28 && d.N != 32) return false;
-    // Below two groups of two sample pairs per SM the call is latency bound either way: stay with
-    // the whole-line kernels (one pair per warp spreads a small batch over more SMs).  The tuning
-    // field forces the half-line kernels (tests).
-    if (impl == PDE_ADI_TUNE_IMPL_HALF_LINE || tune_p(d) != 0) return true;
+    // Training calls on 28 x 28 / 32 x 32 planes take the half-line kernels at every batch size: at the
+    // reference's own batches (64 ... 512) a call is latency bound, and half the dependent chain per
+    // thread plus TMA-staged coefficients is what shortens it (measured, kernels only: fashion B 256
+    // 64 -> 43 us, mnist B 64 111 -> 68 us, cifar10 pde2 B 512 196 -> 170 us, svhn B 256 212 -> 162 us).
     DeviceProps props;
-    if (query_props(&props) != PDE_OK) return false;
-    return (d.B + 3) / 4 >= 2 * props.sm_count;
+    return query_props(&props) == PDE_OK;
 }
 
 size_t table_floats(const pde_adi_desc &d) { return 4 * stab_floats_per_table(d); }

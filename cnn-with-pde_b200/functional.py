@@ -21,7 +21,6 @@ from ctypes import byref
 from dataclasses import dataclass
 
 import torch
-from torch.autograd.function import once_differentiable
 
 from . import _cabi
 from .schedule import adi_schedule
@@ -40,8 +39,28 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None):
+    """cudaStream_t of torch's current stream (the raw query: torch.cuda.current_stream() builds a
+    Python Stream object, ~10 us, every call)."""
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
+def _no_double_backward(what: str):
+    # the backward passes call raw-pointer kernels: autograd cannot differentiate them again, and
+    # returning their results under create_graph=True would silently treat them as constants
+    if torch.is_grad_enabled():
+        raise RuntimeError(f"{what}: the B200 PDE layers are once differentiable (no create_graph=True / double backward)")
+
+
+def _autocast_to_fp32(t):
+    """What custom_fwd(cast_inputs=torch.float32) does for the input, at a fraction of its host cost:
+    under CUDA autocast a half-precision input is cast up (tracked by autograd, so its gradient comes
+    back in its own dtype); the layers themselves always compute in fp32 and call no op that autocast
+    would touch."""
+    if t.dtype != torch.float32 and t.is_floating_point() and torch.is_autocast_enabled("cuda"):
+        return t.float()
+    return t
 
 
 def _guard(device):
@@ -71,11 +90,18 @@ def env_tuning() -> int:
         PDE_B200_SPLIT_QF=1|2|4 groups per half-line forward block
         PDE_B200_FWD_NP=1|2     sample pairs per whole-line forward warp
     """
+    raw = getattr(os.environ, "_data", None)   # bytes-keyed dict behind os.environ: membership costs ~50 ns
+    if raw is not None and not (_TUNING_KEYS_B & raw.keys()):
+        return 0
     env = os.environ
     impl = _cabi.TUNE_IMPL_WHOLE_LINE if env.get("PDE_B200_ADI_LEGACY") else (
         _cabi.TUNE_IMPL_HALF_LINE if env.get("PDE_B200_ADI_SPLIT") else 0)
     num = lambda k: int(env.get(k) or 0)   # noqa: E731
     return _cabi.adi_tuning(impl, num("PDE_B200_SPLIT_P"), num("PDE_B200_SPLIT_QF"), num("PDE_B200_FWD_NP"))
+
+
+_TUNING_KEYS = ("PDE_B200_ADI_LEGACY", "PDE_B200_ADI_SPLIT", "PDE_B200_SPLIT_P", "PDE_B200_SPLIT_QF", "PDE_B200_FWD_NP")
+_TUNING_KEYS_B = frozenset(k.encode() for k in _TUNING_KEYS)
 
 
 # ------------------------------------------------------------------------------ implicit ADI
@@ -95,6 +121,13 @@ class AdiConfig:
     cmin: float = 1e-6
     cmax: float = 10.0
     eps: float = 1e-6
+
+    def __post_init__(self):
+        object.__setattr__(self, "_hash", hash((self.N, self.C, self.steps, self.dt, self.hx, self.hy, self.lie, self.smooth,
+                                                self.has_max, self.chan_op, self.skip, self.cmin, self.cmax, self.eps)))
+
+    def __hash__(self):   # computed once: the configuration keys the plan cache on every call
+        return self._hash
 
     def desc(self, B: int, tuning: int = 0) -> "_cabi.AdiDesc":
         return _cabi.AdiDesc(B, self.C, self.N, self.steps, int(self.lie), int(self.smooth), int(self.has_max),
@@ -148,7 +181,6 @@ def _remember_tables(key, tables):
 
 class _AdiFunction(torch.autograd.Function):
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg: AdiConfig, grad_mode: bool = True):
         _require_cuda(u, "PDE layer input")
         L = _cabi.lib()
@@ -164,7 +196,7 @@ class _AdiFunction(torch.autograd.Function):
         # caller passes the mode it saw
         training = grad_mode and any(ctx.needs_input_grad)
         with _guard(dev):
-            st = _stream()
+            st = _stream(dev)
             tables, key = None, None
             if not training and not torch.cuda.is_current_stream_capturing():
                 key = (plan, tuple((p.data_ptr(), p._version) for p in (alpha_base, beta_base, alpha_tc, beta_tc)))
@@ -193,9 +225,8 @@ class _AdiFunction(torch.autograd.Function):
         return out
 
     @staticmethod
-    @torch.amp.custom_bwd(device_type="cuda")
-    @once_differentiable
     def backward(ctx, gout):
+        _no_double_backward("PDE layer")
         L = _cabi.lib()
         plan = ctx.plan
         cfg = plan.cfg
@@ -223,7 +254,7 @@ class _AdiFunction(torch.autograd.Function):
             gskip_p = base + 4 * (plan.grad_numel + C * C) if skipw is not None else None
             _cabi.check(L.pde_adi_backward_saved(plan.dref, tables.data_ptr(), _ptr(u), _ptr(gout), _ptr(chan), _ptr(skipw),
                                                  _ptr(ckpt), _ptr(gin), gp[0], gp[1], gp[2], gp[3], gchan_p, gskip_p,
-                                                 ws.data_ptr(), ws_bytes, _stream()), "pde_adi_backward_saved")
+                                                 ws.data_ptr(), ws_bytes, _stream(dev)), "pde_adi_backward_saved")
         gmaps = [flat[k * plane:(k + 1) * plane].view(s) for k, s in enumerate(ctx.param_shapes)]
         gchan = flat[plan.grad_numel:plan.grad_numel + C * C].view(C, C) if chan is not None else None
         gskip = flat[plan.grad_numel + C * C].view(()) if skipw is not None else None
@@ -231,6 +262,7 @@ class _AdiFunction(torch.autograd.Function):
 
 
 def adi_layer(u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg: AdiConfig):
+    u = _autocast_to_fp32(u)
     return _AdiFunction.apply(u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg, torch.is_grad_enabled())
 
 
@@ -246,47 +278,56 @@ class EmoConfig:
     def desc(self, B: int) -> "_cabi.EmoDesc":
         import numpy as np
         f = lambda v: float(np.float32(v))
-        tuning = _cabi.EMO_TUNE_GENERIC if os.environ.get("PDE_B200_EMO_TILED") == "0" else 0
-        return _cabi.EmoDesc(B, self.N, self.Nt, f(0.5 * self.dt), f(self.dt), f(self.dx ** 2), f(self.dy ** 2), tuning)
+        return _cabi.EmoDesc(B, self.N, self.Nt, f(0.5 * self.dt), f(self.dt), f(self.dx ** 2), f(self.dy ** 2), 0)
+
+
+@functools.lru_cache(maxsize=256)
+def _emo_plan(cfg: EmoConfig, B: int, generic: bool, device_index: int):
+    """(descriptor, its byref, backward workspace bytes) of a call: depends on nothing else."""
+    d = cfg.desc(B)
+    d.tuning = _cabi.EMO_TUNE_GENERIC if generic else 0
+    return d, byref(d), _cabi.lib().pde_emotion_backward_workspace_bytes(byref(d))
 
 
 class _EmotionFunction(torch.autograd.Function):
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, u0, w6, xs, ys, cfg: EmoConfig):
         _require_cuda(u0, "PDELayer input")
         L = _cabi.lib()
-        u0 = u0.contiguous()
-        w6c, xs, ys = w6.detach().contiguous(), xs.contiguous(), ys.contiguous()
-        d = cfg.desc(u0.shape[0])
-        with torch.cuda.device(u0.device):
+        u0 = _contig(u0)
+        w6c, xs, ys = _contig(w6.detach()), _contig(xs), _contig(ys)
+        dev = u0.device
+        plan = _emo_plan(cfg, u0.shape[0], os.environ.get("PDE_B200_EMO_TILED") == "0",
+                         dev.index if dev.index is not None else torch.cuda.current_device())
+        d = plan[0]
+        with _guard(u0.device):
             out = torch.empty_like(u0)
-            _cabi.check(L.pde_emotion_forward(byref(d), _ptr(u0), _ptr(w6c), _ptr(xs), _ptr(ys), _ptr(out), _stream()),
+            _cabi.check(L.pde_emotion_forward(plan[1], _ptr(u0), _ptr(w6c), _ptr(xs), _ptr(ys), _ptr(out), _stream(u0.device)),
                         "pde_emotion_forward")
-        ctx.desc = d   # the backward pass uses the same descriptor (tuning included)
+        ctx.plan = plan   # the backward pass uses the same descriptor (tuning included)
         ctx.save_for_backward(u0, w6c, xs, ys)
         return out
 
     @staticmethod
-    @torch.amp.custom_bwd(device_type="cuda")
-    @once_differentiable
     def backward(ctx, gout):
+        _no_double_backward("PDELayer")
         L = _cabi.lib()
         u0, w6, xs, ys = ctx.saved_tensors
-        gout = gout.contiguous().float()
-        d = ctx.desc
-        with torch.cuda.device(u0.device):
-            ws_bytes = L.pde_emotion_backward_workspace_bytes(byref(d))
+        gout = _contig(gout)
+        if gout.dtype != torch.float32:
+            gout = gout.float()
+        d, dref, ws_bytes = ctx.plan
+        with _guard(u0.device):
             ws = _bytes(ws_bytes, u0.device)
             gin = torch.empty_like(u0) if ctx.needs_input_grad[0] else None
             gw = torch.empty(6, dtype=torch.float32, device=u0.device)
-            _cabi.check(L.pde_emotion_backward(byref(d), _ptr(u0), _ptr(gout), _ptr(w6), _ptr(xs), _ptr(ys), _ptr(gin),
-                                               _ptr(gw), _ptr(ws), ws_bytes, _stream()), "pde_emotion_backward")
+            _cabi.check(L.pde_emotion_backward(dref, _ptr(u0), _ptr(gout), _ptr(w6), _ptr(xs), _ptr(ys), _ptr(gin),
+                                               _ptr(gw), _ptr(ws), ws_bytes, _stream(u0.device)), "pde_emotion_backward")
         return gin, gw, None, None, None
 
 
 def emotion_layer(u0, w6, xs, ys, cfg: EmoConfig):
-    return _EmotionFunction.apply(u0, w6, xs, ys, cfg)
+    return _EmotionFunction.apply(_autocast_to_fp32(u0), _autocast_to_fp32(w6), xs, ys, cfg)
 
 
 # ----------------------------------------------------------------------- explicit, zero ghosts
@@ -299,44 +340,49 @@ class TinyConfig:
     blend: float = 0.1
 
 
+@functools.lru_cache(maxsize=256)
+def _tiny_plan(cfg: TinyConfig, shape, device_index: int):
+    B, C, H, W = shape
+    d = _cabi.TinyDesc(B, C, H, W, cfg.steps, cfg.dt, cfg.cmin, cfg.cmax, cfg.blend)
+    return d, byref(d), _cabi.lib().pde_tiny_backward_workspace_bytes(byref(d))
+
+
 class _TinyFunction(torch.autograd.Function):
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, u, alpha_base, channel_scaling, cfg: TinyConfig):
         _require_cuda(u, "ImprovedDiffusionLayer input")
         L = _cabi.lib()
-        u = u.contiguous()
-        B, C, H, W = u.shape
-        al, sc = alpha_base.detach().contiguous(), channel_scaling.detach().contiguous()
-        d = _cabi.TinyDesc(B, C, H, W, cfg.steps, cfg.dt, cfg.cmin, cfg.cmax, cfg.blend)
-        with torch.cuda.device(u.device):
+        u = _contig(u)
+        al, sc = _contig(alpha_base.detach()), _contig(channel_scaling.detach())
+        dev = u.device
+        plan = _tiny_plan(cfg, tuple(u.shape), dev.index if dev.index is not None else torch.cuda.current_device())
+        with _guard(u.device):
             out = torch.empty_like(u)
-            _cabi.check(L.pde_tiny_forward(byref(d), _ptr(u), _ptr(al), _ptr(sc), _ptr(out), _stream()),
+            _cabi.check(L.pde_tiny_forward(plan[1], _ptr(u), _ptr(al), _ptr(sc), _ptr(out), _stream(u.device)),
                         "pde_tiny_forward")
-        ctx.cfg = cfg
+        ctx.plan = plan
         ctx.save_for_backward(u, al, sc)
         return out
 
     @staticmethod
-    @torch.amp.custom_bwd(device_type="cuda")
-    @once_differentiable
     def backward(ctx, gout):
+        _no_double_backward("ImprovedDiffusionLayer")
         L = _cabi.lib()
         u, al, sc = ctx.saved_tensors
-        cfg = ctx.cfg
-        gout = gout.contiguous().float()
-        B, C, H, W = u.shape
-        d = _cabi.TinyDesc(B, C, H, W, cfg.steps, cfg.dt, cfg.cmin, cfg.cmax, cfg.blend)
-        with torch.cuda.device(u.device):
-            ws_bytes = L.pde_tiny_backward_workspace_bytes(byref(d))
+        gout = _contig(gout)
+        if gout.dtype != torch.float32:
+            gout = gout.float()
+        C = u.shape[1]
+        d, dref, ws_bytes = ctx.plan
+        with _guard(u.device):
             ws = _bytes(ws_bytes, u.device)
             gin = torch.empty_like(u) if ctx.needs_input_grad[0] else None
             ga = torch.empty(C, dtype=torch.float32, device=u.device)
             gs = torch.empty(C, dtype=torch.float32, device=u.device)
-            _cabi.check(L.pde_tiny_backward(byref(d), _ptr(u), _ptr(gout), _ptr(al), _ptr(sc), _ptr(gin), _ptr(ga),
-                                            _ptr(gs), _ptr(ws), ws_bytes, _stream()), "pde_tiny_backward")
+            _cabi.check(L.pde_tiny_backward(dref, _ptr(u), _ptr(gout), _ptr(al), _ptr(sc), _ptr(gin), _ptr(ga),
+                                            _ptr(gs), _ptr(ws), ws_bytes, _stream(u.device)), "pde_tiny_backward")
         return gin, ga, gs, None
 
 
 def tiny_layer(u, alpha_base, channel_scaling, cfg: TinyConfig):
-    return _TinyFunction.apply(u, alpha_base, channel_scaling, cfg)
+    return _TinyFunction.apply(_autocast_to_fp32(u), alpha_base, channel_scaling, cfg)

@@ -42,6 +42,19 @@ def test_cuda_matches_oracle_at_config_shape(c):
     assert not bad, f"{c.name}: further from fp64 than the fp32 oracle + 1e-5: {bad}"
 
 
+@pytest.mark.parametrize("c", [c for c in K.CONFIG_CASES if c.kind in ("mnist", "fashion", "svhn", "cifar10", "cifar2")],
+                         ids=lambda c: c.name)
+def test_cuda_whole_line_kernels_at_config_shape(monkeypatch, c):
+    """Training calls on 28 x 28 / 32 x 32 planes default to the half-line kernels (adi_split.cu) at every
+    batch size; the whole-line kernels of adi.cu (other plane sizes, four channels, inference) must stay
+    right on the same shapes."""
+    monkeypatch.setenv("PDE_B200_ADI_LEGACY", "1")
+    params, io = K.make_params(c), K.make_io(c)
+    got = runners.run_cuda(c, params=params, io=io)
+    o32 = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+    _assert_close(got, o32, TOL, c.name + " (whole-line kernels) vs oracle fp32")
+
+
 @pytest.mark.parametrize("c", [K.CONFIG_CASES[1], K.CONFIG_CASES[3], K.CONFIG_CASES[7], K.CONFIG_CASES[9]],
                          ids=lambda c: c.name)
 def test_cuda_without_grad_input(c):
@@ -158,7 +171,6 @@ def test_cuda_backward_without_saved_checkpoints(monkeypatch, env):
     """pde_adi_backward without checkpoints from the forward call (it makes them in its workspace),
     and the whole-line kernels of adi.cu on the sizes the half-line kernels normally serve."""
     monkeypatch.setenv(env, "1")
-    monkeypatch.setenv("PDE_B200_ADI_SPLIT", "1")   # small batches default to the whole-line kernels
     for c in _SPLIT_CASES + [K.case("split_fashion_dt5", "fashion", B=8, perturb=False, dt=5.0)]:
         params, io = K.make_params(c), K.make_io(c)
         want = runners.run_oracle(c, params=params, io=io, dtype=np.float32)

@@ -47,8 +47,7 @@ struct Geo {
 //                               and cell H closes both; written only when the call can be served
 //                               by those kernels.
 // The block reduces the sweep's largest r and "some cell clamped" and writes its header entries;
-// nothing crosses blocks: flags_kernel (one warp, next in the stream) folds them into the call-wide
-// flags the backward kernels read.
+// nothing crosses blocks (the consumers fold them into the call-wide flags: header_flags).
 // ------------------------------------------------------------------------------------------
 template <int N>
 __global__ void __launch_bounds__(128) prepare_kernel(pde_adi_desc d, pde_adi_schedule sch, SlotMap sm,
@@ -681,7 +680,8 @@ __global__ void __launch_bounds__(192, 1) bwd_kernel(const Args a) {
     }
 
     const Tables T = split_tables(a.tables, d);
-    const bool exact = T.hdr->mode_exact != 0;
+    bool exact, any_clamped_unused;
+    header_flags(T.hdr, d.steps, a.sps, &exact, &any_clamped_unused);
     // per-sweep scalars (dt/h^2, t, "some cell clamped") are read by every warp every sweep
     __shared__ float h_scale[PDE_MAX_SWEEPS], h_t[PDE_MAX_SWEEPS];
     __shared__ int h_clamped[PDE_MAX_SWEEPS];
@@ -1198,16 +1198,6 @@ static void make_slot_map(const pde_adi_desc &d, const pde_adi_schedule &sch, Sl
     m->nslots = nslots;
 }
 
-__global__ void flags_kernel(char *tables, int steps, int sps) {
-    Header *hdr = reinterpret_cast<Header *>(tables);
-    bool exact, any_clamped;
-    header_flags(hdr, steps, sps, &exact, &any_clamped);
-    if (threadIdx.x == 0) {
-        hdr->mode_exact = exact ? 1 : 0;
-        hdr->any_clamped = any_clamped ? 1 : 0;
-    }
-}
-
 template <int N>
 static int launch_prepare(const pde_adi_desc &d, const pde_adi_schedule &sch, const SlotMap &sm, const float *ab,
                           const float *bb, const float *atc, const float *btc, char *tables, int want_split,
@@ -1215,7 +1205,6 @@ static int launch_prepare(const pde_adi_desc &d, const pde_adi_schedule &sch, co
     const int S = d.steps * sweeps_per_step(d);
     const int threads = ((d.C * N + 31) / 32) * 32;
     prepare_kernel<N><<<S, threads, 0, st>>>(d, sch, sm, ab, bb, atc, btc, tables, want_split);
-    flags_kernel<<<1, 32, 0, st>>>(tables, d.steps, sweeps_per_step(d));
     return cuda_last_error();
 }
 
@@ -1228,10 +1217,7 @@ extern "C" int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sc
     if (reinterpret_cast<uintptr_t>(tables) & 255u) return PDE_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int S = d->steps * sweeps_per_step(*d);
-    if (S == 0) {   // zero steps: identity; the backward kernel still reads the flags
-        flags_kernel<<<1, 32, 0, st>>>(static_cast<char *>(tables), 0, sweeps_per_step(*d));
-        return cuda_last_error();
-    }
+    if (S == 0) return PDE_OK;   // zero steps: identity, no tables
     SlotMap sm;
     make_slot_map(*d, *sched, &sm);
     const int want_split = split::supported(*d) ? 1 : 0;

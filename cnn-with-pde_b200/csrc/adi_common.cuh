@@ -15,11 +15,9 @@ constexpr int kHeaderBytes = 4096;
 constexpr float kAmpLimit = 256.0f;  // see DESIGN.md "reverse reconstruction"
 
 struct Header {
-    // call-wide flags, folded from the per-sweep entries by flags_kernel (header_flags)
-    int mode_exact;    // rebuilding sweep inputs would amplify rounding noise: per-sweep checkpoints
-    int any_clamped;   // 1 if any cell of any sweep sits outside the clamp interval
-    int pad[2];
-    // written per sweep by prepare_kernel (one block per sweep, no cross-block step)
+    // written per sweep by prepare_kernel (one block per sweep, no cross-block step); the call-wide
+    // flags the backward kernels need are folded from them by header_flags: by the half-line forward
+    // kernel into the head of the checkpoint buffer (CkFlags), by the whole-line backward kernel itself
     float scale[PDE_MAX_SWEEPS];
     float t[PDE_MAX_SWEEPS];
     unsigned rmax_bits[PDE_MAX_SWEEPS];
@@ -63,6 +61,13 @@ __host__ __device__ inline Tables split_tables(const void *tables, const pde_adi
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// head of the checkpoint buffer (first 256 bytes), written by sfwd_kernel, read by sbwd_kernel
+struct CkFlags {
+    int mode_exact;    // rebuilding sweep inputs would amplify rounding noise: per-sweep checkpoints
+    int any_clamped;   // 1 if any cell of any sweep sits outside the clamp interval
+};
+constexpr int kCkHeaderFloats = 64;
+
 struct Args {
     pde_adi_desc d;
     int S, sps, G, nitems, need_gin;
@@ -75,6 +80,7 @@ struct Args {
     // read by the backward one) and the number of partial sets per channel
     const float *stab;
     float *ckpt;
+    CkFlags *ck_flags;
 };
 
 // pde_adi_desc.tuning (include/pde_b200.h)

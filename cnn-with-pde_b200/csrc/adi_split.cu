@@ -400,6 +400,17 @@ __device__ __forceinline__ void planes_to_tile_async(const float *__restrict__ g
     }
 }
 
+// One warp folds the per-sweep header entries into the flags the backward kernel reads.  Not inlined:
+// the forward kernels' register allocation has no slack for it (12 - 24 bytes of spills when inlined).
+__device__ __noinline__ void write_ck_flags(const Header *hdr, int steps, int sps, CkFlags *out) {
+    bool ex, anyc;
+    header_flags(hdr, steps, sps, &ex, &anyc);
+    if ((threadIdx.x & 31) == 0) {
+        out->mode_exact = ex ? 1 : 0;
+        out->any_clamped = anyc ? 1 : 0;
+    }
+}
+
 // MIX1: instantiation for layers with a pre-step channel mix (chan_op == 1), which runs inside the
 // first sweep phase of a step; the others keep the plain schedule (and their register allocation).
 template <int N, int P, int Q, bool MIX1>
@@ -426,6 +437,8 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
     {
         const Header *hdr = reinterpret_cast<const Header *>(a.tables);
         for (int i = threadIdx.x; i < S; i += nthr) h_slot[i] = hdr->slot[i];
+        // the call-wide flags of the backward pass travel with the checkpoints
+        if (a.ck_flags && blockIdx.x == 0 && threadIdx.x < 32) write_ck_flags(hdr, d.steps, sps, a.ck_flags);
     }
     if (threadIdx.x == 0) {
         mbar_init(&cbar[0], 1);
@@ -785,7 +798,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
         for (int col = 0; col < 64; col += 16) tmem_st16(tbase + col, z);
         tmem_wait_st();
     }
-    const bool exact = hdr->mode_exact != 0;
+    const bool exact = a.ck_flags->mode_exact != 0;
     const size_t T = stab_floats_per_table(d);
     const float4 *tab_r = reinterpret_cast<const float4 *>(a.stab);
     const float4 *tab_inv = reinterpret_cast<const float4 *>(a.stab + T);
@@ -798,7 +811,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
     const float om = 1.0f - sig;
     const float onepe = 1.0f + d.eps;
     const bool smooth = d.smooth != 0;
-    const bool defer_smooth = smooth && hdr->any_clamped == 0;   // see reverse_finish
+    const bool defer_smooth = smooth && a.ck_flags->any_clamped == 0;   // see reverse_finish
     float gm[PDE_MAX_CHANNELS] = {0.f, 0.f, 0.f, 0.f};
     float gw = 0.0f;
     const int sps = a.sps;
@@ -1148,7 +1161,7 @@ size_t checkpoint_bytes(const pde_adi_desc &d) {
     if (!supported(d) || make_plan(d, &p) != PDE_OK) return 0;
     // one tile image per (group, step, channel)
     const size_t groups = (size_t)((p.ngroups + kMaxQ - 1) / kMaxQ) * kMaxQ;
-    return groups * d.steps * d.C * p.tile_bytes + 256;
+    return groups * d.steps * d.C * p.tile_bytes + 256 + kCkHeaderFloats * sizeof(float);
 }
 
 template <int N>
@@ -1274,7 +1287,11 @@ int forward(const pde_adi_desc &d, const char *tables, const float *u, const flo
     fill_args(d, tables, &a);
     a.nitems = (p.ngroups + p.Qf - 1) / p.Qf;
     a.u = u; a.chan = chan; a.skipw = skipw; a.out = out;
-    a.ckpt = ckpt ? reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ckpt) + 255u) & ~(uintptr_t)255u) : nullptr;
+    if (ckpt) {   // [CkFlags, 256 bytes][tile images]
+        float *base = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ckpt) + 255u) & ~(uintptr_t)255u);
+        a.ck_flags = reinterpret_cast<CkFlags *>(base);
+        a.ckpt = base + kCkHeaderFloats;
+    }
     const int cap = props.sm_count * per_sm;
     const int grid = a.nitems < cap ? a.nitems : cap;
     if (debug_enabled())
@@ -1305,7 +1322,11 @@ int backward(const pde_adi_desc &d, const char *tables, const float *u, const fl
     a.need_gin = gin != nullptr;
     a.tmem_cols = p.tmem_cols;
     a.u = u; a.gout = gout; a.chan = chan; a.skipw = skipw; a.gin = gin;
-    a.ckpt = const_cast<float *>(reinterpret_cast<const float *>((reinterpret_cast<uintptr_t>(ckpt) + 255u) & ~(uintptr_t)255u));
+    {
+        float *base = const_cast<float *>(reinterpret_cast<const float *>((reinterpret_cast<uintptr_t>(ckpt) + 255u) & ~(uintptr_t)255u));
+        a.ck_flags = reinterpret_cast<CkFlags *>(base);
+        a.ckpt = base + kCkHeaderFloats;
+    }
     a.scratch = ws;
     a.part_maps = ws + w.scratch_floats;
     a.part_chan = a.part_maps + w.maps_floats;

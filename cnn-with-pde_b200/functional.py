@@ -244,20 +244,17 @@ class _AdiFunction(torch.autograd.Function):
             ws_bytes = plan.ws_saved_bytes if ckpt is not None else plan.ws_bytes
             ws = _bytes(ws_bytes, dev)
             gin = torch.empty_like(u) if ctx.needs_input_grad[0] else None
-            # one allocation for every gradient output: four maps, the channel matrix, the skip weight
+            # the four coefficient-map gradients share one allocation (one unbind instead of four views)
             C, N = cfg.C, cfg.N
-            plane = C * N * N
-            flat = torch.empty(plan.grad_numel + C * C + 1, dtype=torch.float32, device=dev)
-            base = flat.data_ptr()
-            gp = [base + 4 * k * plane for k in range(4)]
-            gchan_p = base + 4 * plan.grad_numel if chan is not None else None
-            gskip_p = base + 4 * (plan.grad_numel + C * C) if skipw is not None else None
+            gm = torch.empty((4,) + tuple(ctx.param_shapes[0]), dtype=torch.float32, device=dev)
+            base, plane = gm.data_ptr(), 4 * C * N * N
+            gchan = torch.empty((C, C), dtype=torch.float32, device=dev) if chan is not None else None
+            gskip = torch.empty((), dtype=torch.float32, device=dev) if skipw is not None else None
             _cabi.check(L.pde_adi_backward_saved(plan.dref, tables.data_ptr(), _ptr(u), _ptr(gout), _ptr(chan), _ptr(skipw),
-                                                 _ptr(ckpt), _ptr(gin), gp[0], gp[1], gp[2], gp[3], gchan_p, gskip_p,
-                                                 ws.data_ptr(), ws_bytes, _stream(dev)), "pde_adi_backward_saved")
-        gmaps = [flat[k * plane:(k + 1) * plane].view(s) for k, s in enumerate(ctx.param_shapes)]
-        gchan = flat[plan.grad_numel:plan.grad_numel + C * C].view(C, C) if chan is not None else None
-        gskip = flat[plan.grad_numel + C * C].view(()) if skipw is not None else None
+                                                 _ptr(ckpt), _ptr(gin), base, base + plane, base + 2 * plane, base + 3 * plane,
+                                                 _ptr(gchan), _ptr(gskip), ws.data_ptr(), ws_bytes, _stream(dev)),
+                        "pde_adi_backward_saved")
+        gmaps = gm.unbind(0)
         return (gin, gmaps[0], gmaps[1], gmaps[2], gmaps[3], gchan, gskip, None, None)
 
 

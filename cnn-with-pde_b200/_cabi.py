@@ -34,6 +34,7 @@ EXPORTS = (
     "pde_adi_backward_saved",
     "pde_emotion_backward_workspace_bytes", "pde_emotion_forward", "pde_emotion_backward",
     "pde_tiny_backward_workspace_bytes", "pde_tiny_forward", "pde_tiny_backward",
+    "pde_tiny_split",
 )
 
 
@@ -54,6 +55,10 @@ class EmoDesc(Structure):
 class TinyDesc(Structure):
     _fields_ = [(n, c_int32) for n in ("B", "C", "H", "W", "steps")] + \
                [(n, c_float) for n in ("dt", "cmin", "cmax", "blend")]
+
+
+class TinySplitDesc(Structure):
+    _fields_ = [(n, c_int32) for n in ("B", "H", "W", "mode")] + [("cx", c_float * 3), ("cy", c_float * 3), ("eps", c_float)]
 
 
 class PdeB200Error(RuntimeError):
@@ -110,6 +115,8 @@ def lib():
     L.pde_tiny_forward.argtypes = [POINTER(TinyDesc), fp, fp, fp, fp, vp]
     L.pde_tiny_backward.restype = c_int
     L.pde_tiny_backward.argtypes = [POINTER(TinyDesc), fp, fp, fp, fp, fp, fp, fp, vp, c_size_t, vp]
+    L.pde_tiny_split.restype = c_int
+    L.pde_tiny_split.argtypes = [POINTER(TinySplitDesc), fp, fp, vp]
     if L.pde_b200_abi_version() != ABI_VERSION:
         raise PdeB200Error("libpde_b200.so ABI version mismatch; rebuild it")
     _lib = L

@@ -11,10 +11,11 @@
 // The frozen top / bottom ghost rows live in registers.  All Nt steps run on-chip: one HBM read and
 // one HBM write per cell per call.
 //
-// Backward: phase 1 replays the forward steps and writes every state u^k to a per-warp history in
-// global memory laid out [k][row][column][lane] (each access a coalesced 128 bytes; the history of
-// the warps in flight is sized to stay in L2); phase 2 keeps the adjoint plane in registers, streams
-// u^k back row by row a few rows ahead of its use, and accumulates
+// Backward: the forward steps are replayed into a per-warp history in global memory laid out
+// [k][row][column][lane] (each access a coalesced 128 bytes) -- half the trajectory at a time, each
+// half replayed from the layer input right before it is reversed, so that the history of the warps in
+// flight (8 per SM x 46 KB = 54 MB for the reference model) stays in L2; the reverse pass keeps the
+// adjoint plane in registers, streams u^k back row by row a few rows ahead of its use, and accumulates
 //   dA_i += lam * d2_row u^k, weighted on the fly by {1, sin 2 pi y_i, sin 4 pi y_i}  (3 registers),
 //   dB_j += lam * d2_col u^k per owned column                                        (CW registers),
 // in fp32 within a step and in double across steps and planes.  What flows into the frozen ghost ring is summed
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_bwd_tiled(const EmoArgs a
     tile_coefficients(a, sh, N);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, sub = lane & 15;
     const int r0 = half * RH, j0 = sub * CW;
-    const int Nt = a.d.Nt;
+    const int Nt = a.d.Nt, S1 = (Nt + 1) / 2;   // states per history segment
     float b[CW], bm[CW], bp[CW];
 #pragma unroll
     for (int c = 0; c < CW; ++c) {
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_bwd_tiled(const EmoArgs a
     float *gl = sh.ghost[warp][0], *gr = sh.ghost[warp][1];
     float *eslot = &sh.gadj[warp][0][lane];              // this lane's column of slots, stride 32
     const int wg = blockIdx.x * kTileWarps + warp;
-    float *hist = hist_all + (size_t)wg * Nt * RH * HROW + lane;
+    float *hist = hist_all + (size_t)wg * (S1 + 1) * RH * HROW + lane;   // S1 states + the parked adjoint
     double dA0 = 0.0, dA1 = 0.0, dA2 = 0.0, dBd[CW];
 #pragma unroll
     for (int c = 0; c < CW; ++c) dBd[c] = 0.0;
@@ -193,28 +194,8 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_bwd_tiled(const EmoArgs a
     for (int plane = wg; plane < a.d.B; plane += gridDim.x * kTileWarps) {
         const size_t off = (size_t)plane * N * N;
         float gedge[CW];
-        {   // ------------------------------ phase 1: u^0 .. u^{Nt-1} into the history
-            float u[RH][CW];
-            tile_load<N>(a.u0 + off, half, sub, r0, j0, u, gedge, gl, gr);
-#pragma unroll 1
-            for (int k = 0; k < Nt; ++k) {
-                float *hk = hist + (size_t)k * RH * HROW;
-#pragma unroll
-                for (int r = 0; r < RH; ++r)
-#pragma unroll
-                    for (int c = 0; c < CW; ++c) __stcg(hk + (r * CW + c) * 32, u[r][c]);
-                if (k + 1 < Nt) tile_step<N>(u, gedge, b, sh.a + 1 + r0, gl + r0, gr + r0, half, sub);
-            }
-        }
-        // ------------------------------ phase 2: adjoint
-        float lam[RH][CW];
-        {
-            const float *go = a.gout + off;
-#pragma unroll
-            for (int r = 0; r < RH; ++r)
-#pragma unroll
-                for (int c = 0; c < CW; ++c) lam[r][c] = __ldcs(go + (r0 + r) * N + j0 + c);
-        }
+        // ------------------------------ adjoint state
+        float lam[RH][CW];   // = gout once the first segment has been replayed
 #pragma unroll
         for (int r = 0; r < RH; ++r) eslot[r * 32] = 0.0f;
         float eedge[CW];
@@ -222,9 +203,53 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_bwd_tiled(const EmoArgs a
         for (int c = 0; c < CW; ++c) eedge[c] = 0.f;
         __syncwarp();
         constexpr int AHEAD = 4;    // history rows requested ahead of their use
+        // The history holds HALF the trajectory at a time (one checkpoint, the layer input itself):
+        // segment 1 = states S1 .. Nt-1, segment 0 = states 0 .. S1-1, each replayed from u^0 into the same
+        // slots right before it is reversed.  13 forward steps instead of 9 for Nt = 10, but the history of
+        // the warps in flight (54 MB instead of 109) stays in L2 instead of spilling to HBM.
+#pragma unroll 1
+        for (int seg = (Nt > S1 ? 1 : 0); seg >= 0; --seg) {
+        const int kb = seg ? S1 : 0, ke = seg ? Nt : S1;
+        // the adjoint plane waits in a spare history slot while the registers replay the forward steps
+        float *park = hist + (size_t)S1 * RH * HROW;
+        const bool parked = seg == 0 && Nt > S1;
+        if (parked) {
+#pragma unroll
+            for (int r = 0; r < RH; ++r)
+#pragma unroll
+                for (int c = 0; c < CW; ++c) __stcg(park + (r * CW + c) * 32, lam[r][c]);
+        }
+        {   // ------------------------------ replay: u^kb .. u^{ke-1} into the history
+            float u[RH][CW];
+            tile_load<N>(a.u0 + off, half, sub, r0, j0, u, gedge, gl, gr);
+#pragma unroll 1
+            for (int k = 0; k < ke; ++k) {
+                if (k >= kb) {
+                    float *hk = hist + (size_t)(k - kb) * RH * HROW;
+#pragma unroll
+                    for (int r = 0; r < RH; ++r)
+#pragma unroll
+                        for (int c = 0; c < CW; ++c) __stcg(hk + (r * CW + c) * 32, u[r][c]);
+                }
+                if (k + 1 < ke) tile_step<N>(u, gedge, b, sh.a + 1 + r0, gl + r0, gr + r0, half, sub);
+            }
+        }
+        if (parked) {
+#pragma unroll
+            for (int r = 0; r < RH; ++r)
+#pragma unroll
+                for (int c = 0; c < CW; ++c) lam[r][c] = __ldcg(park + (r * CW + c) * 32);
+        } else {
+            const float *go = a.gout + off;
+#pragma unroll
+            for (int r = 0; r < RH; ++r)
+#pragma unroll
+                for (int c = 0; c < CW; ++c) lam[r][c] = __ldcs(go + (r0 + r) * N + j0 + c);
+        }
+        // ------------------------------ reverse over the segment
 #pragma unroll 1   // the body is 24 unrolled rows; more copies only thrash the instruction cache
-        for (int k = Nt - 1; k >= 0; --k) {
-            const float *hk = hist + (size_t)k * RH * HROW;
+        for (int k = ke - 1; k >= kb; --k) {
+            const float *hk = hist + (size_t)(k - kb) * RH * HROW;
             // fp32 partial sums live for one step only (72 terms per lane); across steps and planes
             // the sums are carried in double: the six gradients are sums with heavy cancellation
             float fA0 = 0.f, fA1 = 0.f, fA2 = 0.f, fB[CW];
@@ -319,6 +344,7 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_bwd_tiled(const EmoArgs a
 #pragma unroll
             for (int c = 0; c < CW; ++c) dBd[c] += (double)fB[c];
         }
+        }
         __syncwarp();
         if (a.need_gin) {
             float *gi = a.gin + off;
@@ -399,7 +425,8 @@ static int emo_tiled_bwd_grid(const pde_emo_desc *d, int sm_count) {
 }
 
 static size_t emo_tiled_hist_floats(const pde_emo_desc *d, int grid) {
-    return (size_t)grid * kTileWarps * (d->Nt > 0 ? d->Nt : 1) * (d->N / 2) * (d->N / 16) * 32;
+    const int seg = (d->Nt + 1) / 2;   // the history holds half the trajectory at a time
+    return (size_t)grid * kTileWarps * (seg + 1) * (d->N / 2) * (d->N / 16) * 32;   // + the parked adjoint
 }
 
 static size_t emo_tiled_workspace_bytes(const pde_emo_desc *d, int sm_count) {

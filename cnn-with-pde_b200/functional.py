@@ -383,3 +383,71 @@ class _TinyFunction(torch.autograd.Function):
 
 def tiny_layer(u, alpha_base, channel_scaling, cfg: TinyConfig):
     return _TinyFunction.apply(_autocast_to_fp32(u), alpha_base, channel_scaling, cfg)
+
+
+# --------------------------------------------- tiny_imagenet's dormant scalar-coefficient methods
+TINY_SPLIT_MODES = {"implicit_diffusion_step": 0, "solve_implicit_x": 1, "solve_implicit_y": 2,
+                    "diffuse_x_explicit": 3, "diffuse_y_explicit": 4}
+
+
+def _tiny_split_desc(mode: int, B: int, H: int, W: int, coeff_x: float, coeff_y: float, dt: float, eps: float):
+    """Band values exactly as the reference produces them: Python-double arithmetic
+    (`r = coeff * dt / (1.0 ** 2)`, `1 + 2 * r`, `1 + r`: tiny_imagenet.py:109,113-121; `coeff * self.dt`:
+    :207), rounded to fp32 where torch.full / the scalar multiply round them."""
+    import numpy as np
+    f = lambda v: float(np.float32(v))   # noqa: E731
+
+    def bands(coeff, step):
+        r = coeff * step / (1.0 ** 2)
+        return (f(-r), f(1 + 2 * r), f(1 + r))
+
+    if mode == 0:
+        cx, cy = bands(coeff_x, dt / 2), bands(coeff_y, dt / 2)     # implicit_diffusion_step: :96,99
+    elif mode in (1, 2):
+        cx, cy = bands(coeff_x, dt), bands(coeff_y, dt)
+    else:
+        cx, cy = (f(coeff_x * dt), 0.0, 0.0), (f(coeff_y * dt), 0.0, 0.0)
+    d = _cabi.TinySplitDesc(B, H, W, mode)
+    for i in range(3):
+        d.cx[i], d.cy[i] = cx[i], cy[i]
+    d.eps = f(eps)
+    return d
+
+
+class _TinySplitFunction(torch.autograd.Function):
+    """All five maps are linear in u with symmetric bands: backward is the same kernel on the gradient."""
+
+    @staticmethod
+    def forward(ctx, u, desc):
+        _require_cuda(u, "ImprovedDiffusionLayer dormant-path input")
+        u = _contig(u)
+        out = torch.empty_like(u)
+        with _guard(u.device):
+            _cabi.check(_cabi.lib().pde_tiny_split(byref(desc), _ptr(u), _ptr(out), _stream(u.device)), "pde_tiny_split")
+        ctx.desc = desc
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        _no_double_backward("ImprovedDiffusionLayer dormant path")
+        gout = _contig(gout)
+        if gout.dtype != torch.float32:
+            gout = gout.float()
+        gin = torch.empty_like(gout)
+        with _guard(gout.device):
+            _cabi.check(_cabi.lib().pde_tiny_split(byref(ctx.desc), _ptr(gout), _ptr(gin), _stream(gout.device)),
+                        "pde_tiny_split")
+        return gin, None
+
+
+def tiny_split(method: str, u, coeff_x: float = 0.0, coeff_y: float = 0.0, dt: float = 0.01, eps: float = 1e-6):
+    """One of ImprovedDiffusionLayer's dormant methods (tiny_imagenet.py:88-233) on planes u (B, H, W).
+    The coefficients are Python numbers, as the reference requires (it hands them to torch.full)."""
+    if u.dim() != 3:
+        raise ValueError(f"{method}: expected (B, H, W) planes, got shape {tuple(u.shape)}")
+    B, H, W = u.shape
+    if H > 64 or W > 64:
+        raise _cabi.PdeB200Error(f"{method}: planes up to 64 x 64 are built, got {H} x {W}")
+    u = _autocast_to_fp32(u)
+    d = _tiny_split_desc(TINY_SPLIT_MODES[method], B, H, W, float(coeff_x), float(coeff_y), float(dt), float(eps))
+    return _TinySplitFunction.apply(u, d)

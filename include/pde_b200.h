@@ -178,6 +178,28 @@ int pde_tiny_backward(const pde_tiny_desc *d, const float *u, const float *gout,
                       float *g_alpha_base, float *g_channel_scaling,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * The dormant scalar-coefficient methods of ImprovedDiffusionLayer, tiny_imagenet.py:88-233:
+ * implicit_diffusion_step (:88-102), solve_implicit_x / _y (:104-157, with the clamp(denom) Thomas
+ * variant of :159-190) and diffuse_x_explicit / diffuse_y_explicit (:199-233).  The reference stores
+ * `use_implicit` (:21) and never reads it, so no forward reaches them; these entry points serve a
+ * caller that does.  u, out: [B][H][W] planes, H, W <= 64.  All five maps are linear in u and
+ * self-adjoint: the gradient with respect to u is the same call on the upstream gradient.
+ * ------------------------------------------------------------------------------------- */
+#define PDE_TINY_SPLIT_ADI 0          /* x solve with cx, then y solve with cy                  */
+#define PDE_TINY_SPLIT_IMPLICIT_X 1
+#define PDE_TINY_SPLIT_IMPLICIT_Y 2
+#define PDE_TINY_SPLIT_EXPLICIT_X 3
+#define PDE_TINY_SPLIT_EXPLICIT_Y 4
+typedef struct pde_tiny_split_desc {
+    int32_t B, H, W, mode;
+    /* implicit modes: {fp32(-r), fp32(1 + 2 r), fp32(1 + r)} with r = coeff * dt / 1.0**2 evaluated in
+     * double as the reference does before torch.full rounds it; explicit modes: [0] = fp32(coeff * dt) */
+    float cx[3], cy[3];
+    float eps;                /* stability_eps: lower clamp of the Thomas pivots                 */
+} pde_tiny_split_desc;
+int pde_tiny_split(const pde_tiny_split_desc *d, const float *u, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,7 +63,7 @@ def lib():
             build()
         _lib = ctypes.CDLL(_LIB_PATH)
         for name in ("adi_forward", "adi_backward", "emotion_forward", "emotion_backward",
-                     "tiny_forward", "tiny_backward"):
+                     "tiny_forward", "tiny_backward", "tiny_split"):
             for suf in ("f32", "f64"):
                 getattr(_lib, f"oracle_{name}_{suf}").restype = ctypes.c_int
     return _lib
@@ -292,3 +292,46 @@ def tiny_backward(spec: TinySpec, u, gout, alpha_base, scaling, need_gin=True, n
     if rc:
         raise RuntimeError(f"oracle_tiny_backward failed rc={rc}")
     return {"gin": gin, "alpha_base": ga, "channel_scaling": gs}
+
+
+# tiny_imagenet.py:88-233 -- the dormant scalar-coefficient methods of ImprovedDiffusionLayer
+TINY_SPLIT_MODES = {"implicit_diffusion_step": 0, "solve_implicit_x": 1, "solve_implicit_y": 2,
+                    "diffuse_x_explicit": 3, "diffuse_y_explicit": 4}
+
+
+def tiny_split_coefficients(mode: int, coeff_x: float, coeff_y: float, dt: float, dtype):
+    """The constants the reference hands to ATen, computed in Python double exactly as it does and
+    rounded to the tensor dtype the way torch.full / a Python-scalar multiply round them.
+    Implicit (tiny_imagenet.py:109,113-121): r = coeff * dt / (1.0 ** 2); bands -r, 1 + 2 r, 1 + r
+    (implicit_diffusion_step passes dt / 2 to both solves, :96,99).  Explicit (:207): coeff * dt."""
+    dtype = np.dtype(dtype)
+
+    def bands(coeff, step):
+        r = coeff * step / (1.0 ** 2)
+        return np.array([-r, 1 + 2 * r, 1 + r], dtype=dtype)
+
+    if mode == 0:
+        return bands(coeff_x, dt / 2), bands(coeff_y, dt / 2)
+    if mode in (1, 2):
+        return bands(coeff_x, dt), bands(coeff_y, dt)
+    return np.array([coeff_x * dt, 0, 0], dtype=dtype), np.array([coeff_y * dt, 0, 0], dtype=dtype)
+
+
+def tiny_split(method: str, u, coeff_x: float = 0.0, coeff_y: float = 0.0, dt: float = 0.01, eps: float = 1e-6,
+               nthreads=0) -> np.ndarray:
+    """One of the dormant methods on planes u (B, H, W); `dt` is the argument the method receives
+    (solve_implicit_x / _y take it explicitly, the others use the layer's dt)."""
+    mode = TINY_SPLIT_MODES[method]
+    dtp = np.asarray(u).dtype
+    suf = _suffix(dtp)
+    u = _as(u, dtp)
+    B, H, W = u.shape
+    cx, cy = tiny_split_coefficients(mode, coeff_x, coeff_y, dt, dtp)
+    out = np.empty_like(u)
+    fn = getattr(lib(), f"oracle_tiny_split_{suf}")
+    ct = ctypes.c_float if suf == "f32" else ctypes.c_double
+    fn.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ct, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    rc = fn(B, H, W, mode, _p(cx), _p(cy), ct(dtp.type(eps)), nthreads, _p(u), _p(out))
+    if rc:
+        raise RuntimeError(f"oracle_tiny_split failed rc={rc}")
+    return out

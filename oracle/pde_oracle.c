@@ -768,3 +768,98 @@ int FN(oracle_tiny_backward)(const oracle_tiny_desc *d, const REAL *u, const REA
     free(ga);
     return 0;
 }
+
+/* ===================================================================================== */
+/* tiny_imagenet.ImprovedDiffusionLayer, dormant methods (tiny_imagenet.py:88-233):      */
+/* scalar-coefficient ADI step with clamp(denom) pivots, and the explicit x / y splits.  */
+/* Nobody in the reference calls them (use_implicit is stored at :21 and never read);    */
+/* they are restated for whoever does.  All of them are linear in u with a constant      */
+/* (Python float) coefficient, so the only gradient is the one with respect to u.        */
+/* ===================================================================================== */
+
+/* thomas_algorithm_batch (tiny_imagenet.py:159-190) for one line of n cells with stride st, the
+ * constant bands of solve_implicit_x / _y (:107-118, :141-152): a = c = -r, b = 1 + 2r, b_0 =
+ * b_{n-1} = 1 + r, every one a Python double rounded to the tensor dtype by torch.full. */
+static void FN(tiny_thomas_line)(int n, REAL am, REAL bmid, REAL bend, REAL eps, const REAL *d, size_t st, REAL *x,
+                                 REAL *cp, REAL *dp) {
+    /* first row (:170-171): no clamp on b_0 */
+    cp[0] = am / bend;
+    dp[0] = d[0] / bend;
+    for (int i = 1; i < n; ++i) {
+        const REAL b = i == n - 1 ? bend : bmid;
+        REAL prod = am * cp[i - 1];
+        REAL denom = b - prod;                       /* :175 */
+        denom = denom < eps ? eps : denom;           /* :176 clamp(min=stability_eps) */
+        cp[i] = i < n - 1 ? am / denom : R(0);       /* :178-179 */
+        REAL pd = am * dp[i - 1];
+        REAL num = d[(size_t)i * st] - pd;
+        dp[i] = num / denom;                         /* :180 */
+    }
+    x[(size_t)(n - 1) * st] = dp[n - 1];             /* :184 */
+    for (int i = n - 2; i >= 0; --i) {
+        REAL pr = cp[i] * x[(size_t)(i + 1) * st];
+        x[(size_t)i * st] = dp[i] - pr;              /* :187 */
+    }
+}
+
+/* diffuse_x_explicit / diffuse_y_explicit (tiny_imagenet.py:199-233) for one line: k = coeff * dt. */
+static void FN(tiny_explicit_line)(int n, REAL k, const REAL *u, size_t st, REAL *out) {
+    for (int i = 0; i < n; ++i) out[(size_t)i * st] = u[(size_t)i * st];
+    if (n > 2)
+        for (int i = 1; i < n - 1; ++i) {
+            REAL two = R(2) * u[(size_t)i * st];
+            REAL acc = u[(size_t)(i - 1) * st] - two;
+            acc = acc + u[(size_t)(i + 1) * st];
+            REAL sc = k * acc;
+            out[(size_t)i * st] = u[(size_t)i * st] + sc;
+        }
+    if (n > 1) {
+        REAL d0 = u[st] - u[0];
+        REAL s0 = k * d0;
+        out[0] = u[0] + s0;
+        REAL d1 = u[(size_t)(n - 2) * st] - u[(size_t)(n - 1) * st];
+        REAL s1 = k * d1;
+        out[(size_t)(n - 1) * st] = u[(size_t)(n - 1) * st] + s1;
+    } else {
+        /* W == 1: u[:, :, 1] does not exist in the reference (IndexError); keep the value */
+    }
+}
+
+/* mode 0: implicit_diffusion_step (x solve with rx, then y solve with ry; :88-102)
+ *      1: solve_implicit_x   2: solve_implicit_y   3: diffuse_x_explicit   4: diffuse_y_explicit
+ * u, out: [B][H][W] planes.  For modes 0-2 cx / cy = {a, b_mid, b_end} already rounded to REAL;
+ * for modes 3-4 cx[0] / cy[0] = coeff * dt rounded to REAL.  All five maps are self-adjoint,
+ * so the gradient with respect to u is the same call on the upstream gradient. */
+int FN(oracle_tiny_split)(int B, int H, int W, int mode, const REAL *cx, const REAL *cy, REAL eps, int nthreads,
+                          const REAL *u, REAL *out) {
+    if (H < 1 || W < 1 || H > 4096 || W > 4096 || mode < 0 || mode > 4) return -2;
+    const size_t P = (size_t)H * W;
+    const int nt = FN(pick_threads)(nthreads);
+#pragma omp parallel num_threads(nt)
+    {
+        const int n = H > W ? H : W;
+        REAL *cp = (REAL *)malloc(sizeof(REAL) * (size_t)n * 2);
+        REAL *dp = cp + n;
+        REAL *tmp = (REAL *)malloc(sizeof(REAL) * P);
+#pragma omp for schedule(static)
+        for (int b = 0; b < B; ++b) {
+            const REAL *src = u + P * b;
+            REAL *dst = out + P * b;
+            if (mode == 0 || mode == 1) {
+                REAL *xo = mode == 0 ? tmp : dst;
+                for (int h = 0; h < H; ++h)
+                    FN(tiny_thomas_line)(W, cx[0], cx[1], cx[2], eps, src + (size_t)h * W, 1, xo + (size_t)h * W, cp, dp);
+                src = xo;
+            }
+            if (mode == 0 || mode == 2)
+                for (int w = 0; w < W; ++w) FN(tiny_thomas_line)(H, cy[0], cy[1], cy[2], eps, src + w, (size_t)W, dst + w, cp, dp);
+            if (mode == 3)
+                for (int h = 0; h < H; ++h) FN(tiny_explicit_line)(W, cx[0], src + (size_t)h * W, 1, dst + (size_t)h * W);
+            if (mode == 4)
+                for (int w = 0; w < W; ++w) FN(tiny_explicit_line)(H, cy[0], src + w, (size_t)W, dst + w);
+        }
+        free(cp);
+        free(tmp);
+    }
+    return 0;
+}

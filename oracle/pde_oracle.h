@@ -100,6 +100,12 @@ int oracle_tiny_backward_f64(const oracle_tiny_desc *d, const double *u, const d
                              const double *alpha_base, const double *scaling, double *gin,
                              double *g_alpha, double *g_scaling);
 
+/* tiny_imagenet.py:88-233 (dormant methods: scalar-coefficient ADI step, explicit x / y splits). */
+int oracle_tiny_split_f32(int B, int H, int W, int mode, const float *cx, const float *cy, float eps, int nthreads,
+                          const float *u, float *out);
+int oracle_tiny_split_f64(int B, int H, int W, int mode, const double *cx, const double *cy, double eps, int nthreads,
+                          const double *u, double *out);
+
 #ifdef __cplusplus
 }
 #endif

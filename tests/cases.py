@@ -103,6 +103,20 @@ CONFIG_CASES = [
 ]
 
 
+# tiny_imagenet.ImprovedDiffusionLayer's dormant methods (tiny_imagenet.py:88-233):
+# (fixture name, method, planes (B, H, W), the layer's dt, the method's positional arguments after u)
+TINY_SPLIT_CASES = [
+    ("adi_64", "implicit_diffusion_step", (3, 64, 64), 0.01, (0.05, 0.05)),          # the model's own size / init values
+    ("adi_64_strong", "implicit_diffusion_step", (2, 64, 64), 0.5, (3.0, 7.5)),      # r = 0.75, 1.9
+    ("adi_48x40", "implicit_diffusion_step", (5, 48, 40), 0.2, (1.3, 0.4)),          # H != W, W not a multiple of 8
+    ("solve_x_33", "solve_implicit_x", (2, 33, 33), 0.01, (0.9, 0.3)),               # odd edge, explicit dt argument
+    ("solve_y_64", "solve_implicit_y", (2, 64, 64), 0.01, (2.5, 0.1)),
+    ("solve_x_clamped", "solve_implicit_x", (2, 6, 6), 0.01, (-0.3, 1.0)),           # negative r: pivots hit the clamp
+    ("explicit_x_64", "diffuse_x_explicit", (3, 64, 64), 0.01, (0.11,)),
+    ("explicit_y_30x64", "diffuse_y_explicit", (3, 30, 64), 0.02, (0.13,)),
+]
+
+
 def default_params(c: Case) -> Dict[str, np.ndarray]:
     """Reference init values, deterministic parts only (SURVEY.md section 8b state_dict row)."""
     C, H, W = c.shape

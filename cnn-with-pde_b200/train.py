@@ -131,7 +131,8 @@ def _dist_env():
 
 
 def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = False, amp: bool = False,
-        seed: int = 1234, pool: int = 4, quiet: bool = False, sync: str = "flat", nccl_in_graph: bool = True):
+        seed: int = 1234, pool: int = 4, quiet: bool = False, sync: str = "flat", nccl_in_graph: bool = True,
+        no_dropout: bool = False, keep_model: bool = False):
     """Train `steps` timed steps (after `warmup`) of `model_name` at per-GPU batch `batch` on the
     current rank's GPU; returns a dict with whole-job img/s (max-over-ranks device time)."""
     world, rank, local = _dist_env()
@@ -147,6 +148,10 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
     torch.manual_seed(seed)            # identical initial weights on every rank
     model = r.build().to(dev)
     model.train()
+    if no_dropout:   # a step without random masks: what the graph-vs-eager equality test compares
+        for m in model.modules():
+            if isinstance(m, nn.Dropout):
+                m.p = 0.0
     criterion = nn.CrossEntropyLoss(label_smoothing=r.label_smoothing)
 
     side = torch.cuda.Stream()
@@ -257,10 +262,12 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
         "params": sum(p.numel() for p in model.parameters()), "data": "synthetic, device resident",
         "scaling": "weak",
     }
+    if keep_model:
+        out["_model"] = model
     if own_pg:
         dist.destroy_process_group()
     if rank == 0 and not quiet:
-        print(json.dumps(out), flush=True)
+        print(json.dumps({k: v for k, v in out.items() if not k.startswith("_")}), flush=True)
     return out
 
 

@@ -153,6 +153,45 @@ def test_launcher_trains_one_gpu(graph):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,batch", [("fashion", 64), ("cifar10", 48)])
+def test_graph_captured_step_equals_eager_step(name, batch):
+    """The CUDA-graph-captured optimiser step (forward, loss, backward, clipping, fused AdamW) against
+    the same step run eagerly: same seed, same synthetic batches, dropout off (its masks come from
+    different Philox offsets under capture).  After six steps the loss and every parameter agree to
+    the noise of the atomics in stock torch's pooling / embedding backward kernels."""
+    from cnn_with_pde_b200 import train
+    runs = [train.run(name, batch, 4, 2, graph=g, quiet=True, no_dropout=True, keep_model=True) for g in (False, True)]
+    assert runs[0]["cuda_graph"] is False and runs[1]["cuda_graph"] is True
+    assert abs(runs[0]["loss"] - runs[1]["loss"]) <= 1e-5 * abs(runs[0]["loss"]), (runs[0]["loss"], runs[1]["loss"])
+    sd_e, sd_g = runs[0]["_model"].state_dict(), runs[1]["_model"].state_dict()
+    worst = 0.0
+    for k in sd_e:
+        a, b = sd_e[k].double(), sd_g[k].double()
+        if a.numel() and a.dtype.is_floating_point:
+            worst = max(worst, float((a - b).norm() / a.norm().clamp_min(1e-30)))
+    assert worst <= 1e-5, worst
+    # the PDE coefficients really moved (the step is not a no-op) and moved identically
+    moved = [k for k in sd_e if is_pde_param(k)]
+    assert moved
+    fresh = train._recipes()[name].build().state_dict()
+    assert any(not torch.equal(sd_g[k].cpu(), fresh[k]) for k in moved)
+
+
+@pytest.mark.gpu
+def test_amp_recipe_scales_unscales_and_steps():
+    """--amp is the CIFAR scripts' recipe (cifar10.py:440,458-467): autocast forward, GradScaler.scale(loss)
+    .backward(), unscale_, clip_grad_norm_, scaler.step, scaler.update.  The PDE layers stay fp32 inside; the
+    run must train (finite loss, parameters move) eagerly and under a CUDA graph."""
+    from cnn_with_pde_b200 import train
+    for graph in (False, True):
+        out = train.run("cifar10", 32, 4, 2, graph=graph, amp=True, quiet=True, keep_model=True)
+        assert out["grad_scaler"] is True and out["autocast"] is True and np.isfinite(out["loss"])
+        fresh = train._recipes()["cifar10"].build().state_dict()
+        sd = out["_model"].state_dict()
+        assert any(not torch.equal(sd[k].cpu(), fresh[k]) for k in sd if "alpha_base" in k)
+
+
+@pytest.mark.gpu
 def test_cifar2_hybrid_model_trains_and_branch_order_does_not_matter(monkeypatch):
     """cifar_2version's hybrid model on the B200 diffusion layers: serial and concurrent branches
     give the same logits and PDE gradients; the launcher trains it under a CUDA graph."""

@@ -276,6 +276,37 @@ def test_cuda_layers_under_autocast():
         assert torch.equal(y2, y_ref)
 
 
+@pytest.mark.parametrize("name,kind,key", [("autocast_cifar10_pde3", "cifar10", "cifar10_pde3"),
+                                           ("autocast_cifar2_diffusion2", "cifar2", "cifar2_diffusion2")])
+def test_cuda_layer_in_the_scripts_autocast_loop_against_the_reference_run_the_same_way(name, kind, key):
+    """The CIFAR scripts call the model inside torch.autocast (cifar10.py:459, cifar_2version.py:521).
+    Fixture (tests/golden/make_golden_autocast.py): the unmodified reference layer run inside autocast and
+    run plainly.  Its autocast run is 4e-3 ... 9e-3 away from its own fp32 run (the channel mix drops to
+    reduced precision, cifar10.py:71).  Our layer, called inside CUDA autocast, must (a) reproduce the
+    reference's fp32 numbers at the usual 1e-5 and (b) therefore sit as close to the reference's autocast
+    numbers as the reference's own two runs sit to each other."""
+    import os
+    import torch
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "autocast_cifar.npz"))
+    c = K.case(name, kind, B=4, **K.SCRIPT_INSTANCES[key])
+    params, (u, g) = K.make_params(c), K.make_io(c)
+    for dtype in (torch.float16, torch.bfloat16):
+        layer = runners.make_cuda_layer(c, params)
+        x = torch.from_numpy(u).cuda().requires_grad_(True)
+        with torch.autocast("cuda", dtype=dtype):
+            y = layer(x)
+            assert y.dtype == torch.float32
+        y.backward(torch.from_numpy(g).cuda())
+        got = {"y": y.detach().cpu().numpy(), "gin": x.grad.cpu().numpy()}
+        got.update({"g_" + k: p.grad.cpu().numpy() for k, p in layer.named_parameters()})
+        for k, v in got.items():
+            fp32, amp = z[f"{name}/fp32/{k}"], z[f"{name}/amp/{k}"]
+            e_fp32 = max(runners.rel_l2(v, fp32), runners.rel_max(v, fp32))
+            assert e_fp32 <= TOL, (k, dtype, e_fp32)
+            gap = runners.rel_l2(amp, fp32)                    # the reference against itself
+            assert runners.rel_l2(v, amp) <= 1.05 * gap + TOL, (k, dtype, runners.rel_l2(v, amp), gap)
+
+
 def test_cuda_split_few_steps_and_single_channel_ops(monkeypatch):
     """Half-line kernels at the ends of the schedule: one and two steps (the checkpoint stream runs
     one step ahead, across items), Lie splitting, channel ops with a single channel, batches of

@@ -63,8 +63,8 @@ def test_cuda_matches_reference_fixture_and_oracle(case):
     want = O.tiny_split(method, z[name + "/u"], **_kw(method, args, dt_layer))
     assert max(runners.rel_l2(got_y, want), runners.rel_max(got_y, want)) <= tol
     # forward() still ignores use_implicit, as the reference does (tiny_imagenet.py:21,34-51)
-    u4 = torch.randn(2, 3, shape[1], shape[1], device="cuda")
-    plain = ImprovedDiffusionLayer(size=shape[1], channels=3, dt=dt_layer, num_steps=1, use_implicit=False).cuda()
+    u4 = torch.randn(2, 3, 64, 64, device="cuda")
+    plain = ImprovedDiffusionLayer(size=64, channels=3, dt=dt_layer, num_steps=1, use_implicit=False).cuda()
     assert torch.equal(layer(u4), plain(u4))
 
 

@@ -84,6 +84,7 @@ def _recipes():
 
 
 MODELS = ("mnist", "fashion", "cifar10", "cifar2", "svhn", "emotion", "tiny")
+GRAPH_PRIMING_STEPS = 3   # eager steps on the capture stream before a CUDA graph is recorded
 
 
 class FlatGradSync:
@@ -170,6 +171,12 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
     x_in, y_in = xs[0].clone(), ys[0].clone()
     loss_out = torch.zeros((), device=dev)
 
+    state = {"done": 0}   # optimiser steps taken so far: step k trains on batch k % pool, captured or not
+
+    def feed(k):
+        x_in.copy_(xs[k % pool], non_blocking=True)
+        y_in.copy_(ys[k % pool], non_blocking=True)
+
     # cifar10.py:440: GradScaler on CUDA; a disabled scaler is the identity (scale = 1, plain step).
     # With the flat all-reduce the ranks exchange SCALED gradients; unscale_ runs after the exchange,
     # so an overflow on one rank is seen by all and the scalers stay in step.
@@ -207,8 +214,10 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
         if use_ddp:
             raise RuntimeError("--graph needs --sync flat (DDP's reducer is not captured)")
         with torch.cuda.stream(side):
-            for _ in range(3):
+            for _ in range(GRAPH_PRIMING_STEPS):   # real optimiser steps on the rotating batches, like every other
+                feed(state["done"])
                 step_body()
+                state["done"] += 1
             side.synchronize()
             parts = [step_body] if (world == 1 or nccl_in_graph) else [fwd_bwd, update]
             pool_id = None
@@ -222,9 +231,9 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
                     flat.all_reduce()          # keep the eager sequence of the step intact
         torch.cuda.current_stream().wait_stream(side)
 
-    def one_step(i):
-        x_in.copy_(xs[i % pool], non_blocking=True)
-        y_in.copy_(ys[i % pool], non_blocking=True)
+    def one_step(_i):
+        feed(state["done"])
+        state["done"] += 1
         if not graphs:
             step_body()
         elif len(graphs) == 1:
@@ -255,7 +264,7 @@ def run(model_name: str, batch: int, steps: int, warmup: int, graph: bool = Fals
         "model": model_name, "n_gpus": world, "batch_per_gpu": batch, "global_batch": batch * world,
         "steps": steps, "warmup": warmup, "ms_per_step": ms / max(steps, 1),
         "img_per_s": batch * world * steps / (ms * 1e-3) if ms > 0 else 0.0,
-        "loss": float(loss_out.item()), "cuda_graph": bool(graphs), "autocast": amp,
+        "loss": float(loss_out.item()), "cuda_graph": bool(graphs), "autocast": amp, "optimizer_steps": state["done"],
         "grad_sync": "none" if world == 1 else ("ddp" if use_ddp else (
             "flat all-reduce inside the CUDA graph" if len(graphs) == 1 else "flat all-reduce")),
         "grad_scaler": bool(amp),

@@ -160,8 +160,11 @@ def test_graph_captured_step_equals_eager_step(name, batch):
     different Philox offsets under capture).  After six steps the loss and every parameter agree to
     the noise of the atomics in stock torch's pooling / embedding backward kernels."""
     from cnn_with_pde_b200 import train
-    runs = [train.run(name, batch, 4, 2, graph=g, quiet=True, no_dropout=True, keep_model=True) for g in (False, True)]
+    # the captured run takes GRAPH_PRIMING_STEPS eager steps before it records the graph: same total
+    runs = [train.run(name, batch, 4, 2 + (0 if g else train.GRAPH_PRIMING_STEPS), graph=g, quiet=True, no_dropout=True,
+                      keep_model=True) for g in (False, True)]
     assert runs[0]["cuda_graph"] is False and runs[1]["cuda_graph"] is True
+    assert runs[0]["optimizer_steps"] == runs[1]["optimizer_steps"] == 6 + train.GRAPH_PRIMING_STEPS
     assert abs(runs[0]["loss"] - runs[1]["loss"]) <= 1e-5 * abs(runs[0]["loss"]), (runs[0]["loss"], runs[1]["loss"])
     sd_e, sd_g = runs[0]["_model"].state_dict(), runs[1]["_model"].state_dict()
     worst = 0.0

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PDE_B200_LIB") or os.path.join(_HERE, "libpde_b200.so")
 MAX_SWEEPS = 192
 MAX_CHANNELS = 4
+MAX_BRANCHES = 4
 ABI_VERSION = 3
 
 # pde_adi_desc.tuning / pde_emo_desc.tuning (include/pde_b200.h)
@@ -32,6 +33,7 @@ EXPORTS = (
     "pde_adi_forward", "pde_adi_backward",
     "pde_adi_checkpoint_bytes", "pde_adi_backward_saved_workspace_bytes", "pde_adi_forward_train",
     "pde_adi_backward_saved",
+    "pde_adi_multi_prepare", "pde_adi_multi_forward_train", "pde_adi_multi_backward_saved",
     "pde_emotion_backward_workspace_bytes", "pde_emotion_forward", "pde_emotion_backward",
     "pde_tiny_backward_workspace_bytes", "pde_tiny_forward", "pde_tiny_backward",
     "pde_tiny_split",
@@ -103,6 +105,13 @@ def lib():
     L.pde_adi_backward_saved.restype = c_int
     L.pde_adi_backward_saved.argtypes = [POINTER(AdiDesc), vp, fp, fp, fp, fp, vp, fp, fp, fp, fp, fp, fp, fp, vp,
                                          c_size_t, vp]
+    pp = c_void_p   # arrays of pointers / descriptors travel as their address
+    L.pde_adi_multi_prepare.restype = c_int
+    L.pde_adi_multi_prepare.argtypes = [c_int, pp, pp, pp, pp, pp, pp, pp, vp]
+    L.pde_adi_multi_forward_train.restype = c_int
+    L.pde_adi_multi_forward_train.argtypes = [c_int, pp, pp, fp, pp, pp, pp, pp, vp]
+    L.pde_adi_multi_backward_saved.restype = c_int
+    L.pde_adi_multi_backward_saved.argtypes = [c_int, pp, pp, fp, pp, pp, pp, pp, pp, pp, pp, pp, pp, pp, pp, pp, pp, vp]
     L.pde_emotion_backward_workspace_bytes.restype = c_size_t
     L.pde_emotion_backward_workspace_bytes.argtypes = [POINTER(EmoDesc)]
     L.pde_emotion_forward.restype = c_int

@@ -3,7 +3,7 @@ import torch
 import torch.nn as nn
 
 from ._base import cached_config, check_input
-from .functional import AdiConfig, adi_layer
+from .functional import AdiConfig, adi_layer, adi_multi_layer
 
 
 class EnhancedDiffusionLayer(nn.Module):
@@ -47,6 +47,21 @@ class EnhancedDiffusionLayer(nn.Module):
         check_input(u, self.channels, self.size, self.size, type(self).__name__)
         return adi_layer(u, self.alpha_base, self.beta_base, self.alpha_time_coeff, self.beta_time_coeff,
                          self.channel_mixing, None, self._config())
+
+    def _branch(self):
+        """This layer as one branch of a multi-layer call (apply_to_same_input)."""
+        return (self.alpha_base, self.beta_base, self.alpha_time_coeff, self.beta_time_coeff, self.channel_mixing, None,
+                self._config())
+
+
+def apply_to_same_input(u, layers):
+    """layers[i](u) for several diffusion layers that read the same input -- the branch loops of
+    MultiScaleExtractor.forward (cifar10.py:272-274) and HybridPDEExtractor.forward (cifar_2version.py:287-288) --
+    with one launch per pass for all of them (one coefficient-table launch, one forward, one backward, one
+    gradient finish) instead of one per layer."""
+    for layer in layers:
+        check_input(u, layer.channels, layer.size, layer.size, type(layer).__name__)
+    return adi_multi_layer(u, [layer._branch() for layer in layers])
 
 
 from .classifiers import CIFAR10PDENoConv, EnhancedFC, MultiScaleExtractor, SpatialAttention  # noqa: E402,F401  (cifar10.py:215-361)

@@ -138,10 +138,12 @@ class MultiScaleExtractor(nn.Module):
         self.attention3 = SpatialAttention(channels, input_size)
         self.combine_weights = nn.Parameter(torch.ones(3) / 3)
 
-    # The three branches read the same input and are independent until the combine: at the script's
-    # batch (512) one PDE layer fills less than one wave of the GPU, so the branches run on three
-    # streams (fork / join around the current stream; captured as parallel branches of a CUDA graph;
-    # autograd replays each branch's backward on its own stream).  SURVEY section 8(f) rank 1.
+    # The three branches read the same input and are independent until the combine (SURVEY section 8(f)
+    # rank 1).  fused_branches: the three PDE layers go through ONE launch per pass (blockIdx selects the
+    # layer; cifar10.apply_to_same_input), the attention gates follow on the current stream.
+    # concurrent_branches (used when fusing is off or not possible): the branches run on three streams
+    # (fork / join around the current stream; captured as parallel branches of a CUDA graph).
+    fused_branches = True
     concurrent_branches = True
 
     def _side_streams(self, device):
@@ -152,7 +154,12 @@ class MultiScaleExtractor(nn.Module):
 
     def forward(self, x):
         branches = ((self.pde1, self.attention1), (self.pde2, self.attention2), (self.pde3, self.attention3))
-        if x.is_cuda and self.concurrent_branches and not os.environ.get("PDE_B200_SERIAL_BRANCHES"):
+        serial = bool(os.environ.get("PDE_B200_SERIAL_BRANCHES"))
+        if x.is_cuda and self.fused_branches and not serial and torch.is_grad_enabled():
+            from .cifar10 import apply_to_same_input
+            ys = apply_to_same_input(x, [pde for pde, _ in branches])
+            feats = [att(y) for (_, att), y in zip(branches, ys)]
+        elif x.is_cuda and self.concurrent_branches and not serial:
             cur = torch.cuda.current_stream(x.device)
             sides = self._side_streams(x.device)
             for s in sides:
@@ -305,8 +312,15 @@ class HybridPDEExtractor(nn.Module):
         self.combination_weights = nn.Parameter(torch.ones(4) / 4)
         self.feature_norm = PlaneBatchNorm2d(channels)   # nn.BatchNorm2d in the reference (cifar_2version.py:276)
 
+    fused_branches = True
+
     def forward(self, x):
-        if x.is_cuda and self.concurrent_branches and not os.environ.get("PDE_B200_SERIAL_BRANCHES"):
+        serial = bool(os.environ.get("PDE_B200_SERIAL_BRANCHES"))
+        if x.is_cuda and self.fused_branches and not serial and torch.is_grad_enabled():
+            from .cifar10 import apply_to_same_input
+            d1, d2 = apply_to_same_input(x, [self.diffusion1, self.diffusion2])   # one launch per pass for both
+            par, ham = self.parabolic(x), self.hamiltonian(x)
+        elif x.is_cuda and self.concurrent_branches and not serial:
             # the second diffusion layer on a side stream; the dense blocks keep the GPU busy on the main one
             cur = torch.cuda.current_stream(x.device)
             cache = self.__dict__.setdefault("_streams", {})

@@ -50,13 +50,12 @@ struct Geo {
 // nothing crosses blocks (the consumers fold them into the call-wide flags: header_flags).
 // ------------------------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(128) prepare_kernel(pde_adi_desc d, pde_adi_schedule sch, SlotMap sm,
-                                                      const float *__restrict__ ab, const float *__restrict__ bb,
-                                                      const float *__restrict__ atc, const float *__restrict__ btc,
-                                                      char *tables, int want_split) {
+__device__ __forceinline__ void prepare_body(const pde_adi_desc &d, const pde_adi_schedule &sch, const SlotMap &sm,
+                                             const float *__restrict__ ab, const float *__restrict__ bb,
+                                             const float *__restrict__ atc, const float *__restrict__ btc, char *tables,
+                                             int want_split, const int s) {
     constexpr int H = N / 2, HQ = (H + 3) / 4;
     const int sps = sweeps_per_step(d), C = d.C;
-    const int s = blockIdx.x;
     const int tid = threadIdx.x;
     const int line = tid % N, c = tid / N;
     const bool live = c < C;
@@ -173,6 +172,37 @@ __global__ void __launch_bounds__(128) prepare_kernel(pde_adi_desc d, pde_adi_sc
     }
     if (s == 0)
         for (int u = tid; u < sm.nslots; u += blockDim.x) hdr->rep[u] = sm.rep[u];
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) prepare_kernel(const __grid_constant__ pde_adi_desc d,
+                                                      const __grid_constant__ pde_adi_schedule sch,
+                                                      const __grid_constant__ SlotMap sm, const float *__restrict__ ab,
+                                                      const float *__restrict__ bb, const float *__restrict__ atc,
+                                                      const float *__restrict__ btc, char *tables, int want_split) {
+    prepare_body<N>(d, sch, sm, ab, bb, atc, btc, tables, want_split, blockIdx.x);
+}
+
+// the tables of several layers in one launch (the kernel parameters hold every layer's schedule: ~3 KB each)
+struct PrepareJob {
+    pde_adi_desc d;
+    pde_adi_schedule sch;
+    SlotMap sm;
+    const float *ab, *bb, *atc, *btc;
+    char *tables;
+    int s_begin;   // first block of this layer
+};
+struct PrepareMulti {
+    int n, want_split;
+    PrepareJob job[PDE_MAX_BRANCHES];
+};
+template <int N>
+__global__ void __launch_bounds__(128) prepare_multi_kernel(const __grid_constant__ PrepareMulti m) {
+    int j = m.n - 1;
+    while (j > 0 && (int)blockIdx.x < m.job[j].s_begin) --j;
+    const PrepareJob &job = m.job[j];
+    prepare_body<N>(job.d, job.sch, job.sm, job.ab, job.bb, job.atc, job.btc, job.tables, m.want_split,
+                    (int)blockIdx.x - job.s_begin);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -958,17 +988,17 @@ __global__ void __launch_bounds__(192, 1) bwd_kernel(const Args a) {
 // 32 output elements; its 8 warps each sum an interleaved slice of the partials (independent loads,
 // unrolled) and the 8 slice sums are combined in a fixed order through shared memory.
 constexpr int kFinishCells = 32, kFinishSlices = 8;
-__global__ void __launch_bounds__(kFinishCells *kFinishSlices)
-    finish_kernel(pde_adi_desc d, int nwarps_total, int nsets_small, const float *__restrict__ part_maps,
-                  const float *__restrict__ part_chan, const float *__restrict__ part_skip,
-                  const float *__restrict__ skipw, float *g_ab, float *g_atc, float *g_bb, float *g_btc,
-                  float *g_chan, float *g_skip) {
+__device__ __forceinline__ void finish_body(const pde_adi_desc &d, int nwarps_total, int nsets_small,
+                                            const float *__restrict__ part_maps, const float *__restrict__ part_chan,
+                                            const float *__restrict__ part_skip, const float *__restrict__ skipw, float *g_ab,
+                                            float *g_atc, float *g_bb, float *g_btc, float *g_chan, float *g_skip,
+                                            const unsigned bid) {
     __shared__ double red[kFinishSlices][kFinishCells];
     const int C = d.C, N = d.N;
     const size_t plane = (size_t)N * N;
     const size_t total = 4 * (size_t)C * plane;
     const int lane = threadIdx.x % kFinishCells, slice = threadIdx.x / kFinishCells;
-    const size_t idx = (size_t)blockIdx.x * kFinishCells + lane;
+    const size_t idx = (size_t)bid * kFinishCells + lane;
     double acc = 0.0;
     int kind = 0, c = 0;
     size_t cell = 0;
@@ -998,7 +1028,7 @@ __global__ void __launch_bounds__(kFinishCells *kFinishSlices)
         float *dst = kind == 0 ? g_ab : kind == 1 ? g_atc : kind == 2 ? g_bb : g_btc;
         dst[(size_t)c * plane + cell] = (float)sum;
     }
-    if (blockIdx.x == 0) {
+    if (bid == 0) {
         if (g_chan && threadIdx.x < C * C) {
             const int cc = threadIdx.x / C, dd = threadIdx.x % C;
             double a = 0.0;
@@ -1012,6 +1042,25 @@ __global__ void __launch_bounds__(kFinishCells *kFinishSlices)
             g_skip[0] = (float)(a * sg * (1.0 - sg));
         }
     }
+}
+
+__global__ void __launch_bounds__(kFinishCells *kFinishSlices)
+    finish_kernel(pde_adi_desc d, int nwarps_total, int nsets_small, const float *__restrict__ part_maps,
+                  const float *__restrict__ part_chan, const float *__restrict__ part_skip,
+                  const float *__restrict__ skipw, float *g_ab, float *g_atc, float *g_bb, float *g_btc,
+                  float *g_chan, float *g_skip) {
+    finish_body(d, nwarps_total, nsets_small, part_maps, part_chan, part_skip, skipw, g_ab, g_atc, g_bb, g_btc, g_chan,
+                g_skip, blockIdx.x);
+}
+
+struct FinishMulti {
+    int n, blocks_per_job;
+    FinishJob job[PDE_MAX_BRANCHES];
+};
+__global__ void __launch_bounds__(kFinishCells *kFinishSlices) finish_multi_kernel(const __grid_constant__ FinishMulti m) {
+    const FinishJob &j = m.job[blockIdx.x / m.blocks_per_job];
+    finish_body(j.d, j.nsets_maps, j.nsets_small, j.part_maps, j.part_chan, j.part_skip, j.skipw, j.g_ab, j.g_atc, j.g_bb,
+                j.g_btc, j.g_chan, j.g_skip, blockIdx.x % m.blocks_per_job);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1143,6 +1192,15 @@ void launch_finish(const pde_adi_desc &d, int nsets_maps, int nsets_small, const
         d, nsets_maps, nsets_small, part_maps, part_chan, part_skip, skipw, g_ab, g_atc, g_bb, g_btc, g_chan, g_skip);
 }
 
+void launch_finish_multi(int n, const FinishJob *jobs, cudaStream_t st) {
+    FinishMulti m{};
+    m.n = n;
+    const size_t total = 4 * (size_t)jobs[0].d.C * jobs[0].d.N * jobs[0].d.N;   // the jobs agree in C and N
+    m.blocks_per_job = (int)((total + kFinishCells - 1) / kFinishCells);
+    for (int i = 0; i < n; ++i) m.job[i] = jobs[i];
+    finish_multi_kernel<<<(unsigned)(n * m.blocks_per_job), kFinishCells * kFinishSlices, 0, st>>>(m);
+}
+
 }  // namespace adi
 }  // namespace pde
 
@@ -1231,6 +1289,101 @@ extern "C" int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sc
         default: rc = PDE_ERR_UNSUPPORTED;
     }
     return rc;
+}
+
+// ---------------------------------------------------------------------------- several layers, one launch
+static int multi_validate(int n, const pde_adi_desc *d) {
+    if (n < 1 || n > PDE_MAX_BRANCHES || !d) return PDE_ERR_INVALID;
+    for (int i = 0; i < n; ++i) {
+        const int rc = validate(&d[i]);
+        if (rc) return rc;
+    }
+    if (d[0].B == 0) return PDE_OK;
+    return split::multi_compatible(n, d) ? PDE_OK : PDE_ERR_UNSUPPORTED;
+}
+
+extern "C" int pde_adi_multi_prepare(int n, const pde_adi_desc *d, const pde_adi_schedule *sched,
+                                     const float *const *ab, const float *const *bb, const float *const *atc,
+                                     const float *const *btc, void *const *tables, void *stream) {
+    int rc = multi_validate(n, d);
+    if (rc) return rc;
+    if (!sched || !ab || !bb || !atc || !btc || !tables) return PDE_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PrepareMulti m{};
+    m.want_split = 1;
+    int blocks = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!ab[i] || !bb[i] || !atc[i] || !btc[i] || !tables[i]) return PDE_ERR_INVALID;
+        if (reinterpret_cast<uintptr_t>(tables[i]) & 255u) return PDE_ERR_WORKSPACE;
+        const int S = d[i].steps * sweeps_per_step(d[i]);
+        if (S == 0) continue;
+        PrepareJob &j = m.job[m.n++];
+        j.d = d[i];
+        j.sch = sched[i];
+        make_slot_map(d[i], sched[i], &j.sm);
+        j.ab = ab[i]; j.bb = bb[i]; j.atc = atc[i]; j.btc = btc[i];
+        j.tables = static_cast<char *>(tables[i]);
+        j.s_begin = blocks;
+        blocks += S;
+    }
+    if (blocks == 0) return PDE_OK;
+    const int threads = ((d[0].C * d[0].N + 31) / 32) * 32;
+    if (d[0].N == 28) prepare_multi_kernel<28><<<blocks, threads, 0, st>>>(m);
+    else if (d[0].N == 32) prepare_multi_kernel<32><<<blocks, threads, 0, st>>>(m);
+    else return PDE_ERR_UNSUPPORTED;
+    return cuda_last_error();
+}
+
+extern "C" int pde_adi_multi_forward_train(int n, const pde_adi_desc *d, const void *const *tables, const float *u,
+                                           const float *const *chan, const float *const *skipw, float *const *out,
+                                           void *const *ckpt, void *stream) {
+    int rc = multi_validate(n, d);
+    if (rc) return rc;
+    if (d[0].B == 0) return PDE_OK;
+    if (!tables || !u || !out || !ckpt || !aligned16(u)) return PDE_ERR_INVALID;
+    for (int i = 0; i < n; ++i) {
+        if (!tables[i] || !out[i] || !ckpt[i] || !aligned16(out[i])) return PDE_ERR_INVALID;
+        if (d[i].chan_op && (!chan || !chan[i])) return PDE_ERR_INVALID;
+        if (d[i].skip && (!skipw || !skipw[i])) return PDE_ERR_INVALID;
+    }
+    return split::forward_multi(n, d, tables, u, chan, skipw, out, ckpt, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pde_adi_multi_backward_saved(int n, const pde_adi_desc *d, const void *const *tables, const float *u,
+                                            const float *const *gout, const float *const *chan,
+                                            const float *const *skipw, const void *const *ckpt, float *const *gin,
+                                            float *const *g_ab, float *const *g_bb, float *const *g_atc,
+                                            float *const *g_btc, float *const *g_chan, float *const *g_skip,
+                                            void *const *workspace, const size_t *workspace_bytes, void *stream) {
+    int rc = multi_validate(n, d);
+    if (rc) return rc;
+    if (!g_ab || !g_bb || !g_atc || !g_btc) return PDE_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < n; ++i) {
+        if (!g_ab[i] || !g_bb[i] || !g_atc[i] || !g_btc[i]) return PDE_ERR_INVALID;
+        if (d[i].chan_op && (!g_chan || !g_chan[i])) return PDE_ERR_INVALID;
+        if (d[i].skip && (!g_skip || !g_skip[i])) return PDE_ERR_INVALID;
+    }
+    if (d[0].B == 0) {
+        for (int i = 0; i < n; ++i) {
+            const size_t mapb = (size_t)d[i].C * d[i].N * d[i].N * sizeof(float);
+            PDE_CUDA_TRY(cudaMemsetAsync(g_ab[i], 0, mapb, st));
+            PDE_CUDA_TRY(cudaMemsetAsync(g_bb[i], 0, mapb, st));
+            PDE_CUDA_TRY(cudaMemsetAsync(g_atc[i], 0, mapb, st));
+            PDE_CUDA_TRY(cudaMemsetAsync(g_btc[i], 0, mapb, st));
+            if (g_chan && g_chan[i]) PDE_CUDA_TRY(cudaMemsetAsync(g_chan[i], 0, (size_t)d[i].C * d[i].C * sizeof(float), st));
+            if (g_skip && g_skip[i]) PDE_CUDA_TRY(cudaMemsetAsync(g_skip[i], 0, sizeof(float), st));
+        }
+        return PDE_OK;
+    }
+    if (!tables || !u || !gout || !ckpt || !workspace || !workspace_bytes || !aligned16(u)) return PDE_ERR_INVALID;
+    for (int i = 0; i < n; ++i) {
+        if (!tables[i] || !gout[i] || !aligned16(gout[i]) || (gin && gin[i] && !aligned16(gin[i]))) return PDE_ERR_INVALID;
+        if (d[i].chan_op && (!chan || !chan[i])) return PDE_ERR_INVALID;
+        if (d[i].skip && (!skipw || !skipw[i])) return PDE_ERR_INVALID;
+    }
+    return split::backward_multi(n, d, tables, u, gout, chan, skipw, ckpt, gin, g_ab, g_bb, g_atc, g_btc, g_chan, g_skip,
+                                 workspace, workspace_bytes, st);
 }
 
 extern "C" int pde_adi_forward_train(const pde_adi_desc *d, const void *tables, const float *u, const float *chan,

@@ -130,6 +130,15 @@ void launch_finish(const pde_adi_desc &d, int nsets_maps, int nsets_small, const
                    const float *part_chan, const float *part_skip, const float *skipw, float *g_ab,
                    float *g_atc, float *g_bb, float *g_btc, float *g_chan, float *g_skip, cudaStream_t st);
 
+// one layer's share of a multi-layer finish launch
+struct FinishJob {
+    pde_adi_desc d;
+    int nsets_maps, nsets_small;
+    const float *part_maps, *part_chan, *part_skip, *skipw;
+    float *g_ab, *g_atc, *g_bb, *g_btc, *g_chan, *g_skip;
+};
+void launch_finish_multi(int n, const FinishJob *jobs, cudaStream_t st);
+
 // adi_split.cu
 namespace split {
 // mirrored index of a row / column / line: 0 .. H-1 from the near edge, H .. N-1 from the far edge
@@ -153,6 +162,13 @@ int backward(const pde_adi_desc &d, const char *tables, const float *u, const fl
              const float *skipw, const float *ckpt, float *gin, float *g_ab, float *g_bb, float *g_atc,
              float *g_btc, float *g_chan, float *g_skip, void *workspace, size_t workspace_bytes,
              cudaStream_t st);
+bool multi_compatible(int n, const pde_adi_desc *d);
+int forward_multi(int n, const pde_adi_desc *d, const void *const *tables, const float *u, const float *const *chan,
+                  const float *const *skipw, float *const *out, void *const *ckpt, cudaStream_t st);
+int backward_multi(int n, const pde_adi_desc *d, const void *const *tables, const float *u, const float *const *gout,
+                   const float *const *chan, const float *const *skipw, const void *const *ckpt, float *const *gin,
+                   float *const *g_ab, float *const *g_bb, float *const *g_atc, float *const *g_btc, float *const *g_chan,
+                   float *const *g_skip, void *const *workspace, const size_t *workspace_bytes, cudaStream_t st);
 }  // namespace split
 
 }  // namespace adi

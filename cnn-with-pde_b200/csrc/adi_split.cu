@@ -414,7 +414,7 @@ __device__ __noinline__ void write_ck_flags(const Header *hdr, int steps, int sp
 // MIX1: instantiation for layers with a pre-step channel mix (chan_op == 1), which runs inside the
 // first sweep phase of a step; the others keep the plain schedule (and their register allocation).
 template <int N, int P, int Q, bool MIX1>
-__global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kernel(const Args a) {
+__device__ __forceinline__ void sfwd_body(const Args &a, const int bid, const int nblk) {
     using G = SG<N, P>;
     constexpr int H = G::H, TILE = G::TILE, HQ4 = 4 * G::HQ;
     extern __shared__ __align__(128) float smem[];
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
         const Header *hdr = reinterpret_cast<const Header *>(a.tables);
         for (int i = threadIdx.x; i < S; i += nthr) h_slot[i] = hdr->slot[i];
         // the call-wide flags of the backward pass travel with the checkpoints
-        if (a.ck_flags && blockIdx.x == 0 && threadIdx.x < 32) write_ck_flags(hdr, d.steps, sps, a.ck_flags);
+        if (a.ck_flags && bid == 0 && threadIdx.x < 32) write_ck_flags(hdr, d.steps, sps, a.ck_flags);
     }
     if (threadIdx.x == 0) {
         mbar_init(&cbar[0], 1);
@@ -458,10 +458,10 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
     };
     const size_t plane = (size_t)N * N;
     int cb = 0;
-    if (blockIdx.x < a.nitems) c_fill(0, 0);
+    if (bid < a.nitems) c_fill(0, 0);
 
-    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-        const int next_item = item + gridDim.x;
+    for (int item = bid; item < a.nitems; item += nblk) {
+        const int next_item = item + nblk;
         float *set = smem;
         float *my = set + (size_t)t.c * Q * TILE;   // this channel's Q tiles
         if (threadIdx.x == 0) {   // the next item's planes start their trip from HBM to L2 now
@@ -574,6 +574,26 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
                                          sig, om);
         }
     }
+}
+
+template <int N, int P, int Q, bool MIX1>
+__global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kernel(const Args a) {
+    sfwd_body<N, P, Q, MIX1>(a, blockIdx.x, gridDim.x);
+}
+
+// Several layers applied to the SAME input in one launch (the three PDE branches of cifar10's
+// MultiScaleExtractor, cifar10.py:272-274; the two of cifar_2version's HybridPDEExtractor,
+// cifar_2version.py:287-288): consecutive blocks take the same items of consecutive branches, so the
+// branches walk the input together and all but the first read of a plane come out of L2.
+struct MultiArgs {
+    int n;
+    Args a[PDE_MAX_BRANCHES];
+};
+
+template <int N, int P, int Q, bool MIX1>
+__global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_multi_kernel(const __grid_constant__ MultiArgs m) {
+    const int b = blockIdx.x % m.n;
+    sfwd_body<N, P, Q, MIX1>(m.a[b], blockIdx.x / m.n, gridDim.x / m.n);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -753,7 +773,7 @@ __device__ __forceinline__ void chan_adjoint(float *ggt, const float *gxt, int c
 //            stream (item, last step) ... (item, step 0), (next item, last step) ...
 //   g tiles: the next item's gout planes by LDGSTS while the current item is reversed.
 template <int N, int P, bool CHAN>
-__global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kernel(const Args a) {
+__device__ __forceinline__ void sbwd_body(const Args &a, const int bid, const int nblk) {
     using G = SG<N, P>;
     constexpr int H = G::H, TILE = G::TILE, HQ4 = 4 * G::HQ;
     extern __shared__ __align__(128) float smem[];
@@ -819,7 +839,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
     // exact mode: outputs of the first sps-1 sweeps of the step being reversed, per block
     const size_t scr_slot = (size_t)H * nthr;
     unsigned long long *sweep_scr =
-        reinterpret_cast<unsigned long long *>(a.scratch) + (size_t)blockIdx.x * 2 * scr_slot + threadIdx.x;
+        reinterpret_cast<unsigned long long *>(a.scratch) + (size_t)bid * 2 * scr_slot + threadIdx.x;
     // the layer input is needed in the spare x buffer at step 0 (pre-step mix adjoint, exact
     // recomputation): the first checkpoint of the next item then waits for the end of the item
     const bool defer_cross = exact || (CHAN && d.chan_op == 1);
@@ -854,17 +874,17 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
         }
     };
     int xb = 0, gb = 0, cb = 0;
-    if (blockIdx.x < a.nitems) {
-        x_fill(0, blockIdx.x, d.steps - 1);
+    if (bid < a.nitems) {
+        x_fill(0, bid, d.steps - 1);
         c_fill(0, a.S - 1);
         if (GDB) {
-            planes_to_tile_async<N, P>(a.gout, gset(0) + (size_t)t.c * CS, blockIdx.x, t.c, C, d.B, t.tid_c);
+            planes_to_tile_async<N, P>(a.gout, gset(0) + (size_t)t.c * CS, bid, t.c, C, d.B, t.tid_c);
             cp_async_commit();
         }
     }
 
-    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-        const int next_item = item + gridDim.x;
+    for (int item = bid; item < a.nitems; item += nblk) {
+        const int next_item = item + nblk;
         float *ggt = gset(gb), *gt = ggt + (size_t)t.c * CS;
         if (GDB) {
             cp_async_wait_all();
@@ -1059,7 +1079,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
 
     // ------------------------------ partials: TMEM -> sum over the P pairs -> global [row][col]
     tmem_wait_st();
-    float *pm = a.part_maps + ((size_t)blockIdx.x * C + t.c) * 4 * plane;
+    float *pm = a.part_maps + ((size_t)bid * C + t.c) * 4 * plane;
     const int L = mirror(t.R, N);   // the line's position in the plane
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -1080,7 +1100,7 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
             }
         }
     }
-    const size_t set = ((size_t)blockIdx.x * G::WPC + t.wi) * C + t.c;
+    const size_t set = ((size_t)bid * G::WPC + t.wi) * C + t.c;
 #pragma unroll
     for (int dd = 0; dd < PDE_MAX_CHANNELS; ++dd) {
         const float sgm = warp_sum(gm[dd]);
@@ -1091,6 +1111,17 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
     tmem_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_slot, (uint32_t)a.tmem_cols);
+}
+
+template <int N, int P, bool CHAN>
+__global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kernel(const Args a) {
+    sbwd_body<N, P, CHAN>(a, blockIdx.x, gridDim.x);
+}
+
+template <int N, int P, bool CHAN>
+__global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_multi_kernel(const __grid_constant__ MultiArgs m) {
+    const int b = blockIdx.x % m.n;
+    sbwd_body<N, P, CHAN>(m.a[b], blockIdx.x / m.n, gridDim.x / m.n);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1193,16 +1224,43 @@ static const void *fwd_kernel_for(int N, int P, int Q, bool mix1) {
     return nullptr;
 }
 
+// the multi-branch kernels exist for the two-pairs-per-group geometry (the multi-branch models of the
+// reference are three-channel: cifar10.py:253-258, cifar_2version.py:269-270)
+template <int N>
+static const void *fwd_multi_kernel_n(int Q, bool mix1) {
+    if (mix1)
+        return Q == 2 ? reinterpret_cast<const void *>(sfwd_multi_kernel<N, 2, 2, true>)
+                      : reinterpret_cast<const void *>(sfwd_multi_kernel<N, 2, 1, true>);
+    return Q == 2 ? reinterpret_cast<const void *>(sfwd_multi_kernel<N, 2, 2, false>)
+                  : reinterpret_cast<const void *>(sfwd_multi_kernel<N, 2, 1, false>);
+}
+static const void *fwd_multi_kernel_for(int N, int P, int Q, bool mix1) {
+    if (P != 2 || (Q != 1 && Q != 2)) return nullptr;
+    if (N == 28) return fwd_multi_kernel_n<28>(Q, mix1);
+    if (N == 32) return fwd_multi_kernel_n<32>(Q, mix1);
+    return nullptr;
+}
+static const void *bwd_multi_kernel_for(int N, int P, bool chan) {
+    if (P != 2) return nullptr;
+    if (N == 28)
+        return chan ? reinterpret_cast<const void *>(sbwd_multi_kernel<28, 2, true>)
+                    : reinterpret_cast<const void *>(sbwd_multi_kernel<28, 2, false>);
+    if (N == 32)
+        return chan ? reinterpret_cast<const void *>(sbwd_multi_kernel<32, 2, true>)
+                    : reinterpret_cast<const void *>(sbwd_multi_kernel<32, 2, false>);
+    return nullptr;
+}
+
 struct BwdLaunch {
     int grid, nitems, occ;
     size_t smem;
 };
 
-static int plan_bwd_grid(const pde_adi_desc &d, const Plan &p, BwdLaunch *b) {
+static int plan_bwd_grid(const pde_adi_desc &d, const Plan &p, BwdLaunch *b, const void *kern_override = nullptr) {
     DeviceProps props;
     int rc = query_props(&props);
     if (rc) return rc;
-    const void *kern = bwd_kernel_for(d.N, p.P, d.chan_op != 0);
+    const void *kern = kern_override ? kern_override : bwd_kernel_for(d.N, p.P, d.chan_op != 0);
     if (!kern) return PDE_ERR_UNSUPPORTED;
     // x tile sets double buffered, g sets too for P == 4, two coefficient stages of two tables
     b->smem = (size_t)(p.P >= 4 ? 4 : 3) * d.C * p.tile_bytes + (size_t)4 * d.C * ((d.N / 2 + 3) / 4) * d.N * 2 * 16;
@@ -1338,6 +1396,117 @@ int backward(const pde_adi_desc &d, const char *tables, const float *u, const fl
     if (rc) return rc;
     launch_finish(d, w.nsets_maps, w.nsets_small, a.part_maps, a.part_chan, a.part_skip, skipw, g_ab, g_atc, g_bb, g_btc,
                   g_chan, g_skip, st);
+    return cuda_last_error();
+}
+
+// ------------------------------------------------------------------------------------------
+// several layers on the same input, one launch per pass
+// ------------------------------------------------------------------------------------------
+bool multi_compatible(int n, const pde_adi_desc *d) {
+    if (n < 2 || n > PDE_MAX_BRANCHES || !d) return false;
+    for (int i = 0; i < n; ++i) {
+        if (!supported(d[i])) return false;
+        if (d[i].B != d[0].B || d[i].C != d[0].C || d[i].N != d[0].N || d[i].chan_op != d[0].chan_op ||
+            d[i].skip != d[0].skip || d[i].tuning != d[0].tuning)
+            return false;
+    }
+    Plan p;
+    if (make_plan(d[0], &p) != PDE_OK) return false;
+    return fwd_multi_kernel_for(d[0].N, p.P, p.Qf, d[0].chan_op == 1) != nullptr &&
+           bwd_multi_kernel_for(d[0].N, p.P, d[0].chan_op != 0) != nullptr;
+}
+
+static float *ck_images(void *ckpt, CkFlags **flags) {   // [CkFlags, 256 bytes][tile images]
+    float *base = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ckpt) + 255u) & ~(uintptr_t)255u);
+    *flags = reinterpret_cast<CkFlags *>(base);
+    return base + kCkHeaderFloats;
+}
+
+int forward_multi(int n, const pde_adi_desc *d, const void *const *tables, const float *u, const float *const *chan,
+                  const float *const *skipw, float *const *out, void *const *ckpt, cudaStream_t st) {
+    Plan p;
+    int rc = make_plan(d[0], &p);
+    if (rc) return rc;
+    DeviceProps props;
+    rc = query_props(&props);
+    if (rc) return rc;
+    const void *kern = fwd_multi_kernel_for(d[0].N, p.P, p.Qf, d[0].chan_op == 1);
+    if (!kern) return PDE_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)d[0].C * p.Qf * p.tile_bytes + (size_t)4 * d[0].C * ((d[0].N / 2 + 3) / 4) * d[0].N * 2 * 16;
+    if (smem > (size_t)props.max_smem_optin) return PDE_ERR_UNSUPPORTED;
+    int per_sm = 1;
+    rc = cached_occupancy(kern, p.threads, smem, &per_sm);
+    if (rc) return rc;
+    MultiArgs m{};
+    m.n = n;
+    const int nitems = (p.ngroups + p.Qf - 1) / p.Qf;
+    for (int i = 0; i < n; ++i) {
+        Args &a = m.a[i];
+        fill_args(d[i], static_cast<const char *>(tables[i]), &a);
+        a.nitems = nitems;
+        a.u = u;
+        a.chan = chan ? chan[i] : nullptr;
+        a.skipw = skipw ? skipw[i] : nullptr;
+        a.out = out[i];
+        if (ckpt && ckpt[i]) a.ckpt = ck_images(ckpt[i], &a.ck_flags);
+    }
+    int nblk = props.sm_count * per_sm / n;      // blocks per branch: the branches share the resident set
+    if (nblk > nitems) nblk = nitems;
+    if (nblk < 1) nblk = 1;
+    if (debug_enabled())
+        fprintf(stderr, "[pde_b200] split fwd multi plan: n=%d N=%d C=%d P=%d Q=%d threads=%d smem=%zu occ=%d grid=%d\n", n, d[0].N,
+                d[0].C, p.P, p.Qf, p.threads, smem, per_sm, n * nblk);
+    void *params[] = {&m};
+    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(n * nblk), dim3(p.threads), params, smem, st));
+    return cuda_last_error();
+}
+
+int backward_multi(int n, const pde_adi_desc *d, const void *const *tables, const float *u, const float *const *gout,
+                   const float *const *chan, const float *const *skipw, const void *const *ckpt, float *const *gin,
+                   float *const *g_ab, float *const *g_bb, float *const *g_atc, float *const *g_btc, float *const *g_chan,
+                   float *const *g_skip, void *const *workspace, const size_t *workspace_bytes_, cudaStream_t st) {
+    Plan p;
+    BwdLaunch b;
+    int rc = make_plan(d[0], &p);
+    if (rc) return rc;
+    const void *kern = bwd_multi_kernel_for(d[0].N, p.P, d[0].chan_op != 0);
+    if (!kern) return PDE_ERR_UNSUPPORTED;
+    rc = plan_bwd_grid(d[0], p, &b, kern);
+    if (rc) return rc;
+    int nblk = b.grid / n;                       // blocks per branch (b.grid = resident blocks, capped by the items)
+    if (nblk < 1) nblk = 1;
+    WsLayout w;
+    ws_layout(d[0], p, nblk, &w);
+    const size_t need = (w.scratch_floats + w.maps_floats + w.chan_floats + w.skip_floats) * sizeof(float) + 512;
+    MultiArgs m{};
+    m.n = n;
+    FinishJob jobs[PDE_MAX_BRANCHES];
+    for (int i = 0; i < n; ++i) {
+        if (!workspace || !workspace[i] || workspace_bytes_[i] < need || !ckpt || !ckpt[i]) return PDE_ERR_WORKSPACE;
+        float *ws = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace[i]) + 255u) & ~(uintptr_t)255u);
+        Args &a = m.a[i];
+        fill_args(d[i], static_cast<const char *>(tables[i]), &a);
+        a.nitems = b.nitems;
+        a.need_gin = gin && gin[i];
+        a.tmem_cols = p.tmem_cols;
+        a.u = u;
+        a.gout = gout[i];
+        a.chan = chan ? chan[i] : nullptr;
+        a.skipw = skipw ? skipw[i] : nullptr;
+        a.gin = gin ? gin[i] : nullptr;
+        a.ckpt = ck_images(const_cast<void *>(ckpt[i]), &a.ck_flags);
+        a.scratch = ws;
+        a.part_maps = ws + w.scratch_floats;
+        a.part_chan = a.part_maps + w.maps_floats;
+        a.part_skip = a.part_chan + w.chan_floats;
+        jobs[i] = FinishJob{d[i], w.nsets_maps, w.nsets_small, a.part_maps, a.part_chan, a.part_skip, a.skipw,
+                            g_ab[i], g_atc[i], g_bb[i], g_btc[i], g_chan ? g_chan[i] : nullptr, g_skip ? g_skip[i] : nullptr};
+    }
+    void *params[] = {&m};
+    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(n * nblk), dim3(p.threads), params, b.smem, st));
+    rc = cuda_last_error();
+    if (rc) return rc;
+    launch_finish_multi(n, jobs, st);
     return cuda_last_error();
 }
 

@@ -14,6 +14,7 @@ version counters have not moved.
 from __future__ import annotations
 
 import contextlib
+import ctypes
 import functools
 import os
 
@@ -261,6 +262,136 @@ class _AdiFunction(torch.autograd.Function):
 def adi_layer(u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg: AdiConfig):
     u = _autocast_to_fp32(u)
     return _AdiFunction.apply(u, alpha_base, beta_base, alpha_tc, beta_tc, chan, skipw, cfg, torch.is_grad_enabled())
+
+
+# ------------------------------------------- several implicit layers on the same input, one launch per pass
+def _ptr_array(ptrs):
+    arr = (ctypes.c_void_p * len(ptrs))(*[p if p else None for p in ptrs])
+    return arr
+
+
+class _AdiMultiPlan:
+    """Descriptor / schedule arrays and buffer sizes of a multi-branch call: (configurations, batch, tuning, device)."""
+    __slots__ = ("plans", "n", "descs", "scheds", "ok")
+
+    def __init__(self, cfgs, B, tuning, device_index):
+        self.plans = [_adi_plan(c, B, tuning, device_index) for c in cfgs]
+        self.n = len(cfgs)
+        self.descs = (_cabi.AdiDesc * self.n)(*[p.desc for p in self.plans])
+        self.scheds = (_cabi.AdiSchedule * self.n)(*[p.sched for p in self.plans])
+        c0 = cfgs[0]
+        self.ok = (2 <= self.n <= _cabi.MAX_BRANCHES and all(p.ckpt_bytes > 0 for p in self.plans) and
+                   all((c.N, c.C, c.chan_op, c.skip) == (c0.N, c0.C, c0.chan_op, c0.skip) for c in cfgs))
+
+
+@functools.lru_cache(maxsize=64)
+def _adi_multi_plan(cfgs, B, tuning, device_index):
+    return _AdiMultiPlan(cfgs, B, tuning, device_index)
+
+
+class _AdiMultiFunction(torch.autograd.Function):
+    """n implicit layers applied to one input: inputs (u, cfgs, ab_0, bb_0, atc_0, btc_0, chan_0, skip_0, ab_1, ...),
+    outputs (out_0, ..., out_{n-1}).  One prepare, one forward and one backward (+ one finish) launch for all of
+    them (include/pde_b200.h: pde_adi_multi_*)."""
+
+    @staticmethod
+    def forward(ctx, u, cfgs, *flat):
+        _require_cuda(u, "PDE layer input")
+        L = _cabi.lib()
+        n = len(cfgs)
+        u = _contig(u)
+        per = [flat[6 * i:6 * i + 6] for i in range(n)]
+        dev = u.device
+        mp = _adi_multi_plan(cfgs, u.shape[0], env_tuning(), dev.index if dev.index is not None else torch.cuda.current_device())
+        maps = [[_contig(p) for p in br[:4]] for br in per]
+        chans = [None if br[4] is None else _contig(br[4].detach()) for br in per]
+        skips = [None if br[5] is None else _contig(br[5].detach()) for br in per]
+        keep = []   # the pointer arrays must outlive the calls that read them
+
+        def arr(ptrs):
+            a = _ptr_array(ptrs)
+            keep.append(a)
+            return ctypes.addressof(a)
+
+        with _guard(dev):
+            st = _stream(dev)
+            tables = [_bytes(p.tables_bytes, dev) for p in mp.plans]
+            tab = arr([t.data_ptr() for t in tables])
+            _cabi.check(L.pde_adi_multi_prepare(n, ctypes.addressof(mp.descs), ctypes.addressof(mp.scheds),
+                                                *[arr([m[k].data_ptr() for m in maps]) for k in range(4)], tab, st),
+                        "pde_adi_multi_prepare")
+            outs = [torch.empty_like(u) for _ in range(n)]
+            ckpts = [_bytes(p.ckpt_bytes, dev) for p in mp.plans]
+            _cabi.check(L.pde_adi_multi_forward_train(
+                n, ctypes.addressof(mp.descs), tab, _ptr(u), arr([_ptr(c) for c in chans]), arr([_ptr(s) for s in skips]),
+                arr([o.data_ptr() for o in outs]), arr([c.data_ptr() for c in ckpts]), st), "pde_adi_multi_forward_train")
+        ctx.mp = mp
+        ctx.has = [(c is not None, s is not None) for c, s in zip(chans, skips)]
+        ctx.param_shapes = [br[0].shape for br in per]
+        ctx.save_for_backward(u, *tables, *ckpts, *[t for t in chans + skips if t is not None])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        _no_double_backward("PDE layers")
+        L = _cabi.lib()
+        mp = ctx.mp
+        n = mp.n
+        saved = list(ctx.saved_tensors)
+        u, tables, ckpts, rest = saved[0], saved[1:1 + n], saved[1 + n:1 + 2 * n], saved[1 + 2 * n:]
+        chans = [rest.pop(0) if h[0] else None for h in ctx.has]
+        skips = [rest.pop(0) if h[1] else None for h in ctx.has]
+        gouts = [_contig(g if g.dtype == torch.float32 else g.float()) for g in gouts]
+        dev = u.device
+        keep = []   # the pointer arrays must outlive the call that reads them
+
+        def _keep(a):
+            keep.append(a)
+            return a
+
+        arr = lambda ts: ctypes.addressof(_keep(_ptr_array([_ptr(t) for t in ts])))   # noqa: E731
+        with _guard(dev):
+            wss = [_bytes(p.ws_saved_bytes, dev) for p in mp.plans]
+            wsb = _keep((ctypes.c_size_t * n)(*[p.ws_saved_bytes for p in mp.plans]))
+            need_gin = ctx.needs_input_grad[0]
+            gins = [torch.empty_like(u) for _ in range(n)] if need_gin else [None] * n
+            gms = [torch.empty((4,) + tuple(s), dtype=torch.float32, device=dev) for s in ctx.param_shapes]
+            plane = [4 * p.cfg.C * p.cfg.N * p.cfg.N for p in mp.plans]
+            gch = [torch.empty((p.cfg.C, p.cfg.C), dtype=torch.float32, device=dev) if c is not None else None
+                   for p, c in zip(mp.plans, chans)]
+            gsk = [torch.empty((), dtype=torch.float32, device=dev) if s is not None else None for s in skips]
+            gp = lambda k: ctypes.addressof(_keep(_ptr_array([g.data_ptr() + k * pl for g, pl in zip(gms, plane)])))   # noqa: E731
+            _cabi.check(L.pde_adi_multi_backward_saved(
+                n, ctypes.addressof(mp.descs), arr(tables), _ptr(u), arr(gouts), arr(chans), arr(skips), arr(ckpts), arr(gins),
+                gp(0), gp(1), gp(2), gp(3), arr(gch), arr(gsk), arr(wss), ctypes.addressof(wsb), _stream(dev)),
+                "pde_adi_multi_backward_saved")
+        gin = None
+        if need_gin:
+            gin = gins[0]
+            for g in gins[1:]:
+                gin = gin + g
+        grads = []
+        for i in range(n):
+            grads += list(gms[i].unbind(0)) + [gch[i], gsk[i]]
+        return (gin, None, *grads)
+
+
+def adi_multi_layer(u, branches):
+    """Apply n implicit layers to the same input.  branches: sequence of (alpha_base, beta_base,
+    alpha_time_coeff, beta_time_coeff, chan, skip_weight, cfg).  Returns the n outputs.  Falls back to n
+    single-layer calls when the layers cannot share a launch (different shapes / channel ops, plane sizes the
+    half-line kernels do not serve, inference)."""
+    u = _autocast_to_fp32(u)
+    cfgs = tuple(b[6] for b in branches)
+    fused = u.is_cuda and torch.is_grad_enabled() and any(t is not None and t.requires_grad for b in branches for t in b[:6])
+    if fused:
+        dev = u.device
+        mp = _adi_multi_plan(cfgs, u.shape[0], env_tuning(), dev.index if dev.index is not None else torch.cuda.current_device())
+        fused = mp.ok and u.shape[0] > 0
+    if not fused:
+        return tuple(adi_layer(u, *b[:6], b[6]) for b in branches)
+    flat = [t for b in branches for t in b[:6]]
+    return _AdiMultiFunction.apply(u, cfgs, *flat)
 
 
 # ------------------------------------------------------------------- explicit, frozen ghost ring

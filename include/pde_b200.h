@@ -138,6 +138,35 @@ int pde_adi_backward(const pde_adi_desc *d, const void *tables, const float *u, 
                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Several implicit layers applied to the SAME input, one launch per pass instead of one per layer.
+ * Replaces the branch loops of MultiScaleExtractor.forward (cifar10.py:272-274: pde1, pde2, pde3 on x)
+ * and HybridPDEExtractor.forward (cifar_2version.py:287-288: diffusion1, diffusion2 on x) and what
+ * autograd records under them.  Arrays have n <= PDE_MAX_BRANCHES entries, one per layer; the layers
+ * may differ in steps, dt, spacing and splitting but must agree in B, C, N, chan_op, skip and tuning
+ * (the branches share one kernel instantiation).  PDE_ERR_UNSUPPORTED means "call the layers one by
+ * one": the configuration is not served by the half-line kernels or the layers do not agree.
+ * Buffer sizes are those of the single-layer queries on d[i]; outputs and grad_input are bit-identical
+ * to n single-layer calls, coefficient gradients equal them up to the fp32 summation order (the
+ * branches share the resident blocks, so each block sums a different subset of the batch).  gin[i] (each may be NULL, or gin == NULL) receives the gradient of branch i with
+ * respect to the input; the caller (autograd) adds them up.
+ * ------------------------------------------------------------------------------------- */
+#define PDE_MAX_BRANCHES 4
+int pde_adi_multi_prepare(int n, const pde_adi_desc *d, const pde_adi_schedule *sched,
+                          const float *const *alpha_base, const float *const *beta_base,
+                          const float *const *alpha_time_coeff, const float *const *beta_time_coeff,
+                          void *const *tables, void *stream);
+int pde_adi_multi_forward_train(int n, const pde_adi_desc *d, const void *const *tables, const float *u,
+                                const float *const *chan, const float *const *skip_weight, float *const *out,
+                                void *const *ckpt, void *stream);
+int pde_adi_multi_backward_saved(int n, const pde_adi_desc *d, const void *const *tables, const float *u,
+                                 const float *const *gout, const float *const *chan, const float *const *skip_weight,
+                                 const void *const *ckpt, float *const *gin,
+                                 float *const *g_alpha_base, float *const *g_beta_base,
+                                 float *const *g_alpha_time_coeff, float *const *g_beta_time_coeff,
+                                 float *const *g_chan, float *const *g_skip_weight,
+                                 void *const *workspace, const size_t *workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Explicit family, frozen reflected ghost ring.  Replaces PDELayer.forward / alpha / beta
  * emotion_recognition.py:76-97.
  * ------------------------------------------------------------------------------------- */

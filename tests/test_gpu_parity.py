@@ -367,3 +367,66 @@ def test_cuda_split_results_are_bitwise_reproducible(monkeypatch):
             else:
                 for a, b in zip(first, now):
                     assert torch.equal(a, b), c.name
+
+
+# ------------------------------------------------------- several layers on the same input, one launch per pass
+def _three_cifar_layers(B):
+    cs = [K.case(f"multi_{k}", "cifar10", B=B, seed=1234 + i, **K.SCRIPT_INSTANCES[k])
+          for i, k in enumerate(("cifar10_pde1", "cifar10_pde2", "cifar10_pde3"))]
+    return cs, [K.make_params(c) for c in cs]
+
+
+@pytest.mark.parametrize("B", [3, 512, 4099])
+def test_cuda_multi_branch_launch_matches_single_layer_calls_and_oracle(B):
+    """The three PDE layers of cifar10's MultiScaleExtractor (cifar10.py:253-258,272-274) through
+    cifar10.apply_to_same_input -- one prepare, one forward, one backward and one finish launch for all of
+    them -- against three single-layer calls (outputs and grad_input bit-identical) and against the oracle."""
+    import torch
+    from cnn_with_pde_b200.cifar10 import apply_to_same_input
+    cs, ps = _three_cifar_layers(B)
+    layers = [runners.make_cuda_layer(c, p) for c, p in zip(cs, ps)]
+    u_np, _ = K.make_io(cs[0])
+    gs_np = [K.make_io(c)[1] for c in cs]
+    x = torch.from_numpy(u_np).cuda().requires_grad_(True)
+    ys = apply_to_same_input(x, layers)
+    torch.autograd.backward(list(ys), [torch.from_numpy(g).cuda() for g in gs_np])
+    fused = {"gin": x.grad.clone(), "ys": [y.detach().clone() for y in ys],
+             "grads": [{k: p.grad.clone() for k, p in l.named_parameters()} for l in layers]}
+    x2 = torch.from_numpy(u_np).cuda().requires_grad_(True)
+    for l in layers:
+        for p in l.parameters():
+            p.grad = None
+    ys2 = [l(x2) for l in layers]
+    torch.autograd.backward(ys2, [torch.from_numpy(g).cuda() for g in gs_np])
+    for a, b in zip(fused["ys"], ys2):
+        assert torch.equal(a, b)
+    assert runners.rel_l2(fused["gin"].cpu().numpy(), x2.grad.cpu().numpy()) <= 1e-6
+    for i, (c, p, l) in enumerate(zip(cs, ps, layers)):
+        want = runners.run_oracle(c, params=p, io=(u_np, gs_np[i]), dtype=np.float32, nthreads=0)
+        got = {"y": fused["ys"][i].cpu().numpy(), "gin": None}
+        got.update({"g_" + k: v.cpu().numpy() for k, v in fused["grads"][i].items()})
+        want = {k: v for k, v in want.items() if k != "gin"}
+        _assert_close({k: v for k, v in got.items() if k != "gin"}, want, TOL, f"{c.name} fused B={B}")
+        for k, pp in l.named_parameters():      # and against the single-layer calls, to summation-order noise
+            assert runners.rel_l2(fused["grads"][i][k].cpu().numpy(), pp.grad.cpu().numpy()) <= 2e-6, (c.name, k)
+
+
+def test_cuda_multi_branch_falls_back_when_layers_cannot_share_a_launch():
+    """Different plane sizes / inference / a single layer: apply_to_same_input runs the layers one by one."""
+    import torch
+    from cnn_with_pde_b200.cifar10 import EnhancedDiffusionLayer, apply_to_same_input
+    torch.manual_seed(0)
+    a = EnhancedDiffusionLayer(32, 3, dt=0.001, num_steps=2).cuda()
+    b = EnhancedDiffusionLayer(32, 3, dt=0.002, num_steps=3).cuda()
+    x = torch.randn(5, 3, 32, 32, device="cuda")
+    with torch.no_grad():
+        ya, yb = apply_to_same_input(x, [a, b])
+        assert torch.equal(ya, a(x)) and torch.equal(yb, b(x))
+    (only,) = apply_to_same_input(x, [a])
+    assert torch.equal(only, a(x))
+    c16 = EnhancedDiffusionLayer(16, 3, dt=0.001, num_steps=2).cuda()
+    d16 = EnhancedDiffusionLayer(16, 3, dt=0.002, num_steps=2).cuda()
+    x16 = torch.randn(4, 3, 16, 16, device="cuda", requires_grad=True)
+    y1, y2 = apply_to_same_input(x16, [c16, d16])       # 16 x 16 planes: whole-line kernels, one call per layer
+    (y1.sum() + y2.sum()).backward()
+    assert x16.grad is not None and c16.alpha_base.grad is not None and d16.alpha_base.grad is not None

@@ -405,8 +405,19 @@ def run_b200(args):
         del x, y, yn, xn
         torch.cuda.empty_cache()
         try:
-            train = T.run(args.train_model, args.train_batch, steps=max(args.steps, 20), warmup=max(args.warmup, 5),
+            train = T.run(args.train_model, args.train_batch, steps=max(args.steps, 100), warmup=max(args.warmup, 10),
                           graph=True, quiet=True)
+            if world == 1 and args.train_model == "cifar10":
+                # the same step with the three PDE layers fused into one launch per pass (opt-in: slower, see
+                # classifiers.MultiScaleExtractor)
+                import cnn_with_pde_b200.classifiers as Cl
+                Cl.MultiScaleExtractor.fused_branches = True
+                try:
+                    fused = T.run(args.train_model, args.train_batch, steps=max(args.steps, 100), warmup=max(args.warmup, 10),
+                                  graph=True, quiet=True)
+                    train["fused_branches"] = {"ms_per_step": fused["ms_per_step"], "img_per_s": fused["img_per_s"]}
+                finally:
+                    Cl.MultiScaleExtractor.fused_branches = False
         except Exception as ex:   # the headline line survives a failure of the side measurement
             train = {"error": f"{type(ex).__name__}: {ex}"}
         x = u.clone().requires_grad_(True)

@@ -139,11 +139,17 @@ class MultiScaleExtractor(nn.Module):
         self.combine_weights = nn.Parameter(torch.ones(3) / 3)
 
     # The three branches read the same input and are independent until the combine (SURVEY section 8(f)
-    # rank 1).  fused_branches: the three PDE layers go through ONE launch per pass (blockIdx selects the
-    # layer; cifar10.apply_to_same_input), the attention gates follow on the current stream.
-    # concurrent_branches (used when fusing is off or not possible): the branches run on three streams
-    # (fork / join around the current stream; captured as parallel branches of a CUDA graph).
-    fused_branches = True
+    # rank 1).  Two ways to exploit that, both built and parity-tested:
+    #   concurrent_branches  each branch (PDE layer + its gate) on its own stream: fork / join around the
+    #                        current stream, captured as parallel branches of a CUDA graph; a branch's gate and
+    #                        its backward start as soon as that branch's PDE kernel is done;
+    #   fused_branches       the three PDE layers through ONE launch per pass (blocks dealt to the layers in
+    #                        proportion to their sweeps; cifar10.apply_to_same_input), gates on side streams.
+    # Measured on one B200, batch 512, CUDA graph: 1.15 - 1.24 ms per step with three
+    # concurrent launches, 1.26 ms fused -- one launch makes every gate wait for the slowest layer and the
+    # PDE backward wait for all three gates, which costs more than the four launches it saves.  So the
+    # streams are the default and the fused call is opt-in (set fused_branches = True).
+    fused_branches = False
     concurrent_branches = True
 
     def _side_streams(self, device):
@@ -158,7 +164,22 @@ class MultiScaleExtractor(nn.Module):
         if x.is_cuda and self.fused_branches and not serial and torch.is_grad_enabled():
             from .cifar10 import apply_to_same_input
             ys = apply_to_same_input(x, [pde for pde, _ in branches])
-            feats = [att(y) for (_, att), y in zip(branches, ys)]
+            if self.concurrent_branches:
+                # the gates (a dozen tiny kernels each, forward and backward) of branches 2 and 3 on side streams
+                cur = torch.cuda.current_stream(x.device)
+                sides = self._side_streams(x.device)
+                feats = [None, None, None]
+                for i, s in enumerate(sides, start=1):
+                    s.wait_stream(cur)
+                    ys[i].record_stream(s)
+                    with torch.cuda.stream(s):
+                        feats[i] = branches[i][1](ys[i])
+                feats[0] = branches[0][1](ys[0])
+                for i, s in enumerate(sides, start=1):
+                    cur.wait_stream(s)
+                    feats[i].record_stream(cur)
+            else:
+                feats = [att(y) for (_, att), y in zip(branches, ys)]
         elif x.is_cuda and self.concurrent_branches and not serial:
             cur = torch.cuda.current_stream(x.device)
             sides = self._side_streams(x.device)
@@ -312,7 +333,7 @@ class HybridPDEExtractor(nn.Module):
         self.combination_weights = nn.Parameter(torch.ones(4) / 4)
         self.feature_norm = PlaneBatchNorm2d(channels)   # nn.BatchNorm2d in the reference (cifar_2version.py:276)
 
-    fused_branches = True
+    fused_branches = False   # see MultiScaleExtractor
 
     def forward(self, x):
         serial = bool(os.environ.get("PDE_B200_SERIAL_BRANCHES"))

@@ -583,17 +583,27 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_kern
 
 // Several layers applied to the SAME input in one launch (the three PDE branches of cifar10's
 // MultiScaleExtractor, cifar10.py:272-274; the two of cifar_2version's HybridPDEExtractor,
-// cifar_2version.py:287-288): consecutive blocks take the same items of consecutive branches, so the
-// branches walk the input together and all but the first read of a plane come out of L2.
+// cifar_2version.py:287-288).  The resident blocks are dealt to the branches in proportion to their
+// work (sweeps per item): blocks blk_begin[b] .. blk_begin[b + 1] - 1 walk the items of branch b.
 struct MultiArgs {
     int n;
+    int blk_begin[PDE_MAX_BRANCHES + 1];
     Args a[PDE_MAX_BRANCHES];
 };
 
+__device__ __forceinline__ int multi_branch_of(const MultiArgs &m, int *bid, int *nblk) {
+    int b = m.n - 1;
+    while (b > 0 && (int)blockIdx.x < m.blk_begin[b]) --b;
+    *bid = (int)blockIdx.x - m.blk_begin[b];
+    *nblk = m.blk_begin[b + 1] - m.blk_begin[b];
+    return b;
+}
+
 template <int N, int P, int Q, bool MIX1>
 __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sfwd_multi_kernel(const __grid_constant__ MultiArgs m) {
-    const int b = blockIdx.x % m.n;
-    sfwd_body<N, P, Q, MIX1>(m.a[b], blockIdx.x / m.n, gridDim.x / m.n);
+    int bid, nblk;
+    const int b = multi_branch_of(m, &bid, &nblk);
+    sfwd_body<N, P, Q, MIX1>(m.a[b], bid, nblk);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1120,8 +1130,9 @@ __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_kern
 
 template <int N, int P, bool CHAN>
 __global__ void __launch_bounds__(max_threads<N, P>(), P >= 4 ? 2 : 1) sbwd_multi_kernel(const __grid_constant__ MultiArgs m) {
-    const int b = blockIdx.x % m.n;
-    sbwd_body<N, P, CHAN>(m.a[b], blockIdx.x / m.n, gridDim.x / m.n);
+    int bid, nblk;
+    const int b = multi_branch_of(m, &bid, &nblk);
+    sbwd_body<N, P, CHAN>(m.a[b], bid, nblk);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1416,6 +1427,37 @@ bool multi_compatible(int n, const pde_adi_desc *d) {
            bwd_multi_kernel_for(d[0].N, p.P, d[0].chan_op != 0) != nullptr;
 }
 
+// Deal `total` resident blocks to the branches in proportion to their work per item (sweeps, plus the
+// item's load / store), at most `nitems` each; fills m->blk_begin and returns the grid size.
+static int deal_blocks(int n, const pde_adi_desc *d, int total, int nitems, MultiArgs *m) {
+    double w[PDE_MAX_BRANCHES], wsum = 0.0;
+    for (int i = 0; i < n; ++i) {
+        w[i] = d[i].steps * sweeps_per_step(d[i]) + 3.0;
+        wsum += w[i];
+    }
+    int used = 0, nb[PDE_MAX_BRANCHES];
+    for (int i = 0; i < n; ++i) {
+        nb[i] = (int)(total * w[i] / wsum);
+        if (nb[i] > nitems) nb[i] = nitems;
+        if (nb[i] < 1) nb[i] = 1;
+        used += nb[i];
+    }
+    for (bool grew = true; grew && used < total;) {   // hand out what rounding and the caps left over, heaviest first
+        grew = false;
+        int best = -1;
+        for (int i = 0; i < n; ++i)
+            if (nb[i] < nitems && (best < 0 || w[i] / nb[i] > w[best] / nb[best])) best = i;
+        if (best >= 0) {
+            ++nb[best];
+            ++used;
+            grew = true;
+        }
+    }
+    m->blk_begin[0] = 0;
+    for (int i = 0; i < n; ++i) m->blk_begin[i + 1] = m->blk_begin[i] + nb[i];
+    return m->blk_begin[n];
+}
+
 static float *ck_images(void *ckpt, CkFlags **flags) {   // [CkFlags, 256 bytes][tile images]
     float *base = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ckpt) + 255u) & ~(uintptr_t)255u);
     *flags = reinterpret_cast<CkFlags *>(base);
@@ -1450,14 +1492,12 @@ int forward_multi(int n, const pde_adi_desc *d, const void *const *tables, const
         a.out = out[i];
         if (ckpt && ckpt[i]) a.ckpt = ck_images(ckpt[i], &a.ck_flags);
     }
-    int nblk = props.sm_count * per_sm / n;      // blocks per branch: the branches share the resident set
-    if (nblk > nitems) nblk = nitems;
-    if (nblk < 1) nblk = 1;
+    const int grid = deal_blocks(n, d, props.sm_count * per_sm, nitems, &m);   // the branches share the resident set
     if (debug_enabled())
         fprintf(stderr, "[pde_b200] split fwd multi plan: n=%d N=%d C=%d P=%d Q=%d threads=%d smem=%zu occ=%d grid=%d\n", n, d[0].N,
-                d[0].C, p.P, p.Qf, p.threads, smem, per_sm, n * nblk);
+                d[0].C, p.P, p.Qf, p.threads, smem, per_sm, grid);
     void *params[] = {&m};
-    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(n * nblk), dim3(p.threads), params, smem, st));
+    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(p.threads), params, smem, st));
     return cuda_last_error();
 }
 
@@ -1473,15 +1513,17 @@ int backward_multi(int n, const pde_adi_desc *d, const void *const *tables, cons
     if (!kern) return PDE_ERR_UNSUPPORTED;
     rc = plan_bwd_grid(d[0], p, &b, kern);
     if (rc) return rc;
-    int nblk = b.grid / n;                       // blocks per branch (b.grid = resident blocks, capped by the items)
-    if (nblk < 1) nblk = 1;
-    WsLayout w;
-    ws_layout(d[0], p, nblk, &w);
-    const size_t need = (w.scratch_floats + w.maps_floats + w.chan_floats + w.skip_floats) * sizeof(float) + 512;
+    DeviceProps props;
+    rc = query_props(&props);
+    if (rc) return rc;
     MultiArgs m{};
     m.n = n;
+    const int grid = deal_blocks(n, d, props.sm_count * b.occ, b.nitems, &m);
     FinishJob jobs[PDE_MAX_BRANCHES];
     for (int i = 0; i < n; ++i) {
+        WsLayout w;
+        ws_layout(d[i], p, m.blk_begin[i + 1] - m.blk_begin[i], &w);
+        const size_t need = (w.scratch_floats + w.maps_floats + w.chan_floats + w.skip_floats) * sizeof(float) + 512;
         if (!workspace || !workspace[i] || workspace_bytes_[i] < need || !ckpt || !ckpt[i]) return PDE_ERR_WORKSPACE;
         float *ws = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace[i]) + 255u) & ~(uintptr_t)255u);
         Args &a = m.a[i];
@@ -1503,7 +1545,7 @@ int backward_multi(int n, const pde_adi_desc *d, const void *const *tables, cons
                             g_ab[i], g_atc[i], g_bb[i], g_btc[i], g_chan ? g_chan[i] : nullptr, g_skip ? g_skip[i] : nullptr};
     }
     void *params[] = {&m};
-    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(n * nblk), dim3(p.threads), params, b.smem, st));
+    PDE_CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(p.threads), params, b.smem, st));
     rc = cuda_last_error();
     if (rc) return rc;
     launch_finish_multi(n, jobs, st);

@@ -117,8 +117,13 @@ def test_launcher_refuses_to_run_without_cuda():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", sorted(MODELS))
-def test_whole_model_matches_reference_fixture(name):
+@pytest.mark.parametrize("name", sorted(MODELS) + ["cifar10/fused"])
+def test_whole_model_matches_reference_fixture(name, monkeypatch):
+    if name.endswith("/fused"):
+        # the three PDE layers of MultiScaleExtractor through one launch per pass (pde_adi_multi_*)
+        import cnn_with_pde_b200.classifiers as C
+        monkeypatch.setattr(C.MultiScaleExtractor, "fused_branches", True)
+        name = name.split("/")[0]
     z = np.load(os.path.join(GOLDEN_DIR, f"model_{name}.npz"))
     model = ours(name)
     model.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd_")})

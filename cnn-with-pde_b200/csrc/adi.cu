@@ -49,16 +49,25 @@ struct Geo {
 // The block reduces the sweep's largest r and "some cell clamped" and writes its header entries;
 // nothing crosses blocks (the consumers fold them into the call-wide flags: header_flags).
 // ------------------------------------------------------------------------------------------
+constexpr int kPrepareThreads = 256;
+
 template <int N>
 __device__ __forceinline__ void prepare_body(const pde_adi_desc &d, const pde_adi_schedule &sch, const SlotMap &sm,
                                              const float *__restrict__ ab, const float *__restrict__ bb,
                                              const float *__restrict__ atc, const float *__restrict__ btc, char *tables,
                                              int want_split, const int s) {
-    constexpr int H = N / 2, HQ = (H + 3) / 4;
-    const int sps = sweeps_per_step(d), C = d.C;
+    // Three phases per sweep.  (1) every cell in parallel: raw coefficient -> clamp (-> mask) -> smoothing ->
+    // r = (k dt) / h^2; (2) one thread per line and direction: the pivot recurrences, the only serial part
+    // (top-down for the reference's one-sided elimination, bottom-up for the far half of the twisted one);
+    // (3) every cell in parallel: 1 / pivot, r / pivot and the table stores.  Cells are addressed in LINE
+    // order [c][line][i] (i along the sweep) in shared memory.
+    constexpr int H = N / 2, HQ = (H + 3) / 4, NN = N * N;
+    extern __shared__ __align__(16) float prep_smem[];
+    __shared__ float s_rmax[kPrepareThreads / 32];
+    const int sps = sweeps_per_step(d), C = d.C, cells = C * NN;
+    float *kap = prep_smem, *rr = kap + cells, *den = rr + cells, *den2 = den + cells;   // den2: bottom-up pivots
+    unsigned char *inside = reinterpret_cast<unsigned char *>(den2 + cells);
     const int tid = threadIdx.x;
-    const int line = tid % N, c = tid / N;
-    const bool live = c < C;
     const int axis = sweep_axis(s % sps);
     const float *base = axis ? bb : ab, *tc = axis ? btc : atc;
     const float tt = sch.t[s], dts = sch.dts[s], h2 = sch.h2[s];
@@ -67,102 +76,138 @@ __device__ __forceinline__ void prepare_body(const pde_adi_desc &d, const pde_ad
     float *f = reinterpret_cast<float *>(tables + kHeaderBytes);
     const size_t T = table_elems(d);
 
-    float rmax = 0.0f;
+    // ---- (1a) clamped coefficient, in line order.  The map is read in its own (row-major) order: coalesced.
     int any_clamped = 0;
-    if (live) {
-        // the line walks the map with stride 1 (x sweeps: a row of alpha) or N (y sweeps: a column of beta)
-        const size_t q0 = axis == 0 ? ((size_t)c * N + line) * N : (size_t)c * N * N + line;
-        const int qs = axis == 0 ? 1 : N;
-        // clamped coefficient of cell i (replicate padding beyond the ends) and "inside the clamp interval"
-        auto coef = [&](int i, bool *inside) {
-            i = i < 0 ? 0 : (i > N - 1 ? N - 1 : i);
-            const float raw = __fadd_rn(__ldg(base + q0 + (size_t)i * qs), __fmul_rn(__ldg(tc + q0 + (size_t)i * qs), tt));
-            bool m = raw >= d.cmin;
-            float k = raw < d.cmin ? d.cmin : raw;
-            if (d.has_max) {
-                m = m && raw <= d.cmax;
-                k = k > d.cmax ? d.cmax : k;
-            }
-            *inside = m;
-            return k;
-        };
-        // r_i from the (smoothed) coefficient: (k dt) / h^2, op for op mnist_test.py:83,135-149
-        auto rate = [&](float km, float k0, float kp) {
-            float ks = k0;
-            if (d.smooth) ks = __fadd_rn(__fadd_rn(__fmul_rn(km, third), __fmul_rn(k0, third)), __fmul_rn(kp, third));
-            return __fdiv_rn(__fmul_rn(ks, dts), h2);
-        };
-        auto diag = [&](int i, float r) {
-            return (i == 0 || i == N - 1) ? __fadd_rn(1.0f, r) : __fadd_rn(1.0f, __fmul_rn(2.0f, r));
-        };
-        float *tr = f, *tinv = f + T, *te = f + 2 * T, *tm = f + 3 * T;
-        const size_t TS = split::stab_floats_per_table(d);
-        float *sr = f + 4 * T, *sinv = sr + TS, *se = sr + 2 * TS, *smk = sr + 3 * TS;
-        const int R = split::mirror(line, N);
-        const size_t so = (((size_t)s * C + c) * HQ * N + R) * 8;   // + (k / 4) * N * 8 + half * 4 + k % 4
-
-        // ---- top-down elimination (mnist_test.py:165-185): c*_i = -r_i / den_i.  Serves the whole-line
-        // tables and the near half of the twisted ones (cells 0 .. H-1: the same values).
-        bool in_m, in_0, in_p;
-        float km = coef(-1, &in_m), k0 = coef(0, &in_0), kp;
-        float cst = 0.0f, cst_h = 0.0f;
-#pragma unroll 4
-        for (int i = 0; i < N; ++i) {
-            kp = coef(i + 1, &in_p);
-            const float r = rate(km, k0, kp);
-            rmax = fmaxf(rmax, fabsf(r));
-            any_clamped |= in_0 ? 0 : 1;
-            const float den = i == 0 ? __fadd_rn(diag(i, r), d.eps) : __fadd_rn(__fsub_rn(diag(i, r), __fmul_rn(-r, cst)), d.eps);
-            cst = __fdiv_rn(-r, den);
-            if (i == H - 1) cst_h = cst;
-            const float inv = __fdiv_rn(1.0f, den), e = __fdiv_rn(r, den), mk = in_0 ? 1.0f : 0.0f;
-            const size_t o = (((size_t)s * C + c) * (N / 4) + (i >> 2)) * N * 4 + (size_t)line * 4 + (i & 3);
-            tr[o] = r; tinv[o] = inv; te[o] = e; tm[o] = mk;
-            if (want_split && i < H) {
-                const size_t o2 = so + (size_t)(i >> 2) * N * 8 + (i & 3);
-                sr[o2] = r; sinv[o2] = inv; se[o2] = e; smk[o2] = mk;
-            }
-            km = k0; k0 = kp; in_0 = in_p;
+    for (int q = tid; q < cells; q += kPrepareThreads) {
+        const int c = q / NN, row = (q % NN) / N, col = q % N;
+        const float raw = __fadd_rn(__ldg(base + q), __fmul_rn(__ldg(tc + q), tt));
+        bool m = raw >= d.cmin;
+        float k = raw < d.cmin ? d.cmin : raw;
+        if (d.has_max) {
+            m = m && raw <= d.cmax;
+            k = k > d.cmax ? d.cmax : k;
         }
-        if (want_split) {
-            // ---- twisted pivots: cells N-1 .. H+1 are eliminated bottom-up, cell H closes both
-            float kq = coef(N, &in_m);           // the window now slides downwards: kq = cell i + 1
-            k0 = coef(N - 1, &in_0);
+        // x sweeps: line = row, i = col; y sweeps: line = col, i = row
+        const int lo = axis == 0 ? (c * N + row) * N + col : (c * N + col) * N + row;
+        kap[lo] = k;
+        inside[lo] = m ? 1 : 0;
+        any_clamped |= m ? 0 : 1;
+    }
+    __syncthreads();
+    // ---- (1b) r_i from the (smoothed) coefficient: (k dt) / h^2, op for op mnist_test.py:83,135-149
+    float rmax = 0.0f;
+    for (int q = tid; q < cells; q += kPrepareThreads) {
+        const int i = q % N;
+        float ks = kap[q];
+        if (d.smooth)
+            ks = __fadd_rn(__fadd_rn(__fmul_rn(kap[i > 0 ? q - 1 : q], third), __fmul_rn(kap[q], third)),
+                           __fmul_rn(kap[i < N - 1 ? q + 1 : q], third));
+        const float r = __fdiv_rn(__fmul_rn(ks, dts), h2);
+        rr[q] = r;
+        rmax = fmaxf(rmax, fabsf(r));
+    }
+    __syncthreads();
+    // ---- (2) pivots.  Thread (line, 0): top-down over the whole line (mnist_test.py:165-185, c*_i = -r_i / den_i);
+    // thread (line, 1): bottom-up over cells N-1 .. H+1 (twisted factorisation, adi_split.cu).
+    auto diag = [&](int i, float r) {
+        return (i == 0 || i == N - 1) ? __fadd_rn(1.0f, r) : __fadd_rn(1.0f, __fmul_rn(2.0f, r));
+    };
+    for (int job = tid; job < 2 * C * N; job += kPrepareThreads) {
+        const int dir = job / (C * N), lo = (job % (C * N)) * N;
+        if (dir == 0) {
+            float cst = 0.0f;
+#pragma unroll 4
+            for (int i = 0; i < N; ++i) {
+                const float r = rr[lo + i];
+                const float dn = i == 0 ? __fadd_rn(diag(i, r), d.eps) : __fadd_rn(__fsub_rn(diag(i, r), __fmul_rn(-r, cst)), d.eps);
+                cst = __fdiv_rn(-r, dn);
+                den[lo + i] = dn;
+            }
+        } else if (want_split) {
             float ast = 0.0f;
 #pragma unroll 4
-            for (int i = N - 1; i >= H; --i) {
-                km = coef(i - 1, &in_m);
-                const float r = rate(km, k0, kq);
-                float den;
-                if (i == N - 1) den = __fadd_rn(diag(i, r), d.eps);
-                else if (i > H) den = __fadd_rn(__fsub_rn(diag(i, r), __fmul_rn(-r, ast)), d.eps);
-                else den = __fadd_rn(__fsub_rn(__fsub_rn(diag(i, r), __fmul_rn(-r, cst_h)), __fmul_rn(-r, ast)), d.eps);
-                ast = __fdiv_rn(-r, den);
-                const int k = N - 1 - i;
-                const size_t o2 = so + (size_t)(k >> 2) * N * 8 + 4 + (k & 3);
-                sr[o2] = r; sinv[o2] = __fdiv_rn(1.0f, den); se[o2] = __fdiv_rn(r, den); smk[o2] = in_0 ? 1.0f : 0.0f;
-                kq = k0; k0 = km; in_0 = in_m;
+            for (int i = N - 1; i > H; --i) {
+                const float r = rr[lo + i];
+                const float dn = i == N - 1 ? __fadd_rn(diag(i, r), d.eps) : __fadd_rn(__fsub_rn(diag(i, r), __fmul_rn(-r, ast)), d.eps);
+                ast = __fdiv_rn(-r, dn);
+                den2[lo + i] = dn;
             }
-            for (int k = H; k < 4 * HQ; ++k)     // padding of the last float4 of both halves
-                for (int h = 0; h < 2; ++h) {
-                    const size_t o2 = so + (size_t)(k >> 2) * N * 8 + h * 4 + (k & 3);
-                    sr[o2] = 0.0f; sinv[o2] = 0.0f; se[o2] = 0.0f; smk[o2] = 0.0f;
+            den2[lo + H] = ast;   // c* of cell H + 1 seen from below, for the closing cell
+        }
+    }
+    __syncthreads();
+    // ---- (3) tables.  Whole-line layout [s][c][i/4][line][i%4]: one float4 per (line, i/4).
+    {
+        float *tr = f, *tinv = f + T, *te = f + 2 * T, *tm = f + 3 * T;
+        for (int q4 = tid; q4 < cells / 4; q4 += kPrepareThreads) {
+            const int c = q4 / (NN / 4), line = (q4 % (NN / 4)) % N, iq = (q4 % (NN / 4)) / N;   // consecutive threads: consecutive lines
+            const int lo = (c * N + line) * N + 4 * iq;
+            float4 vr, vi, ve, vm;
+            float *pr = &vr.x, *pi = &vi.x, *pe = &ve.x, *pm = &vm.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float r = rr[lo + k], dn = den[lo + k];
+                pr[k] = r;
+                pi[k] = __fdiv_rn(1.0f, dn);
+                pe[k] = __fdiv_rn(r, dn);
+                pm[k] = inside[lo + k] ? 1.0f : 0.0f;
+            }
+            const size_t o = (((size_t)s * C + c) * (N / 4) + iq) * N * 4 + (size_t)line * 4;
+            *reinterpret_cast<float4 *>(tr + o) = vr;
+            *reinterpret_cast<float4 *>(tinv + o) = vi;
+            *reinterpret_cast<float4 *>(te + o) = ve;
+            *reinterpret_cast<float4 *>(tm + o) = vm;
+        }
+    }
+    if (want_split) {
+        // half-line layout [s][c][k/4][mirrored line][half][k%4] (k = cell counted from the half's plane edge):
+        // near half = the top-down pivots of cells 0 .. H-1, far half = the bottom-up ones of N-1 .. H+1 and the
+        // closing cell H: den_H = diag - (-r_H) c*_{H-1} - (-r_H) a*_{H+1} + eps
+        const size_t TS = split::stab_floats_per_table(d);
+        float *sr = f + 4 * T, *sinv = sr + TS, *se = sr + 2 * TS, *smk = sr + 3 * TS;
+        for (int q4 = tid; q4 < C * N * 2 * HQ; q4 += kPrepareThreads) {
+            const int h = q4 % 2, R = (q4 / 2) % N, kq = (q4 / (2 * N)) % HQ, c = q4 / (2 * N * HQ);
+            const int line = split::mirror(R, N);   // mirror is an involution: table row R holds line mirror(R)
+            const int lo = (c * N + line) * N;
+            float4 vr, vi, ve, vm;
+            float *pr = &vr.x, *pi = &vi.x, *pe = &ve.x, *pm = &vm.x;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = 4 * kq + kk;
+                if (k < H) {
+                    const int i = h ? N - 1 - k : k;
+                    const float r = rr[lo + i];
+                    float dn;
+                    if (!h) dn = den[lo + i];
+                    else if (i > H) dn = den2[lo + i];
+                    else {
+                        const float cst_h = __fdiv_rn(-rr[lo + H - 1], den[lo + H - 1]);
+                        dn = __fadd_rn(__fsub_rn(__fsub_rn(diag(H, r), __fmul_rn(-r, cst_h)), __fmul_rn(-r, den2[lo + H])), d.eps);
+                    }
+                    pr[kk] = r;
+                    pi[kk] = __fdiv_rn(1.0f, dn);
+                    pe[kk] = __fdiv_rn(r, dn);
+                    pm[kk] = inside[lo + i] ? 1.0f : 0.0f;
+                } else {
+                    pr[kk] = 0.0f; pi[kk] = 0.0f; pe[kk] = 0.0f; pm[kk] = 0.0f;
                 }
+            }
+            const size_t o = ((((size_t)s * C + c) * HQ + kq) * N + R) * 8 + h * 4;
+            *reinterpret_cast<float4 *>(sr + o) = vr;
+            *reinterpret_cast<float4 *>(sinv + o) = vi;
+            *reinterpret_cast<float4 *>(se + o) = ve;
+            *reinterpret_cast<float4 *>(smk + o) = vm;
         }
     }
     // the sweep's header entries
-    __shared__ float s_rmax[4];
     const int any = __syncthreads_or(any_clamped);
-    rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, 16));
-    rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, 8));
-    rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, 4));
-    rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, 2));
-    rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, 1));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(kFullMask, rmax, o));
     if ((tid & 31) == 0) s_rmax[tid >> 5] = rmax;
     __syncthreads();
     if (tid == 0) {
         float m = 0.0f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_rmax[w]);
+        for (int w = 0; w < kPrepareThreads / 32; ++w) m = fmaxf(m, s_rmax[w]);
         hdr->rmax_bits[s] = __float_as_uint(m);
         hdr->clamped[s] = any ? 1 : 0;
         hdr->scale[s] = __fdiv_rn(dts, h2);
@@ -171,11 +216,11 @@ __device__ __forceinline__ void prepare_body(const pde_adi_desc &d, const pde_ad
         if (s == 0) hdr->nslots = sm.nslots;
     }
     if (s == 0)
-        for (int u = tid; u < sm.nslots; u += blockDim.x) hdr->rep[u] = sm.rep[u];
+        for (int u = tid; u < sm.nslots; u += kPrepareThreads) hdr->rep[u] = sm.rep[u];
 }
 
 template <int N>
-__global__ void __launch_bounds__(128) prepare_kernel(const __grid_constant__ pde_adi_desc d,
+__global__ void __launch_bounds__(kPrepareThreads) prepare_kernel(const __grid_constant__ pde_adi_desc d,
                                                       const __grid_constant__ pde_adi_schedule sch,
                                                       const __grid_constant__ SlotMap sm, const float *__restrict__ ab,
                                                       const float *__restrict__ bb, const float *__restrict__ atc,
@@ -197,7 +242,7 @@ struct PrepareMulti {
     PrepareJob job[PDE_MAX_BRANCHES];
 };
 template <int N>
-__global__ void __launch_bounds__(128) prepare_multi_kernel(const __grid_constant__ PrepareMulti m) {
+__global__ void __launch_bounds__(kPrepareThreads) prepare_multi_kernel(const __grid_constant__ PrepareMulti m) {
     int j = m.n - 1;
     while (j > 0 && (int)blockIdx.x < m.job[j].s_begin) --j;
     const PrepareJob &job = m.job[j];
@@ -1029,17 +1074,28 @@ __device__ __forceinline__ void finish_body(const pde_adi_desc &d, int nwarps_to
         dst[(size_t)c * plane + cell] = (float)sum;
     }
     if (bid == 0) {
-        if (g_chan && threadIdx.x < C * C) {
-            const int cc = threadIdx.x / C, dd = threadIdx.x % C;
+        // channel-matrix and skip-weight partials: a warp per output, lanes stride over the partial sets
+        // (hundreds to thousands of them), fixed shuffle tree: deterministic, and not one serial thread
+        const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+        constexpr int kWarps = kFinishCells * kFinishSlices / 32;
+        if (g_chan)
+            for (int q = warp; q < C * C; q += kWarps) {
+                const int cc = q / C, dd = q % C;
+                double a = 0.0;
+                for (int w = cc + C * ln; w < nsets_small; w += C * 32) a += (double)part_chan[(size_t)w * PDE_MAX_CHANNELS + dd];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFullMask, a, o);
+                if (ln == 0) g_chan[cc * C + dd] = (float)a;
+            }
+        if (g_skip && warp == kWarps - 1) {
             double a = 0.0;
-            for (int w = cc; w < nsets_small; w += C) a += (double)part_chan[(size_t)w * PDE_MAX_CHANNELS + dd];
-            g_chan[cc * C + dd] = (float)a;
-        }
-        if (g_skip && threadIdx.x == 32) {
-            double a = 0.0;
-            for (int w = 0; w < nsets_small; ++w) a += (double)part_skip[w];
-            const double sg = 1.0 / (1.0 + exp(-(double)skipw[0]));
-            g_skip[0] = (float)(a * sg * (1.0 - sg));
+            for (int w = ln; w < nsets_small; w += 32) a += (double)part_skip[w];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFullMask, a, o);
+            if (ln == 0) {
+                const double sg = 1.0 / (1.0 + exp(-(double)skipw[0]));
+                g_skip[0] = (float)(a * sg * (1.0 - sg));
+            }
         }
     }
 }
@@ -1256,13 +1312,18 @@ static void make_slot_map(const pde_adi_desc &d, const pde_adi_schedule &sch, Sl
     m->nslots = nslots;
 }
 
+// kap, r, top-down pivots, bottom-up pivots (floats) + the clamp mask (bytes), all C * N * N cells of a sweep
+static size_t prepare_smem_bytes(int C, int N) { return (size_t)C * N * N * (4 * sizeof(float) + 1) + 16; }
+
 template <int N>
 static int launch_prepare(const pde_adi_desc &d, const pde_adi_schedule &sch, const SlotMap &sm, const float *ab,
                           const float *bb, const float *atc, const float *btc, char *tables, int want_split,
                           cudaStream_t st) {
     const int S = d.steps * sweeps_per_step(d);
-    const int threads = ((d.C * N + 31) / 32) * 32;
-    prepare_kernel<N><<<S, threads, 0, st>>>(d, sch, sm, ab, bb, atc, btc, tables, want_split);
+    const size_t smem = prepare_smem_bytes(d.C, N);
+    int rc = kernel_info(reinterpret_cast<const void *>(prepare_kernel<N>), smem, nullptr);
+    if (rc) return rc;
+    prepare_kernel<N><<<S, kPrepareThreads, smem, st>>>(d, sch, sm, ab, bb, atc, btc, tables, want_split);
     return cuda_last_error();
 }
 
@@ -1327,10 +1388,18 @@ extern "C" int pde_adi_multi_prepare(int n, const pde_adi_desc *d, const pde_adi
         blocks += S;
     }
     if (blocks == 0) return PDE_OK;
-    const int threads = ((d[0].C * d[0].N + 31) / 32) * 32;
-    if (d[0].N == 28) prepare_multi_kernel<28><<<blocks, threads, 0, st>>>(m);
-    else if (d[0].N == 32) prepare_multi_kernel<32><<<blocks, threads, 0, st>>>(m);
-    else return PDE_ERR_UNSUPPORTED;
+    const size_t smem = prepare_smem_bytes(d[0].C, d[0].N);
+    if (d[0].N == 28) {
+        rc = kernel_info(reinterpret_cast<const void *>(prepare_multi_kernel<28>), smem, nullptr);
+        if (rc) return rc;
+        prepare_multi_kernel<28><<<blocks, kPrepareThreads, smem, st>>>(m);
+    } else if (d[0].N == 32) {
+        rc = kernel_info(reinterpret_cast<const void *>(prepare_multi_kernel<32>), smem, nullptr);
+        if (rc) return rc;
+        prepare_multi_kernel<32><<<blocks, kPrepareThreads, smem, st>>>(m);
+    } else {
+        return PDE_ERR_UNSUPPORTED;
+    }
     return cuda_last_error();
 }
 

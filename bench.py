@@ -393,7 +393,24 @@ def run_b200(args):
     torch.cuda.empty_cache()   # the big-batch buffers of the sections above go back to the driver first
     for _ in range(5):
         small()
-    small_ms = time_phase(small, 50)
+    small_ms = time_phase(small, 200)
+    # the same call replayed from a CUDA graph (how the launcher trains): the kernels without the host side
+    small_graph_ms = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                small()
+            side.synchronize()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg, stream=side):
+                small()
+        torch.cuda.current_stream().wait_stream(side)
+        small_graph_ms = time_phase(cg.replay, 200)
+        del cg
+    except Exception:
+        pass
 
     # ------------------------------------------- whole-model training step (BASELINE metric, part ii)
     # cifar10.CIFAR10PDENoConv (BASELINE configs[2]: 3x32x32, batch 512 per GPU), three PDE layers +
@@ -518,6 +535,9 @@ def run_b200(args):
             "fwd_inference_ms": round(fwd_eval_ms, 4),
             "bwd_no_grad_input_ms": round(bwd_nogin_ms, 4),
             "script_batch_latency_us": round(small_ms * 1e3, 1),
+            "script_batch_latency_note": f"forward+backward at the script's batch ({script_b}) through the nn.Module, eager: bound by the "
+                                         "host (autograd engine + Python + launches; a trivial custom Function costs 55 us on this box)",
+            "script_batch_graph_us": round(small_graph_ms * 1e3, 1) if small_graph_ms else None,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "device": info,

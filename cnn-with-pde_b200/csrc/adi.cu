@@ -1129,7 +1129,7 @@ static int validate(const pde_adi_desc *d) {
     if (d->steps * sweeps_per_step(*d) > PDE_MAX_SWEEPS) return PDE_ERR_UNSUPPORTED;
     if (d->C > PDE_MAX_CHANNELS) return PDE_ERR_UNSUPPORTED;
     switch (d->N) {
-        case 8: case 12: case 16: case 28: case 32: break;
+        case 8: case 12: case 16: case 20: case 24: case 28: case 32: break;
         default: return PDE_ERR_UNSUPPORTED;
     }
     return PDE_OK;
@@ -1156,6 +1156,8 @@ static const void *bwd_kernel_for(int N, bool chan) {
         case 8: return bwd_kernel_ptr<8>(chan);
         case 12: return bwd_kernel_ptr<12>(chan);
         case 16: return bwd_kernel_ptr<16>(chan);
+        case 20: return bwd_kernel_ptr<20>(chan);
+        case 24: return bwd_kernel_ptr<24>(chan);
         case 28: return bwd_kernel_ptr<28>(chan);
         case 32: return bwd_kernel_ptr<32>(chan);
         default: return nullptr;
@@ -1235,6 +1237,8 @@ static int launch_bwd(const Args &a, const BwdPlan &p, cudaStream_t st) {
         case 8: rc = CALL<8>; break;                 \
         case 12: rc = CALL<12>; break;               \
         case 16: rc = CALL<16>; break;               \
+        case 20: rc = CALL<20>; break;               \
+        case 24: rc = CALL<24>; break;               \
         case 28: rc = CALL<28>; break;               \
         case 32: rc = CALL<32>; break;               \
         default: rc = PDE_ERR_UNSUPPORTED;           \
@@ -1345,6 +1349,8 @@ extern "C" int pde_adi_prepare(const pde_adi_desc *d, const pde_adi_schedule *sc
         case 8: rc = launch_prepare<8>(*d, *sched, sm, ab, bb, atc, btc, tb, 0, st); break;
         case 12: rc = launch_prepare<12>(*d, *sched, sm, ab, bb, atc, btc, tb, 0, st); break;
         case 16: rc = launch_prepare<16>(*d, *sched, sm, ab, bb, atc, btc, tb, 0, st); break;
+        case 20: rc = launch_prepare<20>(*d, *sched, sm, ab, bb, atc, btc, tb, 0, st); break;
+        case 24: rc = launch_prepare<24>(*d, *sched, sm, ab, bb, atc, btc, tb, 0, st); break;
         case 28: rc = launch_prepare<28>(*d, *sched, sm, ab, bb, atc, btc, tb, want_split, st); break;
         case 32: rc = launch_prepare<32>(*d, *sched, sm, ab, bb, atc, btc, tb, want_split, st); break;
         default: rc = PDE_ERR_UNSUPPORTED;
@@ -1493,6 +1499,8 @@ extern "C" int pde_adi_forward_train(const pde_adi_desc *d, const void *tables, 
         case 8: rc = launch_fwd<8>(a, NP, props.sm_count, warps * 32, smem, st); break;
         case 12: rc = launch_fwd<12>(a, NP, props.sm_count, warps * 32, smem, st); break;
         case 16: rc = launch_fwd<16>(a, NP, props.sm_count, warps * 32, smem, st); break;
+        case 20: rc = launch_fwd<20>(a, NP, props.sm_count, warps * 32, smem, st); break;
+        case 24: rc = launch_fwd<24>(a, NP, props.sm_count, warps * 32, smem, st); break;
         case 28: rc = launch_fwd<28>(a, NP, props.sm_count, warps * 32, smem, st); break;
         case 32: rc = launch_fwd<32>(a, NP, props.sm_count, warps * 32, smem, st); break;
         default: rc = PDE_ERR_UNSUPPORTED;

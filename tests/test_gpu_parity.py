@@ -103,6 +103,21 @@ def test_cuda_emotion_plane_sizes(ctor):
                       {k: v for k, v in want.items() if k != "gin"}, TOL, c.name + " (no grad_input)")
 
 
+@pytest.mark.parametrize("size", [8, 12, 16, 20, 24])
+def test_cuda_other_plane_sizes(size):
+    """The reference classes take any `size`; the whole-line kernels are built for every multiple of 4 up to
+    32 (28 and 32 are also served by the half-line kernels).  One, three and four channels, odd batches."""
+    todo = [K.case(f"size{size}_mnist", "mnist", B=5, size=size, num_steps=3, dt=0.05, dx=0.7, dy=1.3),
+            K.case(f"size{size}_svhn", "svhn", B=3, size=size, channels=3, num_steps=2),
+            K.case(f"size{size}_cifar10_c4", "cifar10", B=3, size=size, channels=4, dt=0.01, num_steps=2, dx=1.0, dy=1.5),
+            K.case(f"size{size}_cifar2_c2", "cifar2", B=7, size=size, channels=2, dt=0.02, num_steps=3)]
+    for c in todo:
+        params, io = K.make_params(c), K.make_io(c)
+        got = runners.run_cuda(c, params=params, io=io)
+        want = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+        _assert_close(got, want, TOL, c.name)
+
+
 def test_cuda_exact_mode_for_large_coefficients():
     """dt large enough that rebuilding sweep inputs would amplify rounding noise: the kernel must
     switch to per-sweep checkpoints on its own (DESIGN.md 'reverse reconstruction')."""

@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_fwd_tiled(const EmoArgs a
     constexpr int CW = Tile<N>::CW, RH = Tile<N>::RH;
     __shared__ __align__(16) TileShared sh;
     tile_coefficients(a, sh, N);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, sub = lane & 15;
+    const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
+    // broadcast: tells the compiler the warp index (and every loop bound made of it) is warp-uniform, so the
+    // shuffles inside the plane loop need no WARPSYNC.COLLECTIVE / ENDCOLLECTIVE wrappers (4 extra instructions each)
+    const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);
     const int r0 = half * RH, j0 = sub * CW;
     float b[CW];
 #pragma unroll
@@ -172,7 +175,10 @@ __global__ void __launch_bounds__(kTileWarps * 32) emo_bwd_tiled(const EmoArgs a
     constexpr int HROW = CW * 32;               // floats per history row
     __shared__ __align__(16) TileShared sh;
     tile_coefficients(a, sh, N);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, sub = lane & 15;
+    const int lane = threadIdx.x & 31, half = lane >> 4, sub = lane & 15;
+    // broadcast: tells the compiler the warp index (and every loop bound made of it) is warp-uniform, so the
+    // shuffles inside the plane loop need no WARPSYNC.COLLECTIVE / ENDCOLLECTIVE wrappers (4 extra instructions each)
+    const int warp = __shfl_sync(kFullMask, (int)(threadIdx.x >> 5), 0);
     const int r0 = half * RH, j0 = sub * CW;
     const int Nt = a.d.Nt, S1 = (Nt + 1) / 2;   // states per history segment
     float b[CW], bm[CW], bp[CW];

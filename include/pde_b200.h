@@ -110,7 +110,7 @@ int pde_adi_forward(const pde_adi_desc *d, const void *tables, const float *u,
  * that is the state at the end of every step ("checkpoints": pde_adi_checkpoint_bytes(d) bytes,
  * 256-byte aligned, opaque layout), so that the backward kernel does not recompute the forward
  * trajectory.  pde_adi_checkpoint_bytes returns 0 when the configuration is served by kernels
- * that rebuild the trajectory on-chip (small batches, plane edges other than 28 / 32); ckpt may
+ * that rebuild the trajectory on-chip (plane edges other than 28 / 32, four channels); ckpt may
  * then be NULL.  pde_adi_backward (no ckpt) stays valid for every configuration: it makes the
  * checkpoints itself inside its (then batch-sized) workspace.  pde_adi_backward_saved needs
  * pde_adi_backward_saved_workspace_bytes(d) bytes of workspace when ckpt != NULL and

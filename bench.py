@@ -215,7 +215,8 @@ def run_b200(args):
     def step(x):
         for p in params:
             p.grad = None
-        y = layer(x)
+        x.grad = None      # as a training loop's zero_grad(set_to_none=True): grad_input is handed over, not
+        y = layer(x)       # added to last step's by a separate torch kernel (2.5 GB of traffic at this batch)
         y.backward(g)
         if world > 1:
             allreduce_coefficient_grads(params)   # the path's only exchange: one flat NCCL all-reduce
@@ -387,6 +388,7 @@ def run_b200(args):
     def small():
         for p in params:
             p.grad = None
+        xs.grad = None
         layer(xs).backward(gs)
 
     torch.cuda.synchronize()

@@ -148,6 +148,21 @@ def test_cuda_large_batch_properties():
     assert runners.rel_l2(y2.cpu().numpy(), 2.5 * y.detach().cpu().numpy()) <= 1e-6
 
 
+def test_cuda_layers_are_once_differentiable():
+    """The backward passes call raw-pointer kernels: asking autograd for a graph through them
+    (create_graph=True: gradient penalties, higher-order gradients) must raise, not return constants."""
+    import torch
+    for c in (K.case("once_fashion", "fashion", B=2), K.case("once_emotion", "emotion", B=2),
+              K.case("once_tiny", "tiny", B=2, **K.SCRIPT_INSTANCES["tiny"])):
+        layer = runners.make_cuda_layer(c)
+        x = torch.randn(c.B, *c.shape, device="cuda", requires_grad=True)
+        y = layer(x)
+        with pytest.raises(RuntimeError, match="once differentiable"):
+            torch.autograd.grad(y.sum(), x, create_graph=True)
+        (g,) = torch.autograd.grad(layer(x).sum(), x)      # the plain first derivative is fine
+        assert torch.isfinite(g).all()
+
+
 def test_cuda_rejects_cpu_tensors_and_bad_shapes():
     import torch
     from cnn_with_pde_b200.mnist_test import DiffusionLayer

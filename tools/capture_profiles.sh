@@ -8,7 +8,7 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/${R}_bench.json 2> gpurun_out/
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_fashion_bench.csv \
     python bench.py --steps 2 --warmup 1 --inner 1 --cpu-seconds 1 --all-layers 0 --train 0 > gpurun_out/ncu_bench.log 2>&1
 python train.py --model cifar10 --batch 512 --steps 50 --warmup 10 --graph > gpurun_out/plain_train.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2500 -c 700 --csv --log-file gpurun_out/${R}_launches_train_cifar10.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 600 -c 900 --csv --log-file gpurun_out/${R}_launches_train_cifar10.csv \
     python train.py --model cifar10 --batch 512 --steps 6 --warmup 2 > gpurun_out/ncu_train.log 2>&1
 for spec in "fashion 262144 sfwd_kernel|sbwd_kernel" "cifar10_pde1 65536 sfwd_kernel|sbwd_kernel" "emotion 98304 emo_fwd_tiled|emo_bwd_tiled" "tiny 16384 tiny_fwd_kernel|tiny_bwd_kernel" "mnist 262144 sfwd_kernel|sbwd_kernel"; do
   set -- $spec

@@ -17,6 +17,7 @@ MAX_SWEEPS = 192
 MAX_CHANNELS = 4
 MAX_BRANCHES = 4
 ABI_VERSION = 3
+ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE = -1, -2, -3   # include/pde_b200.h
 
 # pde_adi_desc.tuning / pde_emo_desc.tuning (include/pde_b200.h)
 TUNE_IMPL_HALF_LINE = 1

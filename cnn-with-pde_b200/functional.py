@@ -17,6 +17,7 @@ import contextlib
 import ctypes
 import functools
 import os
+import weakref
 
 from ctypes import byref
 from dataclasses import dataclass
@@ -163,21 +164,30 @@ def _adi_plan(cfg: AdiConfig, B: int, tuning: int, device_index: int) -> _AdiPla
     return _AdiPlan(cfg, B, tuning)
 
 
-# coefficient tables of inference calls, reused while the parameters have not changed:
-# (plan, data_ptr and version of the four maps) -> tables.  Never consulted under autograd or
-# during CUDA-graph capture (a captured graph must contain its own prepare launch).
+# Coefficient tables of inference calls, reused while the parameters have not changed.  An entry is valid
+# only for the very tensor objects it was built from (weak references: an address reused by another tensor
+# after the original died must not hit) at the versions it saw.  Never consulted under autograd or during
+# CUDA-graph capture (a captured graph must contain its own prepare launch).
 _TABLE_CACHE_SLOTS = 8
 _table_cache: "dict" = {}
 
 
-def _cached_tables(key):
-    return _table_cache.get(key)
+def _cached_tables(plan, params):
+    key = (id(plan),) + tuple(id(p) for p in params)
+    hit = _table_cache.get(key)
+    if hit is None:
+        return key, None
+    tables, refs, versions = hit
+    if all(r() is p for r, p in zip(refs, params)) and versions == tuple(p._version for p in params):
+        return key, tables
+    del _table_cache[key]
+    return key, None
 
 
-def _remember_tables(key, tables):
+def _remember_tables(key, params, tables):
     if len(_table_cache) >= _TABLE_CACHE_SLOTS:
         _table_cache.pop(next(iter(_table_cache)))
-    _table_cache[key] = tables
+    _table_cache[key] = (tables, tuple(weakref.ref(p) for p in params), tuple(p._version for p in params))
 
 
 class _AdiFunction(torch.autograd.Function):
@@ -192,22 +202,22 @@ class _AdiFunction(torch.autograd.Function):
         chan_c = None if chan is None else _contig(chan.detach())
         skip_c = None if skipw is None else _contig(skipw.detach())
         dev = u.device
-        plan = _adi_plan(cfg, u.shape[0], env_tuning(), dev.index if dev.index is not None else torch.cuda.current_device())
         # needs_input_grad ignores torch.no_grad() and grad mode is always off inside forward(): the
         # caller passes the mode it saw
         training = grad_mode and any(ctx.needs_input_grad)
         with _guard(dev):
+            # (the plan asks the library about the CURRENT device: built under the guard)
+            plan = _adi_plan(cfg, u.shape[0], env_tuning(), dev.index if dev.index is not None else torch.cuda.current_device())
             st = _stream(dev)
             tables, key = None, None
             if not training and not torch.cuda.is_current_stream_capturing():
-                key = (plan, tuple((p.data_ptr(), p._version) for p in (alpha_base, beta_base, alpha_tc, beta_tc)))
-                tables = _cached_tables(key)
+                key, tables = _cached_tables(plan, (alpha_base, beta_base, alpha_tc, beta_tc))
             if tables is None:
                 tables = _bytes(plan.tables_bytes, dev)
                 _cabi.check(L.pde_adi_prepare(plan.dref, plan.sref, *[p.data_ptr() for p in maps], tables.data_ptr(), st),
                             "pde_adi_prepare")
                 if key is not None:
-                    _remember_tables(key, tables)
+                    _remember_tables(key, (alpha_base, beta_base, alpha_tc, beta_tc), tables)
             out = torch.empty_like(u)
             # under autograd the forward kernel also writes the state at the end of every step for
             # the backward kernel (0 bytes when the configuration is served by the kernels that
@@ -279,9 +289,12 @@ class _AdiMultiPlan:
         self.n = len(cfgs)
         self.descs = (_cabi.AdiDesc * self.n)(*[p.desc for p in self.plans])
         self.scheds = (_cabi.AdiSchedule * self.n)(*[p.sched for p in self.plans])
-        c0 = cfgs[0]
-        self.ok = (2 <= self.n <= _cabi.MAX_BRANCHES and all(p.ckpt_bytes > 0 for p in self.plans) and
-                   all((c.N, c.C, c.chan_op, c.skip) == (c0.N, c0.C, c0.chan_op, c0.skip) for c in cfgs))
+        # the library decides whether the layers can share a launch: with compatible descriptors and no
+        # buffers it answers "invalid argument", with incompatible ones "unsupported"
+        self.ok = False
+        if 2 <= self.n <= _cabi.MAX_BRANCHES and B > 0 and all(p.ckpt_bytes > 0 for p in self.plans):
+            rc = _cabi.lib().pde_adi_multi_prepare(self.n, ctypes.addressof(self.descs), None, None, None, None, None, None, None)
+            self.ok = rc == _cabi.ERR_INVALID
 
 
 @functools.lru_cache(maxsize=64)
@@ -302,7 +315,8 @@ class _AdiMultiFunction(torch.autograd.Function):
         u = _contig(u)
         per = [flat[6 * i:6 * i + 6] for i in range(n)]
         dev = u.device
-        mp = _adi_multi_plan(cfgs, u.shape[0], env_tuning(), dev.index if dev.index is not None else torch.cuda.current_device())
+        with _guard(dev):
+            mp = _adi_multi_plan(cfgs, u.shape[0], env_tuning(), dev.index if dev.index is not None else torch.cuda.current_device())
         maps = [[_contig(p) for p in br[:4]] for br in per]
         chans = [None if br[4] is None else _contig(br[4].detach()) for br in per]
         skips = [None if br[5] is None else _contig(br[5].detach()) for br in per]
@@ -386,7 +400,8 @@ def adi_multi_layer(u, branches):
     fused = u.is_cuda and torch.is_grad_enabled() and any(t is not None and t.requires_grad for b in branches for t in b[:6])
     if fused:
         dev = u.device
-        mp = _adi_multi_plan(cfgs, u.shape[0], env_tuning(), dev.index if dev.index is not None else torch.cuda.current_device())
+        with _guard(dev):
+            mp = _adi_multi_plan(cfgs, u.shape[0], env_tuning(), dev.index if dev.index is not None else torch.cuda.current_device())
         fused = mp.ok and u.shape[0] > 0
     if not fused:
         return tuple(adi_layer(u, *b[:6], b[6]) for b in branches)

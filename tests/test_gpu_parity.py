@@ -163,6 +163,40 @@ def test_cuda_layers_are_once_differentiable():
         assert torch.isfinite(g).all()
 
 
+def test_cuda_inference_table_cache_is_safe():
+    """Under no_grad the coefficient tables are reused while the parameters stand.  They must be rebuilt when
+    a parameter is updated in place (optimizer step, load_state_dict), and a new layer whose parameters land
+    on the addresses of a dead one must not inherit its tables."""
+    import gc
+    import torch
+    c = K.case("cache_fashion", "fashion", B=33)
+    u = torch.from_numpy(K.make_io(c)[0]).cuda()
+
+    def reference_output(layer):   # the grad-mode path never consults the cache
+        return layer(u.clone().requires_grad_(True)).detach()
+
+    layer = runners.make_cuda_layer(c, K.make_params(c))
+    with torch.no_grad():
+        y1, y1b = layer(u), layer(u)                      # second call: cached tables
+    assert torch.equal(y1, y1b) and torch.equal(y1, reference_output(layer))
+    with torch.no_grad():
+        layer.alpha_base.mul_(1.5)                        # in-place update: version bump
+        y2 = layer(u)
+    assert not torch.equal(y2, y1) and torch.equal(y2, reference_output(layer))
+    with torch.no_grad():
+        layer.load_state_dict({k: v * 0.5 for k, v in layer.state_dict().items()})
+        y3 = layer(u)
+    assert torch.equal(y3, reference_output(layer))
+    for seed in range(4):                                 # dead layers' addresses get reused by fresh ones
+        del layer
+        gc.collect()
+        c2 = K.case("cache_fashion", "fashion", B=33, seed=100 + seed)
+        layer = runners.make_cuda_layer(c2, K.make_params(c2))
+        with torch.no_grad():
+            y = layer(u)
+        assert torch.equal(y, reference_output(layer)), seed
+
+
 def test_cuda_rejects_cpu_tensors_and_bad_shapes():
     import torch
     from cnn_with_pde_b200.mnist_test import DiffusionLayer

@@ -17,12 +17,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def main():
     rep, kname = sys.argv[1], sys.argv[2]
-    top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+    top = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 30
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "cnn-with-pde_b200", "libpde_b200.so")], cwd=tmp,
                    capture_output=True)
-    dis = subprocess.run(["nvdisasm", "--print-line-info", "-c", os.path.join(tmp, "adi.sm_100a.cubin")],
-                         capture_output=True, text=True).stdout
+    dis = ""
+    for cubin in sorted(os.listdir(tmp)):      # one cubin per .cu file: take the one that holds the kernel
+        if cubin.endswith(".cubin"):
+            d = subprocess.run(["nvdisasm", "--print-line-info", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+            if kname in d:
+                dis = d
+                break
     # walk the disassembly: track current function and current line
     lines_of = []          # per instruction (in order) of the selected function: line number
     cur_fn, cur_line, in_fn = None, None, False
@@ -38,7 +43,7 @@ def main():
             continue
         if in_fn and re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", ln):
             lines_of.append(cur_line)
-    short = "bwd_kernel" if "bwd_kernel" in kname else ("fwd_kernel" if "fwd_kernel" in kname else kname)
+    short = next((k for k in ("sbwd_kernel", "sfwd_kernel", "bwd_kernel", "fwd_kernel") if k in kname), kname)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + short],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -71,7 +76,8 @@ def main():
                     src[f] = open(cand).read().splitlines()
     tinst = sum(a["inst"] for a in agg.values()) or 1.0
     print(f"total samples {tot:.0f}")
-    for ln, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
+    by = "inst" if "--by-inst" in sys.argv else "samples"
+    for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][by])[:top]:
         f, l = ln if ln else ("?", 0)
         text = src.get(f, [""] * (l + 1))[l - 1].strip()[:70] if l else ""
         print(f"{100 * a['samples'] / tot:5.1f}% smp {100 * a['inst'] / tinst:5.1f}% inst | lsb {a['stall_long_sb']:6.0f} ssb {a['stall_short_sb']:5.0f} "

@@ -172,21 +172,24 @@ def test_cuda_inference_table_cache_is_safe():
     c = K.case("cache_fashion", "fashion", B=33)
     u = torch.from_numpy(K.make_io(c)[0]).cuda()
 
-    def reference_output(layer):   # the grad-mode path never consults the cache
-        return layer(u.clone().requires_grad_(True)).detach()
+    def same_as_uncached(layer, y):
+        # the grad-mode path never consults the cache (it runs the half-line kernels: equal up to rounding;
+        # stale tables would be off by percents)
+        ref = layer(u.clone().requires_grad_(True)).detach()
+        return runners.rel_l2(y.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
 
     layer = runners.make_cuda_layer(c, K.make_params(c))
     with torch.no_grad():
         y1, y1b = layer(u), layer(u)                      # second call: cached tables
-    assert torch.equal(y1, y1b) and torch.equal(y1, reference_output(layer))
+    assert torch.equal(y1, y1b) and same_as_uncached(layer, y1)
     with torch.no_grad():
         layer.alpha_base.mul_(1.5)                        # in-place update: version bump
         y2 = layer(u)
-    assert not torch.equal(y2, y1) and torch.equal(y2, reference_output(layer))
+    assert runners.rel_l2(y2.cpu().numpy(), y1.cpu().numpy()) > 1e-3 and same_as_uncached(layer, y2)
     with torch.no_grad():
         layer.load_state_dict({k: v * 0.5 for k, v in layer.state_dict().items()})
         y3 = layer(u)
-    assert torch.equal(y3, reference_output(layer))
+    assert same_as_uncached(layer, y3)
     for seed in range(4):                                 # dead layers' addresses get reused by fresh ones
         del layer
         gc.collect()
@@ -194,7 +197,7 @@ def test_cuda_inference_table_cache_is_safe():
         layer = runners.make_cuda_layer(c2, K.make_params(c2))
         with torch.no_grad():
             y = layer(u)
-        assert torch.equal(y, reference_output(layer)), seed
+        assert same_as_uncached(layer, y), seed
 
 
 def test_cuda_rejects_cpu_tensors_and_bad_shapes():

@@ -594,6 +594,17 @@ def _quick_layer(name, dev, peak):
            "fwd_hbm_frac": round(8 * cells / (fwd * 1e-3) / 1e9 / peak, 4),
            "bwd_hbm_frac": round(12 * cells / (bwd * 1e-3) / 1e9 / peak, 4),
            "fwd_bwd_hbm_frac": round(20 * cells / (tot * 1e-3) / 1e9 / peak, 4)}
+    if kind == "tiny":
+        # the bf16-I/O variant of the one bandwidth-bound layer (pde_tiny_*_bf16): same arithmetic, half the bytes
+        ub, gb = u.bfloat16(), g.bfloat16()
+        xb = ub.clone().requires_grad_(True)
+        fb = t(lambda: layer(xb))
+        yb = layer(xb)
+        bb = t(lambda: torch.autograd.grad(yb, [xb] + params, gb, retain_graph=True, allow_unused=True))
+        res["bf16_io"] = {"fwd_ms": round(fb, 3), "bwd_ms": round(bb, 3),
+                          "fwd_bwd_gcell_updates_per_s": round(cells * nsteps / ((fb + bb) * 1e-3) / 1e9, 2),
+                          "fwd_bwd_hbm_frac": round(10 * cells / ((fb + bb) * 1e-3) / 1e9 / peak, 4)}
+        del ub, gb, xb, yb
     del u, g, x, y
     torch.cuda.empty_cache()
     return res

@@ -37,7 +37,7 @@ EXPORTS = (
     "pde_adi_multi_prepare", "pde_adi_multi_forward_train", "pde_adi_multi_backward_saved",
     "pde_emotion_backward_workspace_bytes", "pde_emotion_forward", "pde_emotion_backward",
     "pde_tiny_backward_workspace_bytes", "pde_tiny_forward", "pde_tiny_backward",
-    "pde_tiny_split",
+    "pde_tiny_split", "pde_tiny_forward_bf16", "pde_tiny_backward_bf16",
 )
 
 
@@ -125,6 +125,10 @@ def lib():
     L.pde_tiny_forward.argtypes = [POINTER(TinyDesc), fp, fp, fp, fp, vp]
     L.pde_tiny_backward.restype = c_int
     L.pde_tiny_backward.argtypes = [POINTER(TinyDesc), fp, fp, fp, fp, fp, fp, fp, vp, c_size_t, vp]
+    L.pde_tiny_forward_bf16.restype = c_int
+    L.pde_tiny_forward_bf16.argtypes = [POINTER(TinyDesc), fp, fp, fp, fp, vp]
+    L.pde_tiny_backward_bf16.restype = c_int
+    L.pde_tiny_backward_bf16.argtypes = [POINTER(TinyDesc), fp, fp, fp, fp, fp, fp, fp, vp, c_size_t, vp]
     L.pde_tiny_split.restype = c_int
     L.pde_tiny_split.argtypes = [POINTER(TinySplitDesc), fp, fp, vp]
     if L.pde_b200_abi_version() != ABI_VERSION:

@@ -16,6 +16,8 @@
 // per block -> tiny finishing kernel (double accumulation, fixed order: deterministic).
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace pde {
@@ -27,12 +29,41 @@ namespace expl {
 constexpr int kTinyThreads = 256;
 constexpr int kMaxStages = 3;
 
+// u, gout, out, gin: fp32 or bf16 planes (the kernels are instantiated for both I/O types; arithmetic,
+// parameters and parameter gradients are fp32 either way)
 struct TinyArgs {
     pde_tiny_desc d;
-    const float *u, *gout, *alpha, *scal;
-    float *out, *gin, *part;
+    const void *u, *gout;
+    const float *alpha, *scal;
+    void *out, *gin;
+    float *part;
     int nplanes, stages, need_gin;
 };
+
+// four results leave as one streaming store: 16 bytes of fp32 or 8 bytes of bf16 (round to nearest even)
+template <typename T>
+__device__ __forceinline__ void st_stream4(T *dst, int q, float4 v);
+template <>
+__device__ __forceinline__ void st_stream4<float>(float *dst, int q, float4 v) {
+    st_stream(reinterpret_cast<float4 *>(dst) + q, v);
+}
+template <>
+__device__ __forceinline__ void st_stream4<__nv_bfloat16>(__nv_bfloat16 *dst, int q, float4 v) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 w;
+    w.x = *reinterpret_cast<const unsigned *>(&lo);
+    w.y = *reinterpret_cast<const unsigned *>(&hi);
+    __stcs(reinterpret_cast<uint2 *>(dst) + q, w);
+}
+
+// bf16 -> fp32 is a shift: two cells per 32-bit word, the lower address in the lower half
+__device__ __forceinline__ float4 widen4(uint2 w) {
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                       __uint_as_float(w.y & 0xffff0000u));
+}
+__device__ __forceinline__ float widen1(const __nv_bfloat16 *p) {
+    return __uint_as_float((unsigned)(*reinterpret_cast<const unsigned short *>(p)) << 16);
+}
 
 __device__ __forceinline__ float clamp_alpha(const pde_tiny_desc &d, float raw, bool *inside) {
     *inside = raw >= d.cmin && raw <= d.cmax;
@@ -44,7 +75,8 @@ struct Strip {
     float lf, rt;
 };
 
-// The float4 at chunk q of a dense H x W plane with its four neighbour strips; zero ghosts.
+// The four cells at chunk q of a dense H x W plane with their four neighbour strips; zero ghosts.  The plane is
+// fp32 (16-byte chunks) or bf16 as it arrived from HBM (8-byte chunks, widened on the way into registers).
 __device__ __forceinline__ Strip load_strip(const float *src, int q, int H, int W) {
     const float4 *s4 = reinterpret_cast<const float4 *>(src);
     const int idx = 4 * q, row = idx / W, col = idx - row * W, w4 = W >> 2;
@@ -55,6 +87,18 @@ __device__ __forceinline__ Strip load_strip(const float *src, int q, int H, int 
     s.dn = row < H - 1 ? s4[q + w4] : zero;
     s.lf = col > 0 ? src[idx - 1] : 0.0f;
     s.rt = col + 4 < W ? src[idx + 4] : 0.0f;
+    return s;
+}
+__device__ __forceinline__ Strip load_strip(const __nv_bfloat16 *src, int q, int H, int W) {
+    const uint2 *s2 = reinterpret_cast<const uint2 *>(src);
+    const int idx = 4 * q, row = idx / W, col = idx - row * W, w4 = W >> 2;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    Strip s;
+    s.c = widen4(s2[q]);
+    s.up = row > 0 ? widen4(s2[q - w4]) : zero;
+    s.dn = row < H - 1 ? widen4(s2[q + w4]) : zero;
+    s.lf = col > 0 ? widen1(src + idx - 1) : 0.0f;
+    s.rt = col + 4 < W ? widen1(src + idx + 4) : 0.0f;
     return s;
 }
 
@@ -77,8 +121,8 @@ __device__ __forceinline__ float blend1(float u, float sc, float adt, float lap,
 }
 
 // one explicit step of a whole plane: src in shared memory, dst in shared or global memory
-template <bool kStream>
-__device__ __forceinline__ void tiny_step(const float *src, float *dst, int H, int W, float sc, float adt,
+template <bool kStream, typename S = float, typename T = float>
+__device__ __forceinline__ void tiny_step(const S *src, T *dst, int H, int W, float sc, float adt,
                                           float bl, int tid) {
     const int nq = (H * W) >> 2;
     for (int q = tid; q < nq; q += kTinyThreads) {
@@ -90,20 +134,23 @@ __device__ __forceinline__ void tiny_step(const float *src, float *dst, int H, i
         o.z = blend1(s.c.z, sc, adt, lp.z, bl);
         o.w = blend1(s.c.w, sc, adt, lp.w, bl);
         if (kStream)
-            st_stream(reinterpret_cast<float4 *>(dst) + q, o);
+            st_stream4<T>(dst, q, o);
         else
             reinterpret_cast<float4 *>(dst)[q] = o;
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kTinyThreads) tiny_fwd_kernel(const TinyArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const pde_tiny_desc &d = a.d;
     const int HW = d.H * d.W, tid = threadIdx.x, stages = a.stages;
-    const uint32_t bytes = (uint32_t)HW * 4u;
+    const uint32_t bytes = (uint32_t)HW * (uint32_t)sizeof(T);
+    const T *gu = static_cast<const T *>(a.u);
+    T *gout = static_cast<T *>(a.out);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-    float *ring = reinterpret_cast<float *>(smem_raw + 128);
-    float *work = ring + (size_t)stages * HW;  // two planes, only touched when steps > 1
+    T *ring = reinterpret_cast<T *>(smem_raw + 128);
+    float *work = reinterpret_cast<float *>(smem_raw + 128 + (size_t)stages * bytes);  // two fp32 planes, only touched when steps > 1
     const int n_my = a.nplanes > (int)blockIdx.x ? (a.nplanes - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
@@ -113,7 +160,7 @@ __global__ void __launch_bounds__(kTinyThreads) tiny_fwd_kernel(const TinyArgs a
     if (tid == 0) {
         for (int k = 0; k < stages - 1 && k < n_my; ++k) {
             mbar_expect_tx(&bars[k], bytes);
-            tma_load_1d(ring + (size_t)k * HW, a.u + (size_t)(blockIdx.x + (size_t)k * gridDim.x) * HW, bytes, &bars[k]);
+            tma_load_1d(ring + (size_t)k * HW, gu + (size_t)(blockIdx.x + (size_t)k * gridDim.x) * HW, bytes, &bars[k]);
         }
     }
     for (int k = 0; k < n_my; ++k) {
@@ -123,7 +170,7 @@ __global__ void __launch_bounds__(kTinyThreads) tiny_fwd_kernel(const TinyArgs a
             const int sn = kn % stages;
             fence_proxy_async();
             mbar_expect_tx(&bars[sn], bytes);
-            tma_load_1d(ring + (size_t)sn * HW, a.u + (size_t)(blockIdx.x + (size_t)kn * gridDim.x) * HW, bytes, &bars[sn]);
+            tma_load_1d(ring + (size_t)sn * HW, gu + (size_t)(blockIdx.x + (size_t)kn * gridDim.x) * HW, bytes, &bars[sn]);
         }
         mbar_wait(&bars[st], (uint32_t)((k / stages) & 1));
         const size_t plane = blockIdx.x + (size_t)k * gridDim.x;
@@ -131,20 +178,26 @@ __global__ void __launch_bounds__(kTinyThreads) tiny_fwd_kernel(const TinyArgs a
         bool inside;
         const float al = clamp_alpha(d, __ldg(a.alpha + c), &inside);
         const float adt = al * d.dt, sc = __ldg(a.scal + c);
-        const float *src = ring + (size_t)st * HW;
-        float *gdst = a.out + plane * HW;
+        const T *in = ring + (size_t)st * HW;    // the plane as it arrived (fp32 or bf16)
+        T *gdst = gout + plane * HW;
         if (d.steps == 0) {
-            for (int q = tid; q < (HW >> 2); q += kTinyThreads)
-                st_stream(reinterpret_cast<float4 *>(gdst) + q, reinterpret_cast<const float4 *>(src)[q]);
-        }
-        for (int s = 0; s < d.steps; ++s) {
-            if (s == d.steps - 1) {
-                tiny_step<true>(src, gdst, d.H, d.W, sc, adt, d.blend, tid);
-            } else {
-                float *dst = work + (size_t)(s & 1) * HW;
-                tiny_step<false>(src, dst, d.H, d.W, sc, adt, d.blend, tid);
-                __syncthreads();
-                src = dst;
+            for (int q = tid; q < (HW >> 2); q += kTinyThreads) st_stream4<T>(gdst, q, load_strip(in, q, d.H, d.W).c);
+        } else if (d.steps == 1) {
+            tiny_step<true, T, T>(in, gdst, d.H, d.W, sc, adt, d.blend, tid);
+        } else {
+            // several steps: the intermediate states are fp32 planes in shared memory
+            tiny_step<false, T, float>(in, work, d.H, d.W, sc, adt, d.blend, tid);
+            __syncthreads();
+            const float *src = work;
+            for (int s = 1; s < d.steps; ++s) {
+                if (s == d.steps - 1) {
+                    tiny_step<true, float, T>(src, gdst, d.H, d.W, sc, adt, d.blend, tid);
+                } else {
+                    float *dst = work + (size_t)(s & 1) * HW;
+                    tiny_step<false, float, float>(src, dst, d.H, d.W, sc, adt, d.blend, tid);
+                    __syncthreads();
+                    src = dst;
+                }
             }
         }
         __syncthreads();  // everyone is done with ring[st] before it is refilled
@@ -153,15 +206,18 @@ __global__ void __launch_bounds__(kTinyThreads) tiny_fwd_kernel(const TinyArgs a
 
 // Backward.  Ring stage = {u plane, gout plane}.  For steps > 1 the forward states u_1..u_{K-1}
 // are rebuilt into `hist` and the adjoint ping-pongs through `gwork`.
+template <typename T>
 __global__ void __launch_bounds__(kTinyThreads) tiny_bwd_kernel(const TinyArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const pde_tiny_desc &d = a.d;
     const int HW = d.H * d.W, tid = threadIdx.x, stages = a.stages, K = d.steps;
-    const uint32_t bytes = (uint32_t)HW * 4u;
+    const uint32_t bytes = (uint32_t)HW * (uint32_t)sizeof(T);
+    const T *gu = static_cast<const T *>(a.u), *ggout = static_cast<const T *>(a.gout);
+    T *ggin = static_cast<T *>(a.gin);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-    float *ring = reinterpret_cast<float *>(smem_raw + 128);          // [stages][2][HW]
-    float *hist = ring + (size_t)stages * 2 * HW;                       // [K-1][HW]
-    float *gwork = hist + (size_t)(K > 1 ? K - 1 : 0) * HW;            // [2][HW]
+    T *ring = reinterpret_cast<T *>(smem_raw + 128);                                        // [stages][2][HW]
+    float *hist = reinterpret_cast<float *>(smem_raw + 128 + (size_t)stages * 2 * bytes);    // [K-1][HW]
+    float *gwork = hist + (size_t)(K > 1 ? K - 1 : 0) * HW;                                  // [2][HW]
     __shared__ float red[2][kTinyThreads / 32];
     const int n_my = a.nplanes > (int)blockIdx.x ? (a.nplanes - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     // gridDim.x is a multiple of C, so every plane of this block has the same channel
@@ -179,8 +235,8 @@ __global__ void __launch_bounds__(kTinyThreads) tiny_bwd_kernel(const TinyArgs a
         const int sn = k % stages;
         const size_t plane = blockIdx.x + (size_t)k * gridDim.x;
         mbar_expect_tx(&bars[sn], 2 * bytes);
-        tma_load_1d(ring + (size_t)sn * 2 * HW, a.u + plane * HW, bytes, &bars[sn]);
-        tma_load_1d(ring + (size_t)sn * 2 * HW + HW, a.gout + plane * HW, bytes, &bars[sn]);
+        tma_load_1d(ring + (size_t)sn * 2 * HW, gu + plane * HW, bytes, &bars[sn]);
+        tma_load_1d(ring + (size_t)sn * 2 * HW + HW, ggout + plane * HW, bytes, &bars[sn]);
     };
     if (tid == 0)
         for (int k = 0; k < stages - 1 && k < n_my; ++k) issue(k);
@@ -192,18 +248,16 @@ __global__ void __launch_bounds__(kTinyThreads) tiny_bwd_kernel(const TinyArgs a
         }
         mbar_wait(&bars[st], (uint32_t)((k / stages) & 1));
         const size_t plane = blockIdx.x + (size_t)k * gridDim.x;
-        const float *u0 = ring + (size_t)st * 2 * HW;
-        const float *g0 = u0 + HW;
-        // forward states u_1 .. u_{K-1}
+        const T *u0 = ring + (size_t)st * 2 * HW, *g0 = u0 + HW;   // the planes as they arrived (fp32 or bf16)
+        // forward states u_1 .. u_{K-1} (fp32 planes in shared memory)
         for (int s = 0; s + 1 < K; ++s) {
-            const float *src = s == 0 ? u0 : hist + (size_t)(s - 1) * HW;
-            tiny_step<false>(src, hist + (size_t)s * HW, d.H, d.W, sc, adt, bl, tid);
+            if (s == 0) tiny_step<false, T, float>(u0, hist, d.H, d.W, sc, adt, bl, tid);
+            else tiny_step<false, float, float>(hist + (size_t)(s - 1) * HW, hist + (size_t)s * HW, d.H, d.W, sc, adt, bl, tid);
             __syncthreads();
         }
-        const float *g = g0;
-        for (int s = K - 1; s >= 0; --s) {
-            const float *us = s == 0 ? u0 : hist + (size_t)(s - 1) * HW;
-            float *gdst = s == 0 ? (a.need_gin ? a.gin + plane * HW : nullptr) : gwork + (size_t)(s & 1) * HW;
+        T *gfinal = a.need_gin ? ggin + plane * HW : nullptr;          // step 0 writes grad_input
+        // one reversed step: state `us` and adjoint `g` in, adjoint out (to gdst, or grad_input at step 0)
+        auto reverse = [&](const auto *us, const auto *g, float *gdst, bool last) {
             for (int q = tid; q < (HW >> 2); q += kTinyThreads) {
                 const Strip su = load_strip(us, q, d.H, d.W);
                 const Strip sg = load_strip(g, q, d.H, d.W);
@@ -216,26 +270,49 @@ __global__ void __launch_bounds__(kTinyThreads) tiny_bwd_kernel(const TinyArgs a
                 accA = fmaf(gw2, lv.z, accA); accA = fmaf(gw3, lv.w, accA);
                 accS = fmaf(z0, su.c.x, accS); accS = fmaf(z1, su.c.y, accS);
                 accS = fmaf(z2, su.c.z, accS); accS = fmaf(z3, su.c.w, accS);
-                if (gdst) {
+                if (last ? gfinal != nullptr : true) {
                     float4 o;
                     o.x = fmaf(sc, z0, sg.c.x - gw0);
                     o.y = fmaf(sc, z1, sg.c.y - gw1);
                     o.z = fmaf(sc, z2, sg.c.z - gw2);
                     o.w = fmaf(sc, z3, sg.c.w - gw3);
-                    if (s == 0)
-                        st_stream(reinterpret_cast<float4 *>(gdst) + q, o);
+                    if (last)
+                        st_stream4<T>(gfinal, q, o);
                     else
                         reinterpret_cast<float4 *>(gdst)[q] = o;
                 }
             }
-            if (s > 0) {
+        };
+        if constexpr (sizeof(T) == 4) {
+            // fp32 I/O: ring planes and shared-memory planes have one type, so one loop (and one copy of the body) serves every step
+            const float *g = reinterpret_cast<const float *>(g0);
+            for (int s = K - 1; s >= 0; --s) {
+                const float *us = s == 0 ? reinterpret_cast<const float *>(u0) : hist + (size_t)(s - 1) * HW;
+                float *gdst = s == 0 ? nullptr : gwork + (size_t)(s & 1) * HW;
+                reverse(us, g, gdst, s == 0);
+                if (s > 0) {
+                    __syncthreads();
+                    g = gdst;
+                }
+            }
+        } else if (K == 1) {
+            reverse(u0, g0, nullptr, true);                // the model's case: both planes straight from the ring
+        } else if (K > 1) {
+            // step K-1 takes the upstream gradient from the ring, the others the adjoint plane of the step after
+            float *gdst = gwork + (size_t)((K - 1) & 1) * HW;
+            reverse(hist + (size_t)(K - 2) * HW, g0, gdst, false);
+            __syncthreads();
+            const float *g = gdst;
+            for (int s = K - 2; s >= 1; --s) {
+                gdst = gwork + (size_t)(s & 1) * HW;
+                reverse(hist + (size_t)(s - 1) * HW, g, gdst, false);
                 __syncthreads();
                 g = gdst;
             }
+            reverse(u0, g, nullptr, true);
         }
         if (K == 0 && a.need_gin)
-            for (int q = tid; q < (HW >> 2); q += kTinyThreads)
-                st_stream(reinterpret_cast<float4 *>(a.gin + plane * HW) + q, reinterpret_cast<const float4 *>(g0)[q]);
+            for (int q = tid; q < (HW >> 2); q += kTinyThreads) st_stream4<T>(ggin + plane * HW, q, load_strip(g0, q, d.H, d.W).c);
         __syncthreads();
     }
     accA = warp_sum(accA);
@@ -259,21 +336,23 @@ __global__ void tiny_finish_kernel(int C, int nblocks, const float *__restrict__
     g_scal[c] = (float)ss;
 }
 
-static int tiny_validate(const pde_tiny_desc *d) {
+static int tiny_validate(const pde_tiny_desc *d, int io_bytes = 4) {
     if (!d) return PDE_ERR_INVALID;
     if (d->B < 0 || d->C < 1 || d->H < 1 || d->W < 1 || d->steps < 0) return PDE_ERR_INVALID;
     if (d->W % 4 != 0) return PDE_ERR_UNSUPPORTED;          // float4 strips, 16-byte TMA granularity
+    if (io_bytes == 2 && (d->H * d->W) % 8 != 0) return PDE_ERR_UNSUPPORTED;   // bf16 planes: 16-byte granularity too
     if (d->C > 1024) return PDE_ERR_UNSUPPORTED;
     return PDE_OK;
 }
 
-// shared-memory plan: ring stages first, then the extra planes; fewer stages if it does not fit
-static int tiny_plan(const pde_tiny_desc *d, bool bwd, int max_smem, int *stages, size_t *smem) {
-    const size_t plane = (size_t)d->H * d->W * sizeof(float);
+// shared-memory plan: ring stages first (planes in their I/O type), then the extra fp32 planes (work / history
+// for several steps); fewer stages if it does not fit
+static int tiny_plan(const pde_tiny_desc *d, bool bwd, int max_smem, int *stages, size_t *smem, int io_bytes = 4) {
+    const size_t plane = (size_t)d->H * d->W * sizeof(float), io_plane = (size_t)d->H * d->W * io_bytes;
     const size_t extra = bwd ? ((size_t)(d->steps > 1 ? d->steps - 1 : 0) + (d->steps > 1 ? 2 : 0)) * plane
                              : (d->steps > 1 ? 2 * plane : 0);
     for (int s = kMaxStages; s >= 1; --s) {
-        const size_t need = 128 + (size_t)s * (bwd ? 2 : 1) * plane + extra;
+        const size_t need = 128 + (size_t)s * (bwd ? 2 : 1) * io_plane + extra;
         if (need <= (size_t)max_smem) {
             *stages = s;
             *smem = need;
@@ -587,9 +666,10 @@ extern "C" size_t pde_tiny_backward_workspace_bytes(const pde_tiny_desc *d) {
     return ((size_t)props.sm_count * 8 + (size_t)d->C) * 2 * sizeof(float) + 256;
 }
 
-extern "C" int pde_tiny_forward(const pde_tiny_desc *d, const float *u, const float *alpha_base,
-                                const float *channel_scaling, float *out, void *stream) {
-    int rc = tiny_validate(d);
+template <typename T>
+static int tiny_forward_impl(const pde_tiny_desc *d, const void *u, const float *alpha_base, const float *channel_scaling,
+                             void *out, void *stream) {
+    int rc = tiny_validate(d, (int)sizeof(T));
     if (rc) return rc;
     if (d->B == 0) return PDE_OK;   // empty batch: a no-op, its tensor pointers may be NULL
     if (!u || !alpha_base || !channel_scaling || !out) return PDE_ERR_INVALID;
@@ -601,20 +681,20 @@ extern "C" int pde_tiny_forward(const pde_tiny_desc *d, const float *u, const fl
     a.d = *d; a.u = u; a.alpha = alpha_base; a.scal = channel_scaling; a.out = out;
     a.nplanes = d->B * d->C;
     size_t smem;
-    rc = tiny_plan(d, false, props.max_smem_optin, &a.stages, &smem);
+    rc = tiny_plan(d, false, props.max_smem_optin, &a.stages, &smem, (int)sizeof(T));
     if (rc) return rc;
     const int grid = tiny_grid(d, props, smem, false);
-    rc = kernel_info(reinterpret_cast<const void *>(tiny_fwd_kernel), smem, nullptr);
+    rc = kernel_info(reinterpret_cast<const void *>(tiny_fwd_kernel<T>), smem, nullptr);
     if (rc) return rc;
-    tiny_fwd_kernel<<<grid, kTinyThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    tiny_fwd_kernel<T><<<grid, kTinyThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     return cuda_last_error();
 }
 
-extern "C" int pde_tiny_backward(const pde_tiny_desc *d, const float *u, const float *gout,
-                                 const float *alpha_base, const float *channel_scaling, float *gin,
-                                 float *g_alpha_base, float *g_channel_scaling, void *workspace,
-                                 size_t workspace_bytes, void *stream) {
-    int rc = tiny_validate(d);
+template <typename T>
+static int tiny_backward_impl(const pde_tiny_desc *d, const void *u, const void *gout, const float *alpha_base,
+                              const float *channel_scaling, void *gin, float *g_alpha_base, float *g_channel_scaling,
+                              void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = tiny_validate(d, (int)sizeof(T));
     if (rc) return rc;
     if (!g_alpha_base || !g_channel_scaling) return PDE_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -633,19 +713,44 @@ extern "C" int pde_tiny_backward(const pde_tiny_desc *d, const float *u, const f
     a.need_gin = gin != nullptr;
     a.nplanes = d->B * d->C;
     size_t smem;
-    rc = tiny_plan(d, true, props.max_smem_optin, &a.stages, &smem);
+    rc = tiny_plan(d, true, props.max_smem_optin, &a.stages, &smem, (int)sizeof(T));
     if (rc) return rc;
     const int grid = tiny_grid(d, props, smem, true);
     const size_t need = (size_t)grid * 2 * sizeof(float) + 256;
     if (!workspace || workspace_bytes < need) return PDE_ERR_WORKSPACE;
     a.part = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255u) & ~(uintptr_t)255u);
-    rc = kernel_info(reinterpret_cast<const void *>(tiny_bwd_kernel), smem, nullptr);
+    rc = kernel_info(reinterpret_cast<const void *>(tiny_bwd_kernel<T>), smem, nullptr);
     if (rc) return rc;
-    tiny_bwd_kernel<<<grid, kTinyThreads, smem, st>>>(a);
+    tiny_bwd_kernel<T><<<grid, kTinyThreads, smem, st>>>(a);
     rc = cuda_last_error();
     if (rc) return rc;
     tiny_finish_kernel<<<1, ((d->C + 31) / 32) * 32, 0, st>>>(d->C, grid, a.part, g_alpha_base, g_channel_scaling);
     return cuda_last_error();
+}
+
+extern "C" int pde_tiny_forward(const pde_tiny_desc *d, const float *u, const float *alpha_base,
+                                const float *channel_scaling, float *out, void *stream) {
+    return tiny_forward_impl<float>(d, u, alpha_base, channel_scaling, out, stream);
+}
+
+extern "C" int pde_tiny_backward(const pde_tiny_desc *d, const float *u, const float *gout,
+                                 const float *alpha_base, const float *channel_scaling, float *gin,
+                                 float *g_alpha_base, float *g_channel_scaling, void *workspace,
+                                 size_t workspace_bytes, void *stream) {
+    return tiny_backward_impl<float>(d, u, gout, alpha_base, channel_scaling, gin, g_alpha_base, g_channel_scaling, workspace,
+                                     workspace_bytes, stream);
+}
+
+extern "C" int pde_tiny_forward_bf16(const pde_tiny_desc *d, const void *u, const float *alpha_base,
+                                     const float *channel_scaling, void *out, void *stream) {
+    return tiny_forward_impl<__nv_bfloat16>(d, u, alpha_base, channel_scaling, out, stream);
+}
+
+extern "C" int pde_tiny_backward_bf16(const pde_tiny_desc *d, const void *u, const void *gout, const float *alpha_base,
+                                      const float *channel_scaling, void *gin, float *g_alpha_base,
+                                      float *g_channel_scaling, void *workspace, size_t workspace_bytes, void *stream) {
+    return tiny_backward_impl<__nv_bfloat16>(d, u, gout, alpha_base, channel_scaling, gin, g_alpha_base, g_channel_scaling,
+                                             workspace, workspace_bytes, stream);
 }
 
 // --------------------------------------------------------------------------------------- emotion

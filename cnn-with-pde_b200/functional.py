@@ -491,17 +491,27 @@ def _tiny_plan(cfg: TinyConfig, shape, device_index: int):
 
 
 class _TinyFunction(torch.autograd.Function):
+    """fp32 planes in, fp32 planes out -- or bfloat16 in, bfloat16 out (pde_tiny_*_bf16: the arithmetic, the
+    parameters and their gradients stay fp32; the one bandwidth-bound layer of the reference moves half the bytes)."""
+
     @staticmethod
     def forward(ctx, u, alpha_base, channel_scaling, cfg: TinyConfig):
-        _require_cuda(u, "ImprovedDiffusionLayer input")
+        if isinstance(u, torch.Tensor) and u.is_cuda and u.dtype == torch.bfloat16:
+            ctx.bf16 = True
+        else:
+            ctx.bf16 = False
+            _require_cuda(u, "ImprovedDiffusionLayer input")
         L = _cabi.lib()
         u = _contig(u)
         al, sc = _contig(alpha_base.detach()), _contig(channel_scaling.detach())
+        if al.dtype != torch.float32 or sc.dtype != torch.float32:   # a module converted with .bfloat16(): the kernels take fp32 scalars
+            al, sc = al.float(), sc.float()
         dev = u.device
         plan = _tiny_plan(cfg, tuple(u.shape), dev.index if dev.index is not None else torch.cuda.current_device())
+        fwd = L.pde_tiny_forward_bf16 if ctx.bf16 else L.pde_tiny_forward
         with _guard(u.device):
             out = torch.empty_like(u)
-            _cabi.check(L.pde_tiny_forward(plan[1], _ptr(u), _ptr(al), _ptr(sc), _ptr(out), _stream(u.device)),
+            _cabi.check(fwd(plan[1], _ptr(u), _ptr(al), _ptr(sc), _ptr(out), _stream(u.device)),
                         "pde_tiny_forward")
         ctx.plan = plan
         ctx.save_for_backward(u, al, sc)
@@ -513,8 +523,8 @@ class _TinyFunction(torch.autograd.Function):
         L = _cabi.lib()
         u, al, sc = ctx.saved_tensors
         gout = _contig(gout)
-        if gout.dtype != torch.float32:
-            gout = gout.float()
+        if gout.dtype != u.dtype:
+            gout = gout.to(u.dtype)
         C = u.shape[1]
         d, dref, ws_bytes = ctx.plan
         with _guard(u.device):
@@ -522,7 +532,8 @@ class _TinyFunction(torch.autograd.Function):
             gin = torch.empty_like(u) if ctx.needs_input_grad[0] else None
             ga = torch.empty(C, dtype=torch.float32, device=u.device)
             gs = torch.empty(C, dtype=torch.float32, device=u.device)
-            _cabi.check(L.pde_tiny_backward(dref, _ptr(u), _ptr(gout), _ptr(al), _ptr(sc), _ptr(gin), _ptr(ga),
+            bwd = L.pde_tiny_backward_bf16 if ctx.bf16 else L.pde_tiny_backward
+            _cabi.check(bwd(dref, _ptr(u), _ptr(gout), _ptr(al), _ptr(sc), _ptr(gin), _ptr(ga),
                                             _ptr(gs), _ptr(ws), ws_bytes, _stream(u.device)), "pde_tiny_backward")
         return gin, ga, gs, None
 

@@ -207,6 +207,18 @@ int pde_tiny_backward(const pde_tiny_desc *d, const float *u, const float *gout,
                       float *g_alpha_base, float *g_channel_scaling,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* bf16-I/O variants: u, out, gout, gin are bfloat16 planes in the same NCHW
+ * layout (H * W a multiple of 8); arithmetic, parameters and parameter gradients stay fp32 and the
+ * results are rounded to nearest even once, on the way out.  This is the one layer of the reference that
+ * is bound by HBM bandwidth, so halving the bytes per cell is what a half-precision pipeline gains from it.
+ * Workspace size: pde_tiny_backward_workspace_bytes. */
+int pde_tiny_forward_bf16(const pde_tiny_desc *d, const void *u, const float *alpha_base,
+                          const float *channel_scaling, void *out, void *stream);
+int pde_tiny_backward_bf16(const pde_tiny_desc *d, const void *u, const void *gout,
+                           const float *alpha_base, const float *channel_scaling, void *gin,
+                           float *g_alpha_base, float *g_channel_scaling,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * The dormant scalar-coefficient methods of ImprovedDiffusionLayer, tiny_imagenet.py:88-233:
  * implicit_diffusion_step (:88-102), solve_implicit_x / _y (:104-157, with the clamp(denom) Thomas

@@ -497,3 +497,34 @@ def test_cuda_multi_branch_falls_back_when_layers_cannot_share_a_launch():
     y1, y2 = apply_to_same_input(x16, [c16, d16])       # 16 x 16 planes: whole-line kernels, one call per layer
     (y1.sum() + y2.sum()).backward()
     assert x16.grad is not None and c16.alpha_base.grad is not None and d16.alpha_base.grad is not None
+
+
+# ------------------------------------------------------------------------------ bf16 I/O (tiny_imagenet layer)
+@pytest.mark.parametrize("ctor,B", [(K.SCRIPT_INSTANCES["tiny"], 5), (dict(size=16, channels=3, num_steps=3, dt=0.02), 7),
+                                    (dict(size=32, channels=2, num_steps=2, dt=0.01), 3)], ids=["64x64", "16x16_3steps", "32x32_2steps"])
+def test_cuda_tiny_layer_bf16_io(ctor, B):
+    """bfloat16 planes in, bfloat16 planes out (pde_tiny_*_bf16): the arithmetic is the fp32 kernels', so on the
+    bf16-rounded inputs the parameter gradients (fp32) match the oracle at 1e-5 and the output / grad_input are
+    the oracle's fp32 results rounded to bf16 (to within one bf16 unit where the fp32 values straddle a tie)."""
+    import torch
+    c = K.case("tiny_bf16", "tiny", B=B, **ctor)
+    params, (u, g) = K.make_params(c), K.make_io(c)
+    ub, gb = torch.from_numpy(u).cuda().bfloat16(), torch.from_numpy(g).cuda().bfloat16()
+    layer = runners.make_cuda_layer(c, params)
+    x = ub.clone().requires_grad_(True)
+    y = layer(x)
+    assert y.dtype == torch.bfloat16
+    y.backward(gb)
+    assert x.grad.dtype == torch.bfloat16
+    want = runners.run_oracle(c, params=params, io=(ub.float().cpu().numpy(), gb.float().cpu().numpy()), dtype=np.float32)
+    for got, ref in ((y, want["y"]), (x.grad, want["gin"])):
+        ref_b = torch.from_numpy(ref).bfloat16().float().numpy()
+        got_f = got.detach().float().cpu().numpy()
+        assert np.all(np.abs(got_f - ref_b) <= 2.0 ** -7 * np.abs(ref_b) + 1e-30)        # at most one bf16 unit
+        assert np.mean(got_f != ref_b) <= 0.01                                            # and almost always none
+    for k in ("alpha_base", "channel_scaling"):
+        a, b = getattr(layer, k).grad.cpu().numpy(), want["g_" + k]
+        assert max(runners.rel_l2(a, b), runners.rel_max(a, b)) <= TOL, k
+    # fp32 input on the same layer still takes the fp32 kernels
+    y32 = layer(torch.from_numpy(u).cuda())
+    assert y32.dtype == torch.float32

@@ -26,6 +26,18 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+# side streams of the branch-parallel extractors: per device, shared by all modules (kept out of the modules'
+# __dict__ so that copy.deepcopy / pickling of a model that has already run keeps working)
+_SIDE_STREAMS = {}
+
+
+def _side_streams(device, n):
+    pool = _SIDE_STREAMS.setdefault(device, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
 def _dense_stack(owner: nn.Module, widths, batch_norm: bool):
     """Register fc1..fcK (and bn1..bn{K-1}) on `owner` for the layer widths w0 -> w1 -> ... -> wK."""
     for k in range(1, len(widths)):
@@ -153,10 +165,7 @@ class MultiScaleExtractor(nn.Module):
     concurrent_branches = True
 
     def _side_streams(self, device):
-        cache = self.__dict__.setdefault("_streams", {})
-        if device not in cache:
-            cache[device] = [torch.cuda.Stream(device=device) for _ in range(2)]
-        return cache[device]
+        return _side_streams(device, 2)
 
     def forward(self, x):
         branches = ((self.pde1, self.attention1), (self.pde2, self.attention2), (self.pde3, self.attention3))
@@ -344,8 +353,7 @@ class HybridPDEExtractor(nn.Module):
         elif x.is_cuda and self.concurrent_branches and not serial:
             # the second diffusion layer on a side stream; the dense blocks keep the GPU busy on the main one
             cur = torch.cuda.current_stream(x.device)
-            cache = self.__dict__.setdefault("_streams", {})
-            side = cache.setdefault(x.device, torch.cuda.Stream(device=x.device))
+            side = _side_streams(x.device, 1)[0]
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 d2 = self.diffusion2(x)

@@ -186,6 +186,28 @@ def test_graph_captured_step_equals_eager_step(name, batch):
 
 
 @pytest.mark.gpu
+def test_models_survive_deepcopy_and_pickle_after_running():
+    """EMA / checkpointing code copies models that have already run: the layers' cached launch plans and the
+    extractors' side streams must not get in the way."""
+    import copy
+    import io
+    for name in ("cifar10", "fashion"):
+        torch.manual_seed(0)
+        model = ours(name).cuda().eval()
+        shape = (3, 32, 32) if name == "cifar10" else (1, 28, 28)
+        x = torch.randn(4, *shape, device="cuda")
+        y = model(x)
+        y.sum().backward()
+        twin = copy.deepcopy(model)
+        buf = io.BytesIO()
+        torch.save(model, buf)
+        buf.seek(0)
+        loaded = torch.load(buf, weights_only=False)
+        with torch.no_grad():
+            assert torch.allclose(twin(x), y, rtol=1e-5, atol=1e-6) and torch.allclose(loaded(x), y, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
 def test_amp_recipe_scales_unscales_and_steps():
     """--amp is the CIFAR scripts' recipe (cifar10.py:440,458-467): autocast forward, GradScaler.scale(loss)
     .backward(), unscale_, clip_grad_norm_, scaler.step, scaler.update.  The PDE layers stay fp32 inside; the

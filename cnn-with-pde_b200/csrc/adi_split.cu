@@ -1183,10 +1183,19 @@ static int make_plan(const pde_adi_desc &d, Plan *p) {
     else if (d.N == 32) { if (p->P == 4) fill_geo<32, 4>(d, p); else fill_geo<32, 2>(d, p); }
     else return PDE_ERR_UNSUPPORTED;
     p->ngroups = (d.B + 2 * p->P - 1) / (2 * p->P);
-    // groups per block: as many as still leave two blocks of work per SM (and fit shared memory)
+    // groups per forward block: as many as still leave two blocks of work per SM and fit the shared memory
+    // the block may take.  The registers decide how many blocks an SM holds (128 per thread, two blocks, for
+    // four pairs per group; ~168 per thread for two pairs: three blocks of 128 threads, one block of 256 or 384),
+    // the tiles get what is left of 227 KB per block beside the two coefficient stages.  For the three-channel
+    // layers that admits two groups (111 KB of tiles; measured at batch 65536: cifar10 pde1 forward 2.49 ->
+    // 2.19 ms, pde2 3.83 -> 3.33, cifar_2version 2.98 -> 2.62, SVHN 5.05 -> 4.67).
+    const size_t coef_stage = (size_t)4 * d.C * ((d.N / 2 + 3) / 4) * d.N * 2 * 16;
+    const int blocks_per_sm = p->threads <= 128 ? 3 : 1;   // two pairs per group
+    const size_t tile_budget = p->P == 4 ? (size_t)101 * 1024   // two blocks: 4 x 25 KB tiles + 14 KB of coefficients each
+                                         : (size_t)227 * 1024 / blocks_per_sm - coef_stage - 2048;
     auto pick = [&](int qmax, size_t tiles_per_group, int forced) {
         int q = qmax;
-        while (q > 1 && ((p->ngroups + q - 1) / q < 2 * sm || (size_t)q * tiles_per_group * p->tile_bytes > 101 * 1024)) q >>= 1;
+        while (q > 1 && ((p->ngroups + q - 1) / q < 2 * sm || (size_t)q * tiles_per_group * p->tile_bytes > tile_budget)) q >>= 1;
         if (forced == 1 || forced == 2 || (forced == 4 && qmax == 4)) q = forced;
         return q;
     };

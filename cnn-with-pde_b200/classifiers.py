@@ -157,10 +157,10 @@ class MultiScaleExtractor(nn.Module):
     #                        its backward start as soon as that branch's PDE kernel is done;
     #   fused_branches       the three PDE layers through ONE launch per pass (blocks dealt to the layers in
     #                        proportion to their sweeps; cifar10.apply_to_same_input), gates on side streams.
-    # Measured on one B200, batch 512, CUDA graph: 1.15 - 1.24 ms per step with three
-    # concurrent launches, 1.26 ms fused -- one launch makes every gate wait for the slowest layer and the
-    # PDE backward wait for all three gates, which costs more than the four launches it saves.  So the
-    # streams are the default and the fused call is opt-in (set fused_branches = True).
+    # Measured on one B200, batch 512, CUDA graph: 1.18 - 1.20 ms per step with three
+    # concurrent launches, 1.13 - 1.24 ms fused depending on the run -- one launch saves four launches but makes
+    # every gate wait for the slowest layer and the PDE backward wait for all three gates.  No consistent winner,
+    # so the streams stay the default and the fused call is opt-in (set fused_branches = True).
     fused_branches = False
     concurrent_branches = True
 

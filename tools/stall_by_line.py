@@ -43,7 +43,8 @@ def main():
             continue
         if in_fn and re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", ln):
             lines_of.append(cur_line)
-    short = next((k for k in ("sbwd_kernel", "sfwd_kernel", "bwd_kernel", "fwd_kernel") if k in kname), kname)
+    short = next((k for k in ("sbwd_multi_kernel", "sfwd_multi_kernel", "sbwd_kernel", "sfwd_kernel", "emo_bwd_tiled", "emo_fwd_tiled",
+                               "tiny_bwd_kernel", "tiny_fwd_kernel", "bwd_kernel", "fwd_kernel") if k in kname), kname)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + short],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))

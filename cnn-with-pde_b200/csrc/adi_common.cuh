@@ -171,5 +171,19 @@ int backward_multi(int n, const pde_adi_desc *d, const void *const *tables, cons
                    float *const *g_skip, void *const *workspace, const size_t *workspace_bytes, cudaStream_t st);
 }  // namespace split
 
+// adi_generic.cu: every other plane edge (2 ... 128, run-time value; one block per sample, state in shared memory)
+namespace generic {
+bool serves(const pde_adi_desc &d);
+size_t tables_bytes(const pde_adi_desc &d);
+size_t workspace_bytes(const pde_adi_desc &d);          // accumulators + per-block sweep history; 0 without a device
+int prepare(const pde_adi_desc &d, const pde_adi_schedule &sch, const float *ab, const float *bb, const float *atc,
+            const float *btc, char *tables, cudaStream_t st);
+int forward(const pde_adi_desc &d, const char *tables, const float *u, const float *chan, const float *skipw, float *out,
+            cudaStream_t st);
+int backward(const pde_adi_desc &d, const char *tables, const float *u, const float *gout, const float *chan,
+             const float *skipw, float *gin, float *g_ab, float *g_bb, float *g_atc, float *g_btc, float *g_chan,
+             float *g_skip, void *workspace, size_t workspace_bytes, cudaStream_t st);
+}  // namespace generic
+
 }  // namespace adi
 }  // namespace pde

@@ -160,9 +160,10 @@ def make_params(c: Case) -> Dict[str, np.ndarray]:
         for k in ("alpha_base", "beta_base"):
             a = p[k].astype(np.float64) + 0.3 * rs.randn(*p[k].shape)
             flat = a.reshape(-1)
-            idx = rs.choice(flat.size, size=12, replace=False)
-            flat[idx[:6]] = -0.5 + 0.4 * rs.rand(6)        # forced below clamp min
-            flat[idx[6:]] = 10.5 + rs.rand(6)              # forced above the CIFAR clamp max
+            n = 12 if flat.size >= 12 else 2               # (2 x 2 planes: one cell on either side)
+            idx = rs.choice(flat.size, size=n, replace=False)
+            flat[idx[:n // 2]] = -0.5 + 0.4 * rs.rand(n // 2)   # forced below clamp min
+            flat[idx[n // 2:]] = 10.5 + rs.rand(n // 2)         # forced above the CIFAR clamp max
             p[k] = a.astype(f)
         for k in ("alpha_time_coeff", "beta_time_coeff"):
             # strong enough that some cells cross a clamp edge inside [0, T]

@@ -104,6 +104,10 @@ def test_implicit_kernels_stay_inside_their_buffers():
         (K.case("guard_whole_cifar10", "cifar10", B=5, **K.SCRIPT_INSTANCES["cifar10_pde3"]), T(impl=P._cabi.TUNE_IMPL_WHOLE_LINE), True),
         (K.case("guard_svhn16", "svhn", B=3, size=16, channels=3, num_steps=2), 0, True),
         (K.case("guard_mnist12", "mnist", B=5, size=12, num_steps=2), 0, False),
+        # adi_generic.cu (plane edge at run time): odd edge, unaligned planes; three channels with both channel ops
+        (K.case("guard_generic7", "mnist", B=3, size=7, num_steps=2), 0, False),
+        (K.case("guard_generic36_svhn", "svhn", B=5, size=36, channels=3, num_steps=2), 0, True),
+        (K.case("guard_generic40_cifar10", "cifar10", B=4, size=40, channels=3, dt=0.01, num_steps=2), 0, True),
     ]
     for c, tuning, need_gin in todo:
         _adi_case(c, tuning, need_gin)

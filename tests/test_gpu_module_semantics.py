@@ -22,6 +22,7 @@ _CASES = [
     K.case("sem_cifar10_pde2", "cifar10", B=9, **K.SCRIPT_INSTANCES["cifar10_pde2"]),
     K.case("sem_cifar2", "cifar2", B=6, **K.SCRIPT_INSTANCES["cifar2_diffusion1"]),
     K.case("sem_svhn", "svhn", B=7, **K.SCRIPT_INSTANCES["svhn"]),
+    K.case("sem_generic36_svhn", "svhn", B=5, size=36, channels=3, num_steps=3),
     K.case("sem_emotion", "emotion", B=5),
     K.case("sem_tiny", "tiny", B=4, **K.SCRIPT_INSTANCES["tiny"]),
 ]

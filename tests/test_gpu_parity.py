@@ -4,6 +4,8 @@ Bar (BASELINE.json north_star): rel-err <= 1e-5 in fp32 for the output, grad_inp
 parameter gradient -- measured both as rel-L2 and as max-abs / max-ref -- and no further from
 the fp64 oracle than the fp32 reference path is, plus 1e-5.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -101,6 +103,52 @@ def test_cuda_emotion_plane_sizes(ctor):
         assert got["gin"] is None
         _assert_close({k: v for k, v in got.items() if k != "gin"},
                       {k: v for k, v in want.items() if k != "gin"}, TOL, c.name + " (no grad_input)")
+
+
+@pytest.mark.parametrize("size", [2, 5, 7, 30, 36, 48, 64, 96, 128])
+def test_cuda_generic_plane_sizes(size):
+    """Every plane edge without kernels of its own (odd ones included, up to 128 while a sample's planes fit one
+    block's shared memory) is served by adi_generic.cu: all four implicit variants, odd batches, perturbed
+    weights with clamped cells, with and without grad_input."""
+    todo = [K.case(f"gsize{size}_mnist", "mnist", B=5, size=size, num_steps=3, dt=0.05, dx=0.7, dy=1.3)]
+    if size <= 96:
+        todo += [K.case(f"gsize{size}_svhn", "svhn", B=3, size=size, channels=3, num_steps=2),
+                 K.case(f"gsize{size}_cifar10_c4", "cifar10", B=3, size=size, channels=4, dt=0.01, num_steps=2, dx=1.0, dy=1.5),
+                 K.case(f"gsize{size}_cifar2_c2", "cifar2", B=7, size=size, channels=2, dt=0.02, num_steps=3)]
+    else:
+        todo += [K.case(f"gsize{size}_cifar10_c3", "cifar10", B=2, size=size, channels=3, dt=0.01, num_steps=2)]
+    for c in todo:
+        params, io = K.make_params(c), K.make_io(c)
+        got = runners.run_cuda(c, params=params, io=io)
+        want = runners.run_oracle(c, params=params, io=io, dtype=np.float32, nthreads=os.cpu_count() or 1)
+        _assert_close(got, want, TOL, c.name)
+    c = todo[-1]
+    params, io = K.make_params(c), K.make_io(c)
+    got = runners.run_cuda(c, params=params, io=io, need_gin=False)
+    want = runners.run_oracle(c, params=params, io=io, dtype=np.float32, need_gin=False, nthreads=os.cpu_count() or 1)
+    assert got["gin"] is None
+    _assert_close({k: v for k, v in got.items() if k != "gin"}, {k: v for k, v in want.items() if k != "gin"}, TOL, c.name)
+
+
+def test_cuda_generic_plane_size_large_batch_and_inference():
+    """More samples than blocks (every block walks several samples and sums their gradients in its own
+    accumulators), fp32 and fp64 oracle; and the same layer under no_grad."""
+    import torch
+    for c in (K.case("gsize36_large", "mnist", B=6001, size=36, num_steps=3, dt=0.05),
+              K.case("gsize40_large_svhn", "svhn", B=1203, size=40, channels=3, num_steps=2)):
+        params, io = K.make_params(c), K.make_io(c)
+        nt = os.cpu_count() or 1
+        got = runners.run_cuda(c, params=params, io=io)
+        o32 = runners.run_oracle(c, params=params, io=io, dtype=np.float32, nthreads=nt)
+        o64 = runners.run_oracle(c, params=params, io=io, dtype=np.float64, nthreads=nt)
+        _assert_close(got, o32, TOL, c.name)
+        e_cuda, e_ref = runners.compare(got, o64), runners.compare(o32, o64)
+        bad = {k: (e_cuda[k], e_ref[k]) for k in e_cuda if not e_cuda[k] <= e_ref[k] + TOL}
+        assert not bad, bad
+        layer = runners.make_cuda_layer(c, params)
+        with torch.no_grad():
+            y = layer(torch.from_numpy(io[0]).cuda())
+        np.testing.assert_array_equal(y.cpu().numpy(), got["y"])
 
 
 @pytest.mark.parametrize("size", [8, 12, 16, 20, 24])

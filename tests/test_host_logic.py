@@ -41,8 +41,13 @@ def test_cabi_host_only_queries():
         assert lib.pde_adi_checkpoint_bytes(ctypes.byref(d)) == 0
         big = cfg.desc(1 << 16)
         assert lib.pde_adi_checkpoint_bytes(ctypes.byref(big)) == 0
-    bad = P.AdiConfig(N=30, C=1, steps=4, dt=0.3, hx=1.0, hy=1.0).desc(1)     # size not built
-    assert lib.pde_adi_tables_bytes(ctypes.byref(bad)) == 0
+    # plane edges without kernels of their own go to the run-time-sized path (one table set, no checkpoints)
+    gen = P.AdiConfig(N=30, C=3, steps=4, dt=0.3, hx=1.0, hy=1.0).desc(5)
+    assert lib.pde_adi_tables_bytes(ctypes.byref(gen)) == 4096 + 4 * (12 * 3 * 30 * 30) * 4
+    assert lib.pde_adi_checkpoint_bytes(ctypes.byref(gen)) == 0
+    for N, C in ((200, 1), (128, 4), (1, 1)):     # larger than a block's shared memory / not a plane
+        bad = P.AdiConfig(N=N, C=C, steps=4, dt=0.3, hx=1.0, hy=1.0).desc(1)
+        assert lib.pde_adi_tables_bytes(ctypes.byref(bad)) == 0, (N, C)
     # struct layouts must match the header
     assert ctypes.sizeof(P._cabi.AdiDesc) == 9 * 4 + 3 * 4 + 4      # ... + tuning
     assert ctypes.sizeof(P._cabi.AdiSchedule) == 3 * 192 * 4

@@ -36,3 +36,30 @@ def test_oracle_f64_vs_reference_fp64_twin(c):
     errs = runners.compare(got, ref)
     bad = {k: e for k, e in errs.items() if not e <= 1e-12}
     assert not bad, bad
+
+
+# plane edges beyond the scripts' own (served by csrc/adi_generic.cu): the reference classes take any `size`,
+# so the oracle is pinned there too -- odd edges, a 2 x 2 plane, 48 and 64 with every channel op
+ODD_SIZES = [
+    K.case("ref_size2_mnist", "mnist", B=3, size=2, num_steps=3, dt=0.05, dx=0.7, dy=1.3),
+    K.case("ref_size7_svhn", "svhn", B=2, size=7, channels=3, num_steps=2),
+    K.case("ref_size30_cifar10_c4", "cifar10", B=2, size=30, channels=4, dt=0.01, num_steps=2, dx=1.0, dy=1.5),
+    K.case("ref_size36_cifar2_c2", "cifar2", B=3, size=36, channels=2, dt=0.02, num_steps=3),
+    K.case("ref_size48_mnist", "mnist", B=2, size=48, num_steps=2, dt=0.05),
+    K.case("ref_size64_svhn", "svhn", B=1, size=64, channels=3, num_steps=1),
+]
+
+
+@pytest.mark.parametrize("c", ODD_SIZES, ids=lambda c: c.name)
+def test_oracle_vs_live_reference_at_other_plane_sizes(c):
+    params, io = K.make_params(c), K.make_io(c)
+    ref = runners.run_reference(c, params=params, io=io)
+    got = runners.run_oracle(c, params=params, io=io, dtype=np.float32)
+    errs = runners.compare(got, ref)
+    assert set(errs) == set(ref)
+    bad = {k: e for k, e in errs.items() if not e <= 5e-6}
+    assert not bad, bad
+    ref64 = runners.run_reference(c, params=params, io=io, double=True)
+    got64 = runners.run_oracle(c, params=params, io=io, dtype=np.float64)
+    bad = {k: e for k, e in runners.compare(got64, ref64).items() if not e <= 1e-12}
+    assert not bad, bad

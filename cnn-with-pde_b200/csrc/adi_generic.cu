@@ -13,7 +13,9 @@
 //     substitution), one __syncthreads() per change of orientation;
 //   * tables, history and gradient accumulators are all stored in LINE coordinates [c][i][line]
 //     (i = position along the sweep, line fastest): whatever the axis, consecutive threads touch
-//     consecutive addresses;
+//     consecutive addresses.  A cell's four table values travel as one float4 (r, 1/pivot, r/pivot, mask),
+//     its two accumulators (base, time coefficient) as one float2, and all indices inside the line loops
+//     are 32-bit: the first version spent 60 % of its instructions on 64-bit address arithmetic;
 //   * the backward pass keeps no checkpoints from the forward call: the block replays the sample's
 //     trajectory, parks the output of every sweep in its own slice of the workspace (the thread that
 //     writes a line is the one that reads it back), then walks the sweeps in reverse: transposed solve
@@ -60,7 +62,7 @@ size_t tables_bytes(const pde_adi_desc &d) { return (size_t)kHeaderBytes + 4 * t
 
 // ------------------------------------------------------------------------------------------
 // tables: one thread per (sweep, channel, line), the whole line serially (the pivot recurrence is
-// serial anyway).  r, 1 / pivot, r / pivot, clamp mask at [s][c][i][line].
+// serial anyway).  One float4 (r, 1 / pivot, r / pivot, clamp mask) per cell at [s][c][i][line].
 // Reference arithmetic: get_alpha_beta_at_time mnist_test.py:33-42 / cifar10.py:53-63,
 // smooth_coefficients mnist_test.py:135-149, rows mnist_test.py:83-93, pivots mnist_test.py:169,177-181.
 // ------------------------------------------------------------------------------------------
@@ -77,9 +79,7 @@ __global__ void __launch_bounds__(128) gprepare_kernel(const __grid_constant__ p
     const float *base = axis ? bb : ab, *tc = axis ? btc : atc;
     const float tt = sch.t[s], dts = sch.dts[s], h2 = sch.h2[s];
     const float third = __fdiv_rn(1.0f, 3.0f);
-    const size_t T = table_elems(d);
-    float *f = reinterpret_cast<float *>(tables + kHeaderBytes);
-    float *tr = f + ((size_t)(s * C + c) * N) * N + l, *tinv = tr + T, *te = tr + 2 * T, *tm = tr + 3 * T;
+    float4 *tq = reinterpret_cast<float4 *>(tables + kHeaderBytes) + ((size_t)(s * C + c) * N) * N + l;
 
     auto coef = [&](int i, bool *inside) {
         const size_t q = axis == 0 ? ((size_t)c * N + l) * N + i : ((size_t)c * N + i) * N + l;
@@ -108,11 +108,7 @@ __global__ void __launch_bounds__(128) gprepare_kernel(const __grid_constant__ p
         const float diag = (i == 0 || i == N - 1) ? __fadd_rn(1.0f, r) : __fadd_rn(1.0f, __fmul_rn(2.0f, r));
         const float dn = i == 0 ? __fadd_rn(diag, d.eps) : __fadd_rn(__fsub_rn(diag, __fmul_rn(-r, cst)), d.eps);
         cst = __fdiv_rn(-r, dn);
-        const size_t o = (size_t)i * N;
-        tr[o] = r;
-        tinv[o] = __fdiv_rn(1.0f, dn);
-        te[o] = __fdiv_rn(r, dn);
-        tm[o] = m_cur ? 1.0f : 0.0f;
+        tq[i * N] = make_float4(r, __fdiv_rn(1.0f, dn), __fdiv_rn(r, dn), m_cur ? 1.0f : 0.0f);
         k_prev = k_cur; k_cur = k_next; m_cur = m_next;
     }
 }
@@ -125,10 +121,10 @@ struct GArgs {
     int S, sps, need_gin;
     int K;                   // samples a block works on at a time (slots)
     const Header *hdr;       // per-sweep dt / h^2 and time (the backward entry points get no schedule)
-    const float *tab;        // r | inv | e | msk, each [S][C][N][N] in line coordinates
+    const float4 *tab;       // (r, 1/pivot, r/pivot, mask) at [S][C][i][line]
     const float *u, *gout, *chan, *skipw;
     float *out, *gin;
-    float *acc;              // per slot:  [4 kinds][C][i][line]   (alpha_base, alpha_tc, beta_base, beta_tc)
+    float2 *acc;             // per slot:  [alpha | beta][C][i][line] of (base, time coefficient)
     float *hist;             // per slot:  [S][C][i][line]         output of every sweep
     float *ins;              // per slot:  [steps][C][row][col]    state at the start of every step (pre-step mix only)
     double *part_chan;       // per block: [C][C]
@@ -203,35 +199,34 @@ constexpr int kChunk = 4;   // cells whose loads are issued together, ahead of t
 // One implicit sweep of the thread's line, in place: d*_i = (d_i + r_i d*_{i-1}) / pivot_i, then
 // x_i = d*_i + (r_i / pivot_i) x_{i+1} (thomas_solver_batch, mnist_test.py:151-198).  hist != nullptr: the
 // result also goes to hist[i * N] (line coordinates, this thread's column of the slice).
-__device__ __forceinline__ void sweep_line(float *__restrict__ line, int step, int N, const float *__restrict__ tr,
-                                           const float *__restrict__ tinv, const float *__restrict__ te,
+__device__ __forceinline__ void sweep_line(float *__restrict__ line, int step, int N, const float4 *__restrict__ tq,
                                            float *__restrict__ hist) {
-    float ds = line[0] * __ldg(tinv);
+    float ds = line[0] * __ldg(&tq[0].y);
     line[0] = ds;
     for (int i0 = 1; i0 < N; i0 += kChunk) {
-        float r4[kChunk], v4[kChunk], p4[kChunk];
+        float4 q4[kChunk];
+        float p4[kChunk];
 #pragma unroll
         for (int k = 0; k < kChunk; ++k)
             if (i0 + k < N) {
-                r4[k] = __ldg(tr + (size_t)(i0 + k) * N);
-                v4[k] = __ldg(tinv + (size_t)(i0 + k) * N);
+                q4[k] = __ldg(tq + (i0 + k) * N);
                 p4[k] = line[(i0 + k) * step];
             }
 #pragma unroll
         for (int k = 0; k < kChunk; ++k)
             if (i0 + k < N) {
-                ds = fmaf(r4[k], ds, p4[k]) * v4[k];
+                ds = fmaf(q4[k].x, ds, p4[k]) * q4[k].y;
                 line[(i0 + k) * step] = ds;
             }
     }
     float x = ds;
-    if (hist) hist[(size_t)(N - 1) * N] = x;
+    if (hist) hist[(N - 1) * N] = x;
     for (int i0 = N - 2; i0 >= 0; i0 -= kChunk) {
         float e4[kChunk], p4[kChunk];
 #pragma unroll
         for (int k = 0; k < kChunk; ++k)
             if (i0 - k >= 0) {
-                e4[k] = __ldg(te + (size_t)(i0 - k) * N);
+                e4[k] = __ldg(&tq[(i0 - k) * N].z);
                 p4[k] = line[(i0 - k) * step];
             }
 #pragma unroll
@@ -239,7 +234,7 @@ __device__ __forceinline__ void sweep_line(float *__restrict__ line, int step, i
             if (i0 - k >= 0) {
                 x = fmaf(e4[k], x, p4[k]);
                 line[(i0 - k) * step] = x;
-                if (hist) hist[(size_t)(i0 - k) * N] = x;
+                if (hist) hist[(i0 - k) * N] = x;
             }
     }
 }
@@ -248,7 +243,7 @@ __device__ __forceinline__ void sweep_line(float *__restrict__ line, int step, i
 __device__ __forceinline__ void run_sample(const GArgs &a, float *tile, const Line &t, bool valid, float *hist, float *ins) {
     const pde_adi_desc &d = a.d;
     const int N = d.N, C = d.C, P = pitch_of(N);
-    const size_t NN = (size_t)N * N, T = (size_t)a.S * C * NN;
+    const size_t NN = (size_t)N * N;
     for (int step = 0; step < d.steps; ++step) {
         if (d.chan_op == 1) {
             if (valid) mix_pixels(tile, a.chan, ins ? ins + (size_t)step * C * NN : nullptr, t, C, N, P);
@@ -257,10 +252,9 @@ __device__ __forceinline__ void run_sample(const GArgs &a, float *tile, const Li
         for (int k = 0; k < a.sps; ++k) {
             const int s = step * a.sps + k, axis = sweep_axis(k);
             if (valid) {
-                const float *tr = a.tab + ((size_t)(s * C + t.c) * N) * N + t.l;
+                const float4 *tq = a.tab + ((size_t)(s * C + t.c) * N) * N + t.l;
                 float *line = tile + (size_t)t.c * N * P + (axis ? t.l : t.l * P);
-                sweep_line(line, axis ? P : 1, N, tr, tr + T, tr + 2 * T,
-                           hist ? hist + ((size_t)(s * C + t.c) * N) * N + t.l : nullptr);
+                sweep_line(line, axis ? P : 1, N, tq, hist ? hist + ((size_t)(s * C + t.c) * N) * N + t.l : nullptr);
             }
             __syncthreads();
         }
@@ -336,20 +330,20 @@ __device__ __forceinline__ void mix_pixels_adjoint(float *__restrict__ tile, con
 // Adjoint of one sweep on the thread's line, in place on g: w_i = g_i + e_{i-1} w_{i-1};
 // lambda_i = (w_i + r_{i+1} lambda_{i+1}) / pivot_i (the transposed system through the same factors), and on
 // the way down dL/dr_i = lambda_i (L x)_i with x the sweep's OUTPUT -> (smoothing^T: a window of three
-// products) -> dt / h^2 -> clamp mask -> the base and time-coefficient accumulators of this line.
-// x and the accumulators were last written by this very thread (plain loads, never the read-only path).
-__device__ __forceinline__ void reverse_line(float *__restrict__ g, int step, int N, const float *__restrict__ tr,
-                                             const float *__restrict__ tinv, const float *__restrict__ te,
-                                             const float *__restrict__ tm, const float *__restrict__ x,
-                                             float *__restrict__ acc_base, float *__restrict__ acc_tc, bool smooth,
-                                             float scale, float tt) {
+// products) -> dt / h^2 -> clamp mask = the contribution gc_i of this sweep to the line's base accumulator
+// (times the sweep's time: to its time-coefficient accumulator).
+// `x` is the thread's column of the history slice and `acc` its column of the slot's accumulators: both were last
+// written by this very thread, earlier in this kernel -- plain loads, never the read-only path (hence no
+// `const __restrict__` on x).
+__device__ __forceinline__ void reverse_line(float *__restrict__ g, int step, int N, const float4 *__restrict__ tq,
+                                             const float *x, float2 *__restrict__ acc, bool smooth, float scale, float tt) {
     float w = g[0];
     for (int i0 = 1; i0 < N; i0 += kChunk) {
         float e4[kChunk], p4[kChunk];
 #pragma unroll
         for (int k = 0; k < kChunk; ++k)
             if (i0 + k < N) {
-                e4[k] = __ldg(te + (size_t)(i0 + k - 1) * N);
+                e4[k] = __ldg(&tq[(i0 + k - 1) * N].z);
                 p4[k] = g[(i0 + k) * step];
             }
 #pragma unroll
@@ -360,46 +354,47 @@ __device__ __forceinline__ void reverse_line(float *__restrict__ g, int step, in
             }
     }
     const float wgt = smooth ? scale * (1.0f / 3.0f) : scale;
-    float lam = w * __ldg(tinv + (size_t)(N - 1) * N);
+    const float4 qn = __ldg(tq + (N - 1) * N);
+    float r_up = qn.x, m_up = qn.w;       // r and mask of cell i + 1 while the loop is at i
+    float lam = w * qn.y;
     g[(N - 1) * step] = lam;
-    float xc = x[(size_t)(N - 1) * N], xm = x[(size_t)(N - 2) * N], xp;
+    float xc = x[(N - 1) * N], xm = x[(N - 2) * N], xp;
     float gs1 = lam * (xm - xc);          // gs_{i+1} while the loop is at i
     float gs2 = gs1;                      // gs_{i+2}; at the far end the replicated term is the cell's own
     for (int i0 = N - 2; i0 >= 0; i0 -= kChunk) {
-        float r4[kChunk], v4[kChunk], p4[kChunk], x4[kChunk], m4[kChunk], b4[kChunk], t4[kChunk];
+        float4 q4[kChunk];
+        float p4[kChunk], x4[kChunk];
+        float2 a4[kChunk];
 #pragma unroll
         for (int k = 0; k < kChunk; ++k) {
             const int i = i0 - k;
             if (i >= 0) {
-                r4[k] = __ldg(tr + (size_t)(i + 1) * N);
-                v4[k] = __ldg(tinv + (size_t)i * N);
-                m4[k] = __ldg(tm + (size_t)(i + 1) * N);
+                q4[k] = __ldg(tq + i * N);
                 p4[k] = g[i * step];
-                x4[k] = i > 0 ? x[(size_t)(i - 1) * N] : 0.0f;
-                b4[k] = acc_base[(size_t)(i + 1) * N];
-                t4[k] = acc_tc[(size_t)(i + 1) * N];
+                x4[k] = i > 0 ? x[(i - 1) * N] : 0.0f;
+                a4[k] = acc[(i + 1) * N];
             }
         }
 #pragma unroll
         for (int k = 0; k < kChunk; ++k) {
             const int i = i0 - k;
             if (i >= 0) {
-                lam = fmaf(r4[k], lam, p4[k]) * v4[k];
+                lam = fmaf(r_up, lam, p4[k]) * q4[k].y;
                 g[i * step] = lam;
                 xp = xc; xc = xm; xm = x4[k];
                 const float lx = i > 0 ? (xm - xc) + (xp - xc) : xp - xc;
                 const float gs0 = lam * lx;
-                const float gc = (smooth ? (gs2 + gs1) + gs0 : gs1) * wgt * m4[k];   // cell i + 1
-                acc_base[(size_t)(i + 1) * N] = b4[k] + gc;
-                acc_tc[(size_t)(i + 1) * N] = fmaf(gc, tt, t4[k]);
+                const float gc = (smooth ? (gs2 + gs1) + gs0 : gs1) * wgt * m_up;   // cell i + 1
+                acc[(i + 1) * N] = make_float2(a4[k].x + gc, fmaf(gc, tt, a4[k].y));
                 gs2 = gs1; gs1 = gs0;
+                r_up = q4[k].x; m_up = q4[k].w;
             }
         }
     }
     // cell 0: gs_{-1} is the cell's own (replicate padding)
-    const float gc = (smooth ? (gs2 + gs1) + gs1 : gs1) * wgt * __ldg(tm);
-    acc_base[0] += gc;
-    acc_tc[0] = fmaf(gc, tt, acc_tc[0]);
+    const float gc = (smooth ? (gs2 + gs1) + gs1 : gs1) * wgt * m_up;
+    const float2 a0 = acc[0];
+    acc[0] = make_float2(a0.x + gc, fmaf(gc, tt, a0.y));
 }
 
 __device__ __forceinline__ double block_sum(double v, double *red) {
@@ -416,17 +411,17 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
 
 // (one instantiation per channel count: the C x C channel-gradient sums are per-thread doubles)
 template <int C>
-__global__ void __launch_bounds__(kMaxThreads) gbwd_kernel(const GArgs a) {
+__global__ void __maxnreg__(C <= 3 ? 128 : 168) gbwd_kernel(const GArgs a) {
     extern __shared__ __align__(16) float gsmem[];
     __shared__ double red[kMaxThreads / 32];
     const pde_adi_desc &d = a.d;
     const int N = d.N, P = pitch_of(N), NN = N * N, K = a.K;
-    const size_t CNN = (size_t)C * NN, T = (size_t)a.S * CNN;
+    const size_t CNN = (size_t)C * NN;
     const Line t = my_line(d, K);
     float *tile = gsmem + (size_t)t.slot * C * N * P;
     const float sig = d.skip ? sigmoid_of(a.skipw) : 0.0f;
     const size_t vb = (size_t)blockIdx.x * K + t.slot;       // the slot's slices of the workspace
-    float *acc = a.acc + vb * 4 * CNN;
+    float2 *acc = a.acc + vb * 2 * CNN;
     float *hist = a.hist + vb * a.S * CNN;
     float *ins = a.ins ? a.ins + vb * d.steps * CNN : nullptr;
     double gm[C * C];
@@ -434,7 +429,7 @@ __global__ void __launch_bounds__(kMaxThreads) gbwd_kernel(const GArgs a) {
     for (int q = 0; q < C * C; ++q) gm[q] = 0.0;
     double gskip = 0.0;
     if (t.active)
-        for (size_t q = t.within; q < 4 * CNN; q += t.cn) acc[q] = 0.0f;
+        for (size_t q = t.within; q < 2 * CNN; q += t.cn) acc[q] = make_float2(0.0f, 0.0f);
     __syncthreads();
 
     for (long long b0 = (long long)blockIdx.x * K; b0 < d.B; b0 += (long long)gridDim.x * K) {
@@ -467,11 +462,10 @@ __global__ void __launch_bounds__(kMaxThreads) gbwd_kernel(const GArgs a) {
                 const int s = step * a.sps + k, axis = sweep_axis(k);
                 if (valid) {
                     const size_t lo = ((size_t)t.c * N) * N + t.l;
-                    const float *tr = a.tab + (size_t)s * CNN + lo;
                     float *line = tile + (size_t)t.c * N * P + (axis ? t.l : t.l * P);
-                    float *ab = acc + (size_t)(axis ? 2 : 0) * CNN + lo;
-                    reverse_line(line, axis ? P : 1, N, tr, tr + T, tr + 2 * T, tr + 3 * T, hist + (size_t)s * CNN + lo,
-                                 ab, ab + CNN, d.smooth != 0, __ldg(&a.hdr->scale[s]), __ldg(&a.hdr->t[s]));
+                    const float scale = __ldg(&a.hdr->scale[s]), tt = __ldg(&a.hdr->t[s]);
+                    reverse_line(line, axis ? P : 1, N, a.tab + (size_t)s * CNN + lo, hist + (size_t)s * CNN + lo,
+                                 acc + (size_t)(axis ? 1 : 0) * CNN + lo, d.smooth != 0, scale, tt);
                 }
                 __syncthreads();
             }
@@ -509,31 +503,35 @@ __global__ void __launch_bounds__(kMaxThreads) gbwd_kernel(const GArgs a) {
 // coordinates ([c][col][row]) to the map's own order
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gfinish_kernel(const __grid_constant__ pde_adi_desc d, int nblk, int nslots,
-                                                      const float *__restrict__ acc, const double *__restrict__ part_chan,
+                                                      const float2 *__restrict__ acc, const double *__restrict__ part_chan,
                                                       const double *__restrict__ part_skip, const float *skipw,
                                                       float *g_ab, float *g_atc, float *g_bb, float *g_btc, float *g_chan,
                                                       float *g_skip) {
     const int N = d.N, C = d.C, NN = N * N;
     const size_t CNN = (size_t)C * NN;
     const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id < 4 * CNN) {
-        // id walks the accumulators in storage order (coalesced reads); the store is the transposed one
-        const int kind = (int)(id / CNN);
-        const size_t rem = id - (size_t)kind * CNN;
+    if (id < 2 * CNN) {
+        // id walks the accumulators in storage order (coalesced reads); the alpha stores are the transposed ones
+        const int beta = id >= CNN;
+        const size_t rem = id - (beta ? CNN : 0);
         const int c = (int)(rem / NN), i = (int)((rem % NN) / N), l = (int)(rem % N);
-        double s = 0.0;
-        for (int b = 0; b < nslots; ++b) s += (double)acc[(size_t)b * 4 * CNN + id];
-        float *out = kind == 0 ? g_ab : (kind == 1 ? g_atc : (kind == 2 ? g_bb : g_btc));
-        const size_t q = kind < 2 ? ((size_t)c * N + l) * N + i : ((size_t)c * N + i) * N + l;
-        out[q] = (float)s;
-    } else if (id < 4 * CNN + (size_t)C * C) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int b = 0; b < nslots; ++b) {
+            const float2 v = acc[(size_t)b * 2 * CNN + id];
+            s0 += (double)v.x;
+            s1 += (double)v.y;
+        }
+        const size_t q = beta ? ((size_t)c * N + i) * N + l : ((size_t)c * N + l) * N + i;
+        (beta ? g_bb : g_ab)[q] = (float)s0;
+        (beta ? g_btc : g_atc)[q] = (float)s1;
+    } else if (id < 2 * CNN + (size_t)C * C) {
         if (d.chan_op) {
-            const int q = (int)(id - 4 * CNN);
+            const int q = (int)(id - 2 * CNN);
             double s = 0.0;
             for (int b = 0; b < nblk; ++b) s += part_chan[(size_t)b * kChanSlots + q];
             g_chan[q] = (float)s;
         }
-    } else if (id == 4 * CNN + (size_t)C * C) {
+    } else if (id == 2 * CNN + (size_t)C * C) {
         if (d.skip) {
             double s = 0.0;
             for (int b = 0; b < nblk; ++b) s += part_skip[b];
@@ -622,7 +620,7 @@ int forward(const pde_adi_desc &d, const char *tables, const float *u, const flo
     a.sps = sweeps_per_step(d);
     a.S = d.steps * a.sps;
     a.hdr = reinterpret_cast<const Header *>(tables);
-    a.tab = reinterpret_cast<const float *>(tables + kHeaderBytes);
+    a.tab = reinterpret_cast<const float4 *>(tables + kHeaderBytes);
     a.u = u; a.chan = chan; a.skipw = skipw; a.out = out;
     long long grid = (long long)props.sm_count * per_sm;
     if (grid > ((long long)d.B + K - 1) / K) grid = ((long long)d.B + K - 1) / K;
@@ -645,9 +643,9 @@ int backward(const pde_adi_desc &d, const char *tables, const float *u, const fl
     a.need_gin = gin != nullptr;
     a.K = p.K;
     a.hdr = reinterpret_cast<const Header *>(tables);
-    a.tab = reinterpret_cast<const float *>(tables + kHeaderBytes);
+    a.tab = reinterpret_cast<const float4 *>(tables + kHeaderBytes);
     a.u = u; a.gout = gout; a.chan = chan; a.skipw = skipw; a.gin = gin;
-    a.acc = reinterpret_cast<float *>(w);
+    a.acc = reinterpret_cast<float2 *>(w);
     w += align256(p.acc_floats * sizeof(float));
     a.hist = reinterpret_cast<float *>(w);
     w += align256(p.hist_floats * sizeof(float));
@@ -659,7 +657,7 @@ int backward(const pde_adi_desc &d, const char *tables, const float *u, const fl
     PDE_CUDA_TRY(cudaLaunchKernel(bwd_kernel_for(d.C), dim3(p.grid), dim3(p.threads), kargs, p.smem, st));
     rc = cuda_last_error();
     if (rc) return rc;
-    const size_t outs = 4 * (size_t)d.C * d.N * d.N + (size_t)d.C * d.C + 1;
+    const size_t outs = 2 * (size_t)d.C * d.N * d.N + (size_t)d.C * d.C + 1;
     gfinish_kernel<<<(unsigned)((outs + 255) / 256), 256, 0, st>>>(d, p.grid, p.grid * p.K, a.acc, a.part_chan, a.part_skip, skipw, g_ab,
                                                                   g_atc, g_bb, g_btc, g_chan, g_skip);
     return cuda_last_error();

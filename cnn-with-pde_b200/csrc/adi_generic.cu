@@ -6,11 +6,12 @@
 // planes of one sample fit one block's shared memory -- is served here, with the plane edge a run-time
 // value:
 //
-//   * one block works on one sample at a time (all its channels: the 3x3 channel ops stay inside the
-//     block), one thread per (channel, line); the state lives in a shared-memory tile with an odd row
-//     pitch, so that walking along rows (x sweeps: lane = row) and along columns (y sweeps) are both
-//     free of bank conflicts; a sweep is two in-place passes over the thread's line (elimination, back
-//     substitution), one __syncthreads() per change of orientation;
+//   * a block works on a few samples at a time ("slots": ~256 threads; all channels of a sample stay
+//     together, so the 3x3 channel ops are block-local), one thread per (channel, line); a sample's state
+//     lives in a shared-memory tile with an odd row pitch, so that walking along rows (x sweeps: lane =
+//     row) and along columns (y sweeps) are both free of bank conflicts; a sweep is two in-place passes
+//     over the thread's line (elimination, back substitution), one __syncthreads() per change of
+//     orientation;
 //   * tables, history and gradient accumulators are all stored in LINE coordinates [c][i][line]
 //     (i = position along the sweep, line fastest): whatever the axis, consecutive threads touch
 //     consecutive addresses.  A cell's four table values travel as one float4 (r, 1/pivot, r/pivot, mask),
@@ -19,8 +20,8 @@
 //   * the backward pass keeps no checkpoints from the forward call: the block replays the sample's
 //     trajectory, parks the output of every sweep in its own slice of the workspace (the thread that
 //     writes a line is the one that reads it back), then walks the sweeps in reverse: transposed solve
-//     through the same factors, lambda . (L x), smoothing^T, clamp mask, accumulate into the block's
-//     fp32 accumulators (one slice per block, summed in double and in fixed order by gfinish_kernel).
+//     through the same factors, lambda . (L x), smoothing^T, clamp mask, accumulate into the slot's
+//     fp32 accumulators (one slice per slot, summed in double and in fixed order by gfinish_kernel).
 //
 // Same arithmetic as the whole-line kernels (fp32 FMA recurrences on 1 / pivot; the pivots themselves
 // op for op the reference's, without contraction); tests/test_gpu_parity.py::test_cuda_generic_plane_sizes.
@@ -32,7 +33,7 @@ namespace adi {
 namespace generic {
 
 constexpr int kMaxN = 128;
-constexpr int kMaxThreads = 384;   // 3 x 128 or 4 x 96 lines: leaves the backward kernel 170 registers
+constexpr int kMaxThreads = 384;   // 3 x 128 or 4 x 96 lines (x 168 registers of gbwd_kernel<4>: one block's worth)
 constexpr size_t kMaxTileBytes = 200u * 1024u;
 constexpr size_t kMaxWorkspaceBytes = (size_t)1 << 30;   // history slices: the grid shrinks to stay below it
 constexpr int kChanSlots = PDE_MAX_CHANNELS * PDE_MAX_CHANNELS;
@@ -195,6 +196,21 @@ __device__ __forceinline__ void mix_pixels(float *__restrict__ tile, const float
 }
 
 constexpr int kChunk = 4;   // cells whose loads are issued together, ahead of the dependent recurrence
+
+// L2 prefetch of a contiguous region by one thread (TMA bulk prefetch: no registers, no shared memory).  The
+// instruction wants a 16-byte aligned address and size; slices of odd planes are neither, so the region is
+// shrunk to the aligned pieces it contains, starting from the aligned address below it (still inside the
+// workspace: the history region itself starts on a 256-byte boundary).
+__device__ __forceinline__ void prefetch_slice_l2(const void *p, size_t bytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p), a0 = a & ~(uintptr_t)15;
+    const char *b = reinterpret_cast<const char *>(a0);
+    bytes = (size_t)(a + bytes - a0);
+    constexpr size_t kPiece = 16384;
+    for (size_t off = 0; off < bytes; off += kPiece) {
+        const unsigned n = (unsigned)((bytes - off < kPiece ? bytes - off : kPiece) & ~(size_t)15);
+        if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b + off), "r"(n) : "memory");
+    }
+}
 
 // One implicit sweep of the thread's line, in place: d*_i = (d_i + r_i d*_{i-1}) / pivot_i, then
 // x_i = d*_i + (r_i / pivot_i) x_{i+1} (thomas_solver_batch, mnist_test.py:151-198).  hist != nullptr: the
@@ -460,6 +476,8 @@ __global__ void __maxnreg__(C <= 3 ? 128 : 168) gbwd_kernel(const GArgs a) {
             }
             for (int k = a.sps - 1; k >= 0; --k) {
                 const int s = step * a.sps + k, axis = sweep_axis(k);
+                // the next slice to be reversed on its way from HBM into L2 (one thread per slot; -3 ... -11 % of the kernel)
+                if (valid && t.within == 0 && s > 0) prefetch_slice_l2(hist + (size_t)(s - 1) * CNN, CNN * sizeof(float));
                 if (valid) {
                     const size_t lo = ((size_t)t.c * N) * N + t.l;
                     float *line = tile + (size_t)t.c * N * P + (axis ? t.l : t.l * P);

@@ -13,7 +13,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 600 -c 9
 for spec in "fashion 262144 sfwd_kernel|sbwd_kernel" "cifar10_pde1 65536 sfwd_kernel|sbwd_kernel" "emotion 98304 emo_fwd_tiled|emo_bwd_tiled" "tiny 16384 tiny_fwd_kernel|tiny_bwd_kernel" "mnist 262144 sfwd_kernel|sbwd_kernel"; do
   set -- $spec
   python tools/prof_layer.py $1 $2 3 > gpurun_out/plain_$1.log 2>&1 || exit 1
-  ncu --set full --clock-control none --import-source on --kernel-name regex:"$3" --launch-skip 2 --launch-count 2 \
+  # (gpurun copies back at most 64 MiB: the source pages travel only with the captures whose stalls are read by line)
+  SRC=on; case $1 in mnist|tiny) SRC=off;; esac
+  ncu --set full --clock-control none --import-source $SRC --kernel-name regex:"$3" --launch-skip 2 --launch-count 2 \
       -o gpurun_out/prof_$1_${R} -f python tools/prof_layer.py $1 $2 3 > gpurun_out/ncu_$1.log 2>&1
 done
 ls -la gpurun_out/*.ncu-rep | tail -8

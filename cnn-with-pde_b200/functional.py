@@ -150,7 +150,8 @@ class _AdiPlan:
         if self.tables_bytes == 0:
             raise _cabi.PdeB200Error(
                 f"unsupported implicit-layer configuration (size={cfg.N}, channels={cfg.C}, steps={cfg.steps}); "
-                "supported: size 2 ... 128 with channels <= 4 while channels * size * (size | 1) * 4 bytes <= 200 KB, "
+                "supported: size 2 ... 128 with channels <= 4 while channels * size * (size | 1) * 4 bytes <= 200 KB "
+                "and channels * size <= 384, "
                 "at most 64 Strang / 96 Lie steps")
         self.sched = adi_schedule(cfg.steps, cfg.dt, cfg.hx, cfg.hy, cfg.lie)
         self.sref = byref(self.sched)

@@ -58,8 +58,9 @@ int pde_b200_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2
 typedef struct pde_adi_desc {
     int32_t B, C, N;          /* batch, channels (<= PDE_MAX_CHANNELS), plane edge H == W == N:
                                  2 ... 128 while C * N * (N | 1) * 4 bytes <= 200 KB (one sample's
-                                 planes in one block's shared memory); 8, 12, ... 32 have kernels
-                                 compiled for them, the rest share run-time-sized ones          */
+                                 planes in one block's shared memory) and C * N <= 384 (a thread
+                                 per line); 8, 12, ... 32 have kernels compiled for them, the
+                                 rest share run-time-sized ones                                 */
     int32_t steps;            /* num_steps                                                   */
     int32_t lie;              /* 0 Strang x(dt/2) y(dt) x(dt/2); 1 Lie x(dt/2) y(dt/2)        */
     int32_t smooth;           /* 3-tap replicate smoothing of the clamped map along the sweep */

@@ -45,7 +45,10 @@ def test_cabi_host_only_queries():
     gen = P.AdiConfig(N=30, C=3, steps=4, dt=0.3, hx=1.0, hy=1.0).desc(5)
     assert lib.pde_adi_tables_bytes(ctypes.byref(gen)) == 4096 + 4 * (12 * 3 * 30 * 30) * 4
     assert lib.pde_adi_checkpoint_bytes(ctypes.byref(gen)) == 0
-    for N, C in ((200, 1), (128, 4), (1, 1)):     # larger than a block's shared memory / not a plane
+    for N, C in ((128, 3), (96, 4), (127, 2), (2, 1)):
+        ok = P.AdiConfig(N=N, C=C, steps=2, dt=0.3, hx=1.0, hy=1.0).desc(1)
+        assert lib.pde_adi_tables_bytes(ctypes.byref(ok)) == 4096 + 4 * (6 * C * N * N) * 4, (N, C)
+    for N, C in ((200, 1), (128, 4), (100, 4), (1, 1)):     # shared memory / threads of a block exceeded; not a plane
         bad = P.AdiConfig(N=N, C=C, steps=4, dt=0.3, hx=1.0, hy=1.0).desc(1)
         assert lib.pde_adi_tables_bytes(ctypes.byref(bad)) == 0, (N, C)
     # struct layouts must match the header

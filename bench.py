@@ -48,6 +48,9 @@ LAYERS = {
     "svhn": ("svhn", dict(size=32, channels=3), 65536, 256),
     "emotion": ("emotion", dict(Nx=48, Ny=48), 98304, 64),
     "tiny": ("tiny", dict(size=64, channels=3, num_steps=1, use_implicit=False), 16384, 32),
+    # plane sizes no script uses: the run-time-sized kernels (csrc/adi_generic.cu) -- reported under other_layers
+    "mnist_48x48": ("mnist", dict(size=48), 32768, 64),
+    "svhn_64x64": ("svhn", dict(size=64, channels=3), 4096, 256),
 }
 
 

@@ -42,3 +42,14 @@ def test_reference_arm_other_ranks_exit_quietly():
     lines = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29591"},
                  "--gpus", "2")
     assert lines == []
+
+
+def test_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: without a device the timed arm must fail, not print a number."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0
+    assert not any(ln.lstrip().startswith("{") for ln in r.stdout.splitlines()), r.stdout[-500:]

@@ -85,6 +85,11 @@ GOLDEN_CASES = [
     case("emotion_pert", "emotion", B=3, **SCRIPT_INSTANCES["emotion"]),
     case("tiny_init", "tiny", B=1, perturb=False, **SCRIPT_INSTANCES["tiny"]),
     case("tiny_pert", "tiny", B=2, size=16, channels=3, num_steps=3, dt=0.02),
+    # plane sizes no script uses (csrc/adi_generic.cu): appended, the indices above are referred to elsewhere
+    case("svhn_7x7_pert", "svhn", B=2, size=7, channels=3, num_steps=2),
+    case("cifar10_c4_30x30_pert", "cifar10", B=2, size=30, channels=4, dt=0.01, num_steps=2, dx=1.0, dy=1.5),
+    case("cifar2_c2_36x36_pert", "cifar2", B=2, size=36, channels=2, dt=0.02, num_steps=3),
+    case("mnist_48x48_pert", "mnist", B=2, size=48, num_steps=2, dt=0.05),
 ]
 
 # BASELINE.json config shapes (full batch); run against the live reference / the oracle.

@@ -1,6 +1,7 @@
 """Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container).
 
-    python -m tests.golden.make_golden            # from the repo root
+    python -m tests.golden.make_golden            # from the repo root: every case
+    python -m tests.golden.make_golden NAME ...   # only the named cases (new ones: the others stay byte-identical)
 
 For every case in tests/cases.GOLDEN_CASES this imports the reference class (tests/refload.py),
 loads the case's weights, runs forward + backward on CPU in fp32 and stores inputs, weights and
@@ -29,7 +30,13 @@ def main():
     import torch
     torch.set_num_threads(1)  # fixed reduction order
     total = 0
+    only = set(sys.argv[1:])
+    unknown = only - {c.name for c in K.GOLDEN_CASES}
+    if unknown:
+        raise SystemExit(f"not in tests/cases.GOLDEN_CASES: {sorted(unknown)}")
     for c in K.GOLDEN_CASES:
+        if only and c.name not in only:
+            continue
         params = K.make_params(c)
         u, g = K.make_io(c)
         ref = runners.run_reference(c, params=params, io=(u, g))

@@ -151,6 +151,39 @@ def test_cuda_generic_plane_size_large_batch_and_inference():
         np.testing.assert_array_equal(y.cpu().numpy(), got["y"])
 
 
+def test_cuda_generic_random_configurations():
+    """Seeded sweep over what adi_generic.cu claims to serve: plane edge 2 ... 64 (any parity), one to four
+    channels, all four layer variants, zero to three steps, batches from one sample to more than a block's
+    slots, with and without grad_input."""
+    rs = np.random.RandomState(20261019)
+    specialised = {8, 12, 16, 20, 24, 28, 32}
+    done = 0
+    while done < 40:
+        size = int(rs.randint(2, 65))
+        if size in specialised:
+            continue
+        kind = ["mnist", "svhn", "cifar10", "cifar2"][rs.randint(4)]
+        steps, B = int(rs.randint(0, 4)), int(rs.choice([1, 2, 3, 5, 9, 17]))
+        if kind == "mnist":
+            ctor = dict(size=size, num_steps=steps, dt=float(rs.choice([0.01, 0.05, 0.3])), dx=float(rs.choice([0.7, 1.0])),
+                        dy=float(rs.choice([1.0, 1.3])))
+        elif kind == "svhn":
+            ctor = dict(size=size, channels=int(rs.randint(1, 5)), num_steps=steps, dt=float(rs.choice([0.01, 0.05])))
+        else:
+            ctor = dict(size=size, channels=int(rs.randint(1, 5)), num_steps=steps, dt=float(rs.choice([0.001, 0.02])),
+                        dx=float(rs.choice([1.0, 2.0])), dy=float(rs.choice([1.0, 1.5])))
+        need_gin = bool(rs.randint(2))
+        c = K.case(f"grand_{done}_{kind}_{size}", kind, B=B, seed=int(rs.randint(1 << 20)), **ctor)
+        params, io = K.make_params(c), K.make_io(c)
+        got = runners.run_cuda(c, params=params, io=io, need_gin=need_gin)
+        want = runners.run_oracle(c, params=params, io=io, dtype=np.float32, need_gin=need_gin)
+        if not need_gin:
+            assert got["gin"] is None
+            got, want = ({k: v for k, v in d.items() if k != "gin"} for d in (got, want))
+        _assert_close(got, want, TOL, f"{c.name} {ctor} B={B} gin={need_gin}")
+        done += 1
+
+
 @pytest.mark.parametrize("size", [8, 12, 16, 20, 24])
 def test_cuda_other_plane_sizes(size):
     """The reference classes take any `size`; the whole-line kernels are built for every multiple of 4 up to

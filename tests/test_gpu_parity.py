@@ -233,6 +233,31 @@ def test_cuda_compiled_sizes_random_configurations(monkeypatch):
                                          f"{c.name} {ctor} B={B} gin={need_gin} whole-line={whole}")
 
 
+def test_cuda_explicit_layers_random_configurations():
+    """Seeded sweep over the two explicit layers: emotion with any plane edge up to 64 (16 / 32 / 48 take the
+    register-tiled kernels, the rest the shared-memory ones) and 1 ... 12 steps; tiny with every edge that is a
+    multiple of 4 up to 64, one to four channels, one to three steps; ragged batches, grad_input on / off."""
+    rs = np.random.RandomState(104729)
+    for done in range(30):
+        need_gin = bool(rs.randint(2))
+        B = int(rs.choice([1, 2, 3, 5, 9, 17, 33]))
+        if rs.randint(2):
+            n = int(rs.choice([16, 32, 48])) if rs.randint(3) == 0 else int(rs.randint(4, 65))
+            ctor = dict(Nx=n, Ny=n, T=float(rs.choice([0.001, 0.003, 0.005, 0.01, 0.012])))
+            c = K.case(f"erand_{done}_emotion_{n}", "emotion", B=B, seed=int(rs.randint(1 << 20)), **ctor)
+        else:
+            n = 4 * int(rs.randint(2, 17))
+            ctor = dict(size=n, channels=int(rs.randint(1, 5)), num_steps=int(rs.randint(1, 4)), dt=float(rs.choice([0.01, 0.02])))
+            c = K.case(f"erand_{done}_tiny_{n}", "tiny", B=B, seed=int(rs.randint(1 << 20)), **ctor)
+        params, io = K.make_params(c), K.make_io(c)
+        got = runners.run_cuda(c, params=params, io=io, need_gin=need_gin)
+        want = runners.run_oracle(c, params=params, io=io, dtype=np.float32, need_gin=need_gin)
+        if not need_gin:
+            assert got["gin"] is None
+            got, want = ({k: v for k, v in d.items() if k != "gin"} for d in (got, want))
+        _assert_close_or_as_good_as_fp32(c, got, want, params, io, need_gin, f"{c.name} {ctor} B={B} gin={need_gin}")
+
+
 @pytest.mark.parametrize("size", [8, 12, 16, 20, 24])
 def test_cuda_other_plane_sizes(size):
     """The reference classes take any `size`; the whole-line kernels are built for every multiple of 4 up to
